@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: GNN propagation -> gather -> MLP -> sigmoid (-> catalog top-k).
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (B200)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU restatement of the reference path
+
+A step = one pass of the hot path over one batch: the model call the reference makes per
+batch (/root/reference/src/models/basic.py:61-63: full-graph propagation, embedding lookup,
+BasicRS MLP, sigmoid).  Headline metric (BASELINE.json): propagation edges/s, i.e.
+K_layers * nnz(A_hat) / step time, whole job; scored pairs/s for full-catalog top-k is
+measured in the same run and reported under "pairs".
+
+Workload at every N: config 5 of BASELINE.json, the scaled synthetic bipartite graph
+(10M users x 1M items x 1e9 edges, dim 128, 3 GCN layers, fp32) - it fits one B200 - so the
+graph is fixed and N GPUs split its rows ("scaling": "strong").  Inputs are larger than L2
+(5.6 GB of features per layer), so no L2 flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+SCALES = {  # name: users, items, undirected edges
+    "c5": (10_000_000, 1_000_000, 1_000_000_000),
+    "c5-tenth": (1_000_000, 100_000, 100_000_000),
+    "c5-hundredth": (100_000, 10_000, 10_000_000),
+}
+DIM, LAYERS = 128, 3
+DENSE_UNITS, CLF_UNITS = [48, 48], [64, 64]  # econfigs/basic-gnn.yaml grid2 scorer
+PAIR_BATCH = 65536
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", default=os.environ.get("CBRS_BENCH_SCALE", "c5"), choices=sorted(SCALES))
+    ap.add_argument("--cpu-scale", default="c5-hundredth", choices=sorted(SCALES))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--catalog-users", type=int, default=2048)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(scale, steps, warmup, threads):
+    """K-layer GCN forward + BasicRS scoring of one batch on the host cores with the oracle
+    (torch-CPU twin, all threads): the CPU restatement of the reference path."""
+    import torch
+    from oracle import synth as osynth
+    from oracle import torch_cpu as oc
+    torch.set_num_threads(threads)
+    n_users, n_items, n_edges = SCALES[scale]
+    row, col = osynth.synth_bipartite(n_users, n_items, n_edges, 42)
+    a_hat, nnz = oc.gcn_filter_torch(row, col, n_users + n_items)
+    rng = np.random.RandomState(0)
+    n = n_users + n_items
+    emb = torch.from_numpy((rng.standard_normal((n, DIM)) * 0.02).astype(np.float32))
+    layers = [(torch.from_numpy(oc.glorot(rng, (DIM, DIM))), torch.zeros(DIM)) for _ in range(LAYERS)]
+    mlp = oc.random_basic_rs(rng, DIM * (LAYERS + 1), DENSE_UNITS, CLF_UNITS)
+    u = torch.from_numpy(rng.randint(0, n_users, size=PAIR_BATCH))
+    i = torch.from_numpy(rng.randint(0, n_items, size=PAIR_BATCH) + n_users)
+
+    def step():
+        x = oc.gcn_forward(emb, a_hat, layers)
+        return oc.basic_rs(x, u, i, mlp)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(edges_per_s=LAYERS * nnz / dt, ms_per_step=dt * 1e3, nnz=nnz,
+                sample="GCN %d layers dim %d on the %s graph (%d users x %d items, nnz(A_hat)=%d) + %d scored pairs per step"
+                       % (LAYERS, DIM, scale, n_users, n_items, nnz, PAIR_BATCH))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    r = cpu_reference_run(args.cpu_scale, args.steps, args.warmup, threads)
+    n_users, n_items, n_edges = SCALES[args.scale]
+    line = {
+        "impl": "reference", "metric": "propagation_edges_per_s", "value": r["edges_per_s"], "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.scale, args.gpus),
+        "cpu_baseline": {"value": r["edges_per_s"], "unit": "edges/s", "cores": threads, "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["edges_per_s"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "TensorFlow/Spektral cannot be installed here; this is the CPU restatement (oracle, torch-CPU, "
+                "all host threads) on a bounded sample of the workload; the rate is per edge.",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(scale, gpus):
+    n_users, n_items, n_edges = SCALES[scale]
+    return {"workload": "%s scaled synthetic bipartite graph, BasicGCN %d layers dim %d fp32, concatenation, "
+                        "BasicRS %s/%s, %d scored pairs per step" % (scale, LAYERS, DIM, DENSE_UNITS, CLF_UNITS, PAIR_BATCH),
+            "users": n_users, "items": n_items, "undirected_edges": n_edges, "dim": DIM, "layers": LAYERS,
+            "parallelism": "rows x%d" % gpus if gpus > 1 else "single",
+            "l2": "inputs larger than L2 (no flush needed)"}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in rows)]
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                    "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+        except Exception as e:  # pragma: no cover
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["parse error: %s" % e]}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from deep_cbrs_amar_renaissance_b200 import _lib as L
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from deep_cbrs_amar_renaissance_b200.distributed import RowPartition
+    from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
+    from deep_cbrs_amar_renaissance_b200.keras_like import set_seed
+    from deep_cbrs_amar_renaissance_b200.models import basic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    ops.check_device()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+
+    n_users, n_items, n_edges = SCALES[args.scale]
+    n = n_users + n_items
+    t_build0 = time.perf_counter()
+    row, col = ops.synth_bipartite(n_users, n_items, n_edges, 42, dev)
+    graph = DeviceGraph(row, col, None, n)
+    del row, col
+    set_seed(42)
+    model = basic.BasicGCN(graph, n_hiddens=[DIM] * LAYERS, embedding_dim=DIM, dense_units=DENSE_UNITS,
+                           clf_units=CLF_UNITS, final_node="concatenation")
+    seq = model.gnn.gnn_layers
+    nnz_total = graph.norm.nnz  # builds the normalised CSR on device
+    heavy = graph.norm.chunks["n_heavy"]
+    part = None
+    if world > 1:
+        part = RowPartition([n_users, n_items], final_types=[1]).attach(seq)
+        part.csr_slices("norm", graph)
+        part.release_full_views(graph)
+    else:
+        graph.release_coo()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    build_s = time.perf_counter() - t_build0
+
+    # the batch: pairs whose users this rank owns (scoring is sharded by user)
+    rng = np.random.RandomState(1234 + rank)
+    if part is not None:
+        u_lo, u_hi = part.ranges[rank][0]
+    else:
+        u_lo, u_hi = 0, n_users
+    u_host = torch.from_numpy(rng.randint(u_lo, max(u_hi, u_lo + 1), size=PAIR_BATCH)).pin_memory()
+    i_host = torch.from_numpy(rng.randint(0, n_items, size=PAIR_BATCH) + n_users).pin_memory()
+    u_dev, i_dev = u_host.to(dev), i_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), t0, t1
+
+    # ---- device-resident timing (value) -------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    ops.PROFILE.clear()
+    ops.PROFILE_ON = False
+    ops.LAUNCHES = 0
+    for _ in range(args.warmup):
+        model((u_dev, i_dev))
+    barrier()
+    ops.PROFILE_ON = True
+    ops.LAUNCHES = 0
+    ms, t0, t1 = timed(lambda: model((u_dev, i_dev)), args.steps, 0)
+    launches = ops.LAUNCHES
+    ops.PROFILE_ON = False
+    clocks = sampler.stop(t0, t1) if sampler else None
+    spmm_ms = [a.elapsed_time(b) for (name, a, b, _) in ops.PROFILE if name == "spmm"]
+    spmm_edges = [meta for (name, _, _, meta) in ops.PROFILE if name == "spmm"]
+    ms_per_step = ms / args.steps
+    value = LAYERS * nnz_total / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public model call with HOST buffers (e2e) --------------------
+    def e2e_step():
+        out = model((u_host, i_host))       # H2D of the id vectors inside
+        return out.cpu()                    # D2H of the scores
+    ms_e2e, _, _ = timed(e2e_step, args.steps, 1)
+    e2e_value = LAYERS * nnz_total / (ms_e2e / args.steps * 1e-3)
+
+    # ---- roofline of the dominant kernel (SpMM) -------------------------------------------
+    local_nnz = sum(spmm_edges) / max(len(spmm_edges), 1)
+    rows_local = sum(b - a for a, b in part.mine) if part is not None else n
+    calls_per_layer = len(part.mine) if part is not None else 1
+    # algorithmic bytes of one SpMM launch: nnz*(4 col + 4 val + D*4 row) + rows*(D*4 out + 8 rowptr)
+    avg_ms = float(np.mean(spmm_ms)) if spmm_ms else float("nan")
+    alg_bytes = local_nnz * (8 + DIM * 4) + (rows_local / calls_per_layer) * (DIM * 4 + 8)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "spmm_chunk_kernel<32,4> (+heavy-row merge)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_per_edge": 8 + DIM * 4, "launches_timed": len(spmm_ms),
+                "share_of_step": (sum(spmm_ms) / args.steps) / ms_per_step if spmm_ms else None}
+
+    # ---- full-catalog scoring + top-10 for a block of this rank's users --------------------
+    model.cache_propagation = True
+    model.propagate()
+    cu = min(args.catalog_users, u_hi - u_lo)
+    users = torch.arange(u_lo, u_lo + cu, device=dev)
+    cat_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users), 1, 1)
+    pairs_per_s = world * cu * n_items / (cat_ms * 1e-3)
+    model.cache_propagation = False
+    model.invalidate()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "propagation_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.scale, world),
+        "edges_per_s_per_gpu": value / world, "nnz_a_hat": nnz_total, "heavy_rows": heavy,
+        "graph_build_s": build_s, "gpu_launches": launches, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": 2 * PAIR_BATCH * 8,
+                "d2h_bytes_per_step": PAIR_BATCH * 4, "ms_per_step": ms_e2e / args.steps},
+        "roofline": roofline,
+        "pairs": {"value": pairs_per_s, "unit": "pairs/s", "what": "full-catalog BasicRS scoring + top-10, %d users x %d items per rank" % (cu, n_items),
+                  "ms": cat_ms},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        r = cpu_reference_run(args.cpu_scale, 2, 1, threads)
+        line["cpu_baseline"] = {"value": r["edges_per_s"], "unit": "edges/s", "cores": threads, "kind": "port",
+                                "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,232 @@
+// CSR x dense propagation kernels for sm_100a: weighted SpMM (GCN / LightGCN),
+// sum and mean aggregators (GraphSAGE).  Rows P1, P2 (aggregate), P4.
+//
+// Replaces tf.sparse.sparse_dense_matmul reached through spektral GCNConv and
+// ops.modal_dot (/root/reference/src/layers/lightgcn_conv.py:53) and the
+// gather + unsorted_segment_mean of GraphSageConv (built at src/models/gnn.py:354-361).
+//
+// HBM-bound gather: per edge 8 B of (col,val) stream + one D*4-byte feature row.
+//  * G lanes own one chunk of a row; lane l holds 4 consecutive floats (one
+//    128-bit load per edge per lane), so a 128-wide row is one 512-B warp request;
+//  * (col,val) are fetched G at a time, coalesced, L1::no_allocate, and handed
+//    round with shuffles; 8 independent row loads are in flight per group;
+//  * accumulation order inside a chunk is ascending column == the oracle's;
+//  * rows longer than chunk_edges are split: each chunk parks a partial and a
+//    second kernel adds the partials in ascending chunk order (fixed tree).
+#include "common.cuh"
+
+namespace cbrs {
+
+struct SpmmParams {
+    const int64_t *rowptr;
+    const int32_t *colidx;
+    const float *vals;
+    const int32_t *chunk_row;
+    const int64_t *chunk_begin;
+    const int32_t *chunk_slot;
+    int64_t n_chunks;
+    int32_t chunk_edges;
+    const float *x;
+    int64_t ldx;
+    float *y;
+    int64_t ldy;
+    int32_t d;
+    int agg;
+    const float *bias;
+    int relu;
+    float *partial;  // [n_slots, d]
+    const int32_t *heavy_row;
+    const int64_t *heavy_slot_ptr;
+    int64_t n_heavy;
+};
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+    float4 v;
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void load(const float *p) { v = ldg4(p); }
+    __device__ __forceinline__ void load_plain(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
+    __device__ __forceinline__ void fma(float a, const Vec &x) {
+        v.x = fmaf(a, x.v.x, v.x); v.y = fmaf(a, x.v.y, v.y); v.z = fmaf(a, x.v.z, v.z); v.w = fmaf(a, x.v.w, v.w);
+    }
+    __device__ __forceinline__ void add(const Vec &x) { v.x += x.v.x; v.y += x.v.y; v.z += x.v.z; v.w += x.v.w; }
+    __device__ __forceinline__ void div(float c) { v.x /= c; v.y /= c; v.z /= c; v.w /= c; }
+    __device__ __forceinline__ void epilogue(const float *bias, int relu) {
+        if (bias) { float4 b = ldg4(bias); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    }
+    __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+};
+template <>
+struct Vec<1> {
+    float v;
+    __device__ __forceinline__ void zero() { v = 0.f; }
+    __device__ __forceinline__ void load(const float *p) { v = __ldg(p); }
+    __device__ __forceinline__ void load_plain(const float *p) { v = *p; }
+    __device__ __forceinline__ void fma(float a, const Vec &x) { v = fmaf(a, x.v, v); }
+    __device__ __forceinline__ void add(const Vec &x) { v += x.v; }
+    __device__ __forceinline__ void div(float c) { v /= c; }
+    __device__ __forceinline__ void epilogue(const float *bias, int relu) {
+        if (bias) v += __ldg(bias);
+        if (relu) v = fmaxf(v, 0.f);
+    }
+    __device__ __forceinline__ void store(float *p) const { *p = v; }
+};
+
+constexpr int kSpmmThreads = 256;
+
+template <int G, int VEC>
+__global__ void __launch_bounds__(kSpmmThreads) spmm_chunk_kernel(const SpmmParams p) {
+    constexpr int U = G < 8 ? G : 8;  // independent row loads in flight per group
+    const int64_t gid = ((int64_t)blockIdx.x * kSpmmThreads + threadIdx.x) / G;
+    if (gid >= p.n_chunks) return;
+    const int lane = threadIdx.x & 31;
+    const int lg = lane & (G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+
+    const int32_t row = p.chunk_row[gid];
+    const int64_t row_b = p.rowptr[row], row_e = p.rowptr[row + 1];
+    const int64_t b = p.chunk_begin[gid];
+    const int64_t e = (b + p.chunk_edges < row_e) ? b + p.chunk_edges : row_e;
+    const int32_t slot = p.chunk_slot[gid];
+    const bool weighted = (p.agg == CBRS_AGG_WEIGHTED) && p.vals != nullptr;
+
+    for (int c0 = 0; c0 < p.d; c0 += G * VEC) {
+        const int col = c0 + lg * VEC;
+        const bool col_ok = col < p.d;
+        const float *xcol = p.x + (col_ok ? col : 0);
+        Vec<VEC> acc;
+        acc.zero();
+        for (int64_t base = b; base < e; base += G) {
+            const int64_t idx = base + lg;
+            int c = 0;
+            float v = 0.f;
+            if (idx < e) {
+                c = ld_stream_i32(p.colidx + idx);
+                v = weighted ? ld_stream_f32(p.vals + idx) : 1.f;
+            }
+            const int cnt = (e - base < G) ? (int)(e - base) : G;
+#pragma unroll
+            for (int k0 = 0; k0 < G; k0 += U) {
+                if (k0 >= cnt) break;
+                int cc[U];
+                float vv[U];
+                Vec<VEC> xr[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    cc[u] = __shfl_sync(gmask, c, k0 + u, G);
+                    vv[u] = __shfl_sync(gmask, v, k0 + u, G);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (col_ok && k0 + u < cnt) xr[u].load(xcol + (int64_t)cc[u] * p.ldx);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (col_ok && k0 + u < cnt) acc.fma(vv[u], xr[u]);
+            }
+        }
+        if (!col_ok) continue;
+        if (slot >= 0) {
+            acc.store(p.partial + (int64_t)slot * p.d + col);
+        } else {
+            if (p.agg == CBRS_AGG_MEAN) {
+                const int64_t cnt_row = row_e - row_b;
+                if (cnt_row > 0) acc.div((float)cnt_row);
+            }
+            acc.epilogue(p.bias ? p.bias + col : nullptr, p.relu);
+            acc.store(p.y + (int64_t)row * p.ldy + col);
+        }
+    }
+}
+
+// heavy rows: add the parked partials in ascending chunk order, then the epilogue
+template <int G, int VEC>
+__global__ void __launch_bounds__(kSpmmThreads) spmm_heavy_kernel(const SpmmParams p) {
+    const int64_t gid = ((int64_t)blockIdx.x * kSpmmThreads + threadIdx.x) / G;
+    if (gid >= p.n_heavy) return;
+    const int lg = threadIdx.x & (G - 1);
+    const int32_t row = p.heavy_row[gid];
+    const int64_t s0 = p.heavy_slot_ptr[gid], s1 = p.heavy_slot_ptr[gid + 1];
+    for (int c0 = 0; c0 < p.d; c0 += G * VEC) {
+        const int col = c0 + lg * VEC;
+        if (col >= p.d) continue;
+        Vec<VEC> acc;
+        acc.zero();
+        for (int64_t s = s0; s < s1; ++s) {
+            Vec<VEC> t;
+            t.load_plain(p.partial + s * p.d + col);
+            acc.add(t);
+        }
+        if (p.agg == CBRS_AGG_MEAN) {
+            const int64_t cnt_row = p.rowptr[row + 1] - p.rowptr[row];
+            if (cnt_row > 0) acc.div((float)cnt_row);
+        }
+        acc.epilogue(p.bias ? p.bias + col : nullptr, p.relu);
+        acc.store(p.y + (int64_t)row * p.ldy + col);
+    }
+}
+
+template <int G, int VEC>
+static int launch(const SpmmParams &p, cudaStream_t s) {
+    const int64_t threads = p.n_chunks * G;
+    if (threads > 0) {
+        spmm_chunk_kernel<G, VEC><<<(unsigned)cdiv(threads, kSpmmThreads), kSpmmThreads, 0, s>>>(p);
+        CBRS_CHECK_LAUNCH("spmm_chunk");
+    }
+    if (p.n_heavy > 0) {
+        spmm_heavy_kernel<G, VEC><<<(unsigned)cdiv(p.n_heavy * G, kSpmmThreads), kSpmmThreads, 0, s>>>(p);
+        CBRS_CHECK_LAUNCH("spmm_heavy");
+    }
+    return CBRS_OK;
+}
+
+template <int VEC>
+static int dispatch_g(int lanes_needed, const SpmmParams &p, cudaStream_t s) {
+    if (lanes_needed <= 1) return launch<1, VEC>(p, s);
+    if (lanes_needed <= 2) return launch<2, VEC>(p, s);
+    if (lanes_needed <= 4) return launch<4, VEC>(p, s);
+    if (lanes_needed <= 8) return launch<8, VEC>(p, s);
+    if (lanes_needed <= 16) return launch<16, VEC>(p, s);
+    return launch<32, VEC>(p, s);
+}
+
+}  // namespace cbrs
+
+using namespace cbrs;
+
+extern "C" size_t cbrs_spmm_workspace_bytes(const cbrs_csr_t *g, int32_t d) {
+    if (!g) return 0;
+    return align_up((size_t)g->n_slots * (size_t)d * sizeof(float)) + 256;
+}
+
+extern "C" int cbrs_spmm_csr(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d, int agg,
+                             const float *bias, int relu, int dtype, void *workspace, size_t workspace_bytes,
+                             void *stream) {
+    CBRS_REQUIRE(g && x && y, CBRS_E_INVALID, "spmm: null argument");
+    CBRS_REQUIRE(dtype == CBRS_DTYPE_F32, CBRS_E_UNSUPPORTED, "spmm: only float32 features are built in this round");
+    CBRS_REQUIRE(d > 0 && ldx >= d && ldy >= d, CBRS_E_INVALID, "spmm: d=%d ldx=%lld ldy=%lld", d, (long long)ldx,
+                 (long long)ldy);
+    CBRS_REQUIRE(agg >= CBRS_AGG_WEIGHTED && agg <= CBRS_AGG_MEAN, CBRS_E_INVALID, "spmm: agg=%d", agg);
+    CBRS_REQUIRE(g->n_rows >= 0 && g->n_chunks >= 0 && g->chunk_edges > 0, CBRS_E_INVALID, "spmm: bad graph descriptor");
+    if (g->n_rows == 0) return CBRS_OK;
+    CBRS_REQUIRE(g->rowptr && g->chunk_row && g->chunk_begin && g->chunk_slot && (g->nnz == 0 || g->colidx),
+                 CBRS_E_INVALID, "spmm: graph descriptor has null arrays");
+    CBRS_REQUIRE(g->n_heavy == 0 || (g->heavy_row && g->heavy_slot_ptr), CBRS_E_INVALID, "spmm: heavy list missing");
+    const size_t need = (size_t)g->n_slots * (size_t)d * sizeof(float);
+    CBRS_REQUIRE(g->n_slots == 0 || (workspace && workspace_bytes >= need), CBRS_E_WORKSPACE,
+                 "spmm: workspace %zu < %zu bytes", workspace_bytes, need);
+    SpmmParams p;
+    p.rowptr = g->rowptr; p.colidx = g->colidx; p.vals = g->vals;
+    p.chunk_row = g->chunk_row; p.chunk_begin = g->chunk_begin; p.chunk_slot = g->chunk_slot;
+    p.n_chunks = g->n_chunks; p.chunk_edges = g->chunk_edges;
+    p.x = (const float *)x; p.ldx = ldx; p.y = (float *)y; p.ldy = ldy; p.d = d; p.agg = agg;
+    p.bias = bias; p.relu = relu; p.partial = (float *)workspace;
+    p.heavy_row = g->heavy_row; p.heavy_slot_ptr = g->heavy_slot_ptr; p.n_heavy = g->n_heavy;
+    const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
+                      ((uintptr_t)y % 16 == 0) && ((uintptr_t)workspace % 16 == 0) &&
+                      (!bias || (uintptr_t)bias % 16 == 0);
+    cudaStream_t s = (cudaStream_t)stream;
+    return vec4 ? dispatch_g<4>(d / 4, p, s) : dispatch_g<1>(d, p, s);
+}

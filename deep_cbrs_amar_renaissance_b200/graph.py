@@ -1,0 +1,98 @@
+"""Device-resident graph: the adjacency the reference hands to its layers as a
+tf.SparseTensor (/root/reference/src/models/gnn.py:49, src/utilities/math.py:37-56),
+kept in HBM as CSR + a chunk decomposition.
+
+Two views are built on demand from the same COO entries:
+  * norm: duplicates summed, self loops added, D^-1/2 (A+I) D^-1/2  -> GCN, LightGCN
+          (what GCNConv.preprocess / LightGCNConv.preprocess return, gnn.py:283,380)
+  * raw : row-major sorted, duplicates kept, values ignored          -> GraphSAGE, GAT
+          (gnn.py:298-319,331-352 pass the adjacency through untouched)
+"""
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import ops
+
+DEFAULT_CHUNK_EDGES = 1024
+
+
+class CsrSlice:
+    """Rows [row_offset, row_offset + n_rows) of a CSR matrix plus its work decomposition."""
+
+    def __init__(self, rowptr, colidx, vals, n_cols, chunk_edges=DEFAULT_CHUNK_EDGES, row_offset=0):
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.n_rows = rowptr.numel() - 1
+        self.n_cols = n_cols
+        self.nnz = colidx.numel()
+        self.row_offset = row_offset
+        self.chunk_edges = chunk_edges
+        self.chunks = ops.build_chunks(rowptr, chunk_edges)
+        c = self.chunks
+        d = L.CsrDesc()
+        d.n_rows, d.nnz = self.n_rows, self.nnz
+        d.rowptr, d.colidx = rowptr.data_ptr(), colidx.data_ptr()
+        d.vals = vals.data_ptr() if vals is not None else None
+        d.chunk_edges, d.n_chunks = chunk_edges, c["n_chunks"]
+        d.chunk_row, d.chunk_begin, d.chunk_slot = (c["chunk_row"].data_ptr(), c["chunk_begin"].data_ptr(),
+                                                    c["chunk_slot"].data_ptr())
+        d.n_heavy, d.n_slots = c["n_heavy"], c["n_slots"]
+        d.heavy_row = c["heavy_row"].data_ptr() if c["n_heavy"] else None
+        d.heavy_slot_ptr = c["heavy_slot_ptr"].data_ptr()
+        self.desc = d
+
+    def row_slice(self, r0, r1, chunk_edges=None):
+        """Rows [r0, r1) with global column ids (1-D row partition)."""
+        b, e = int(self.rowptr[r0].item()), int(self.rowptr[r1].item())
+        rowptr = (self.rowptr[r0:r1 + 1] - b).contiguous()
+        vals = self.vals[b:e].contiguous() if self.vals is not None else None
+        return CsrSlice(rowptr, self.colidx[b:e].contiguous(), vals, self.n_cols,
+                        chunk_edges or self.chunk_edges, self.row_offset + r0)
+
+    def to_scipy(self):
+        from scipy import sparse
+        vals = (self.vals if self.vals is not None else torch.ones_like(self.colidx, dtype=torch.float32)).cpu().numpy()
+        return sparse.csr_matrix((vals, self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
+                                 shape=(self.n_rows, self.n_cols))
+
+
+class DeviceGraph:
+    def __init__(self, row, col, val, n_nodes, chunk_edges=DEFAULT_CHUNK_EDGES, rel=None, n_rel=1):
+        ops.check_device()
+        self.row, self.col, self.val, self.rel = row, col, val, rel
+        self.n_nodes, self.n_rel = int(n_nodes), int(n_rel)
+        self.chunk_edges = chunk_edges
+        self.shape = (self.n_nodes, self.n_nodes)
+        self._views = {}
+
+    @classmethod
+    def from_scipy(cls, adj, device=None, chunk_edges=DEFAULT_CHUNK_EDGES):
+        """scipy sparse (any format; COO entry order is preserved) -> device COO."""
+        if isinstance(adj, DeviceGraph):
+            return adj
+        device = torch.device(device or "cuda")
+        coo = adj.tocoo()
+        row = torch.from_numpy(np.ascontiguousarray(coo.row, dtype=np.int32)).to(device)
+        col = torch.from_numpy(np.ascontiguousarray(coo.col, dtype=np.int32)).to(device)
+        val = torch.from_numpy(np.ascontiguousarray(coo.data, dtype=np.float32)).to(device)
+        return cls(row, col, val, coo.shape[0], chunk_edges)
+
+    def _view(self, name, flags, keep_vals, self_rel=0):
+        if name not in self._views:
+            rowptr, colidx, vals = ops.graph_build_csr(self.row, self.col, self.val, self.n_nodes, flags,
+                                                       rel=self.rel, n_rel=self.n_rel, self_rel=self_rel)
+            self._views[name] = CsrSlice(rowptr, colidx.contiguous(), vals.contiguous() if keep_vals else None,
+                                         self.n_nodes * self.n_rel, self.chunk_edges)
+        return self._views[name]
+
+    def release_coo(self):
+        """Drop the COO entries once the needed views exist (frees 12 B per entry)."""
+        self.row = self.col = self.val = self.rel = None
+
+    @property
+    def norm(self):
+        return self._view("norm", L.GRAPH_DEDUP_SUM | L.GRAPH_ADD_SELF_LOOPS | L.GRAPH_SYM_NORM, True)
+
+    @property
+    def raw(self):
+        return self._view("raw", 0, False)

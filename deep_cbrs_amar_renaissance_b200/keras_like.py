@@ -1,0 +1,185 @@
+"""The slice of the Keras Layer/Model surface the reference's caller uses
+(/root/reference/src/experiment.py:136-197, src/utilities/keras.py:10-22):
+add_weight, lazy build, trainable_weights, get/set_weights, compile, __call__,
+summary, evaluate, predict.  Weights are float32 CUDA tensors; initialisers follow
+Keras (glorot_uniform / zeros / ones) and are drawn on the host from one seeded
+generator so a run is reproducible across devices.
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+_GEN = torch.Generator(device="cpu")
+_GEN.manual_seed(42)
+
+
+def set_seed(seed):
+    """Counterpart of tf.random.set_seed (experiment.py:56)."""
+    _GEN.manual_seed(int(seed))
+
+
+def default_device():
+    """CUDA device of this process.  Without CUDA, weights can still be CREATED on the host
+    (shape / parameter-count logic); every op refuses non-CUDA tensors, so nothing computes."""
+    if not torch.cuda.is_available():
+        return torch.device("cpu")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _init(shape, initializer):
+    shape = tuple(int(s) for s in shape)
+    if initializer == "zeros":
+        return torch.zeros(shape, dtype=torch.float32)
+    if initializer == "ones":
+        return torch.ones(shape, dtype=torch.float32)
+    if initializer == "glorot_uniform":
+        # Keras: fan_in = shape[-2] * receptive field, fan_out = shape[-1] * receptive field
+        if len(shape) == 1:
+            fan_in = fan_out = shape[0]
+        else:
+            rf = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+            fan_in, fan_out = shape[-2] * rf, shape[-1] * rf
+        limit = math.sqrt(6.0 / (fan_in + fan_out))
+        return (torch.rand(shape, generator=_GEN, dtype=torch.float32) * 2.0 - 1.0) * limit
+    raise ValueError("initializer not supported: {}".format(initializer))
+
+
+class L2:
+    """regularizers.l2(l): penalty l * sum(w^2) (src/models/gnn.py:239-246)."""
+
+    def __init__(self, l2):
+        self.l2 = float(l2)
+
+
+class Layer:
+    def __init__(self, name=None):
+        self.name = name or type(self).__name__.lower()
+        self._weights = OrderedDict()
+        self._regularizers = {}
+        self.built = False
+
+    # -- weights ---------------------------------------------------------
+    def add_weight(self, name, shape, initializer="glorot_uniform", regularizer=None, trainable=True):
+        dev = default_device()
+        if initializer == "glorot_uniform" and int(np.prod(shape)) > (1 << 24) and dev.type == "cuda":
+            # large tables (scaled graphs): draw on the device from a generator seeded by the host one
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,), generator=_GEN).item()))
+            limit = math.sqrt(6.0 / (int(shape[-2]) + int(shape[-1])))
+            w = torch.rand(tuple(int(v) for v in shape), generator=gen, dtype=torch.float32, device=dev)
+            w.mul_(2.0 * limit).sub_(limit)
+        else:
+            w = _init(shape, initializer).to(dev)
+        w.trainable = trainable
+        self._weights[name] = w
+        if regularizer is not None:
+            self._regularizers[name] = regularizer
+        return w
+
+    def _sublayers(self):
+        """(attribute path, layer) of every directly owned sub-layer, in attribute order."""
+        out, seen = [], []
+        for attr, v in self.__dict__.items():
+            items = [(attr, v)] if not isinstance(v, (list, tuple)) else [("%s.%d" % (attr, k), it) for k, it in enumerate(v)]
+            for path, it in items:
+                if isinstance(it, Layer) and it is not self and all(it is not s for s in seen):
+                    seen.append(it)
+                    out.append((path, it))
+        return out
+
+    def named_weights(self, prefix=""):
+        """[(path, tensor)]: own weights first, then sub-layers by attribute path,
+        e.g. 'gnn/gnn_layers/seq_layers.0/kernel', 'rs/unet/layers.1/bias'."""
+        out = [(prefix + k, v) for k, v in self._weights.items()]
+        for path, sub in self._sublayers():
+            out.extend(sub.named_weights(prefix + path + "/"))
+        return out
+
+    @property
+    def weights(self):
+        return [w for _, w in self.named_weights()]
+
+    @property
+    def trainable_weights(self):
+        return [w for w in self.weights if getattr(w, "trainable", True)]
+
+    @property
+    def non_trainable_weights(self):
+        return [w for w in self.weights if not getattr(w, "trainable", True)]
+
+    def get_weights(self):
+        return [w.detach().cpu().numpy() for w in self.weights]
+
+    def set_weights(self, arrays):
+        ws = self.weights
+        if len(ws) != len(arrays):
+            raise ValueError("expected {} arrays, got {}".format(len(ws), len(arrays)))
+        for w, a in zip(ws, arrays):
+            a = torch.as_tensor(np.asarray(a, dtype=np.float32))
+            if tuple(a.shape) != tuple(w.shape):
+                raise ValueError("shape mismatch {} vs {}".format(tuple(a.shape), tuple(w.shape)))
+            w.copy_(a.to(w.device))
+
+    def count_params(self):
+        return int(sum(w.numel() for w in self.weights))
+
+    # -- call ------------------------------------------------------------
+    def build(self, input_shape):
+        self.built = True
+
+    def call(self, inputs, **kwargs):
+        raise NotImplementedError
+
+    def __call__(self, inputs, **kwargs):
+        if not self.built:
+            self.build(_shape_of(inputs))
+            self.built = True
+        return self.call(inputs, **kwargs)
+
+
+def _shape_of(x):
+    if isinstance(x, (list, tuple)):
+        return [_shape_of(v) for v in x]
+    return tuple(x.shape) if hasattr(x, "shape") else None
+
+
+class Model(Layer):
+    """compile / predict / evaluate / summary as the reference's Experimenter calls them.
+
+    fit() (the training step: backward kernels, BCE + L2, Adam) is row (f)-1 of the
+    scope table, scheduled after the forward path; it raises until then."""
+
+    def compile(self, loss=None, optimizer=None, metrics=None):
+        self.loss, self.optimizer, self.metrics = loss, optimizer, metrics
+
+    def predict(self, sequence):
+        outs = []
+        for i in range(len(sequence)):
+            x, _ = sequence[i]
+            outs.append(self(x).detach().cpu().numpy())
+        return np.concatenate(outs, axis=0)
+
+    def evaluate(self, sequence):
+        """[binary cross-entropy, accuracy] averaged over samples (Keras clips p to [1e-7, 1-1e-7])."""
+        loss = acc = n = 0.0
+        for i in range(len(sequence)):
+            x, y = sequence[i]
+            p = self(x).detach().cpu().numpy().reshape(-1).astype(np.float64)
+            y = np.asarray(y, dtype=np.float64).reshape(-1)
+            pc = np.clip(p, 1e-7, 1 - 1e-7)
+            loss += float(-(y * np.log(pc) + (1 - y) * np.log(1 - pc)).sum())
+            acc += float(((p > 0.5) == (y > 0.5)).sum())
+            n += len(y)
+        return [loss / max(n, 1), acc / max(n, 1)]
+
+    def fit(self, sequence, epochs=1, workers=1, callbacks=None):
+        raise NotImplementedError("training (backward kernels + Adam) is scheduled after the forward hot path; "
+                                  "see DESIGN.md 'what comes next'")
+
+    def summary(self, print_fn=print, expand_nested=True):
+        print_fn("Model: {}".format(type(self).__name__))
+        for name, w in self.named_weights():
+            print_fn("  {:60s} {:>18s} {:>10d}".format(name, str(tuple(w.shape)), w.numel()))
+        print_fn("Total params: {}".format(self.count_params()))

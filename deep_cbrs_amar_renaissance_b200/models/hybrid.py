@@ -1,0 +1,152 @@
+"""HybridCBRS scorer and the HybridBertGNN family (mirror of
+/root/reference/src/models/hybrid.py:13-181).
+
+`HybridBertGCN(adj, **config.model)` / `model((u_ids, i_ids, u_bert, i_bert)) -> [B,1]`.
+The reference gathers the 768-d content rows on the host per batch
+(src/data/datasets.py:65-66) and ships 2 x [B,768] floats over PCIe; that call form is
+kept, and `set_content_table` adds the B200 form: the [N,768] table is uploaded once
+and the rows are gathered inside the first Dense kernel from the ids alone."""
+import abc
+
+import numpy as np
+import torch
+
+from ..keras_like import Model, default_device
+from ..layers.fusion import FusionLayer
+from .basic import _ids
+from .dense import build_dense_classifier, build_dense_network
+from .gnn import GAT, GCN, DGCF, RGCN, GraphSage, LightGCN
+
+
+def _rows(x):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=default_device(), dtype=torch.float32, non_blocking=True)
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(default_device(), non_blocking=True)
+
+
+class HybridCBRS(Model):
+    def __init__(self, feature_based=True, dense_units=((512, 256, 128), (512, 256, 128), (64, 64)),
+                 clf_units=(64, 64), activation='relu', fusion_method='concatenate', residual=False, **kwargs):
+        super().__init__("hybrid_cbrs")
+        self.feature_based = feature_based
+        if feature_based:
+            self.fuse1a, self.fuse1b, self.fuse2 = FusionLayer('concatenate'), FusionLayer('concatenate'), FusionLayer(fusion_method)
+        else:
+            self.fuse1a, self.fuse1b, self.fuse2 = FusionLayer(fusion_method), FusionLayer(fusion_method), FusionLayer('concatenate')
+        self.dense1a = build_dense_network(dense_units[0], activation=activation)
+        self.dense1b = build_dense_network(dense_units[0], activation=activation)
+        self.dense2a = build_dense_network(dense_units[1], activation=activation)
+        self.dense2b = build_dense_network(dense_units[1], activation=activation)
+        self.dense3a = build_dense_network(dense_units[2], activation=activation)
+        self.dense3b = build_dense_network(dense_units[2], activation=activation)
+        if residual:
+            raise NotImplementedError("residual classifier: tweaks grid only, outside the first hot-path bar")
+        self.residual = self.activation = None
+        self.clf = build_dense_classifier(clf_units, n_classes=1, activation=activation)
+        self.built = True
+
+    def build_for(self, d_graph, d_content):
+        g = self.dense1a.build_for(d_graph)
+        self.dense1b.build_for(d_graph)
+        c = self.dense2a.build_for(d_content)
+        self.dense2b.build_for(d_content)
+        o1 = self.dense3a.build_for(2 * g if self.feature_based else g + c)
+        o2 = self.dense3b.build_for(2 * c if self.feature_based else g + c)
+        self.clf.build_for(o1 + o2)
+
+    def call(self, inputs, **kwargs):
+        ug, ig, ub, ib = inputs
+        return self.call_sources((ug, None), (ig, None), (ub, None), (ib, None))
+
+    def call_sources(self, ug_src, ig_src, ub_src, ib_src):
+        ug = (self.dense1a.call_sources([ug_src]), None)
+        ig = (self.dense1b.call_sources([ig_src]), None)
+        ub = (self.dense2a.call_sources([ub_src]), None)
+        ib = (self.dense2b.call_sources([ib_src]), None)
+        if self.feature_based:
+            x1 = self.dense3a.call_sources([ug, ig])
+            x2 = self.dense3b.call_sources([ub, ib])
+        else:
+            x1 = self.dense3a.call_sources([ug, ub])
+            x2 = self.dense3b.call_sources([ig, ib])
+        return self.clf.call_sources([(x1, None), (x2, None)])
+
+
+class HybridBertGNN(Model, abc.ABC):
+    def __init__(self, dense_units=(32, 16), clf_units=(16, 16), feature_based=False, activation='relu',
+                 fusion_method='concatenate', residual=False, **kwargs):
+        super().__init__(type(self).__name__.lower())
+        self.rs = HybridCBRS(feature_based=feature_based, dense_units=dense_units, clf_units=clf_units,
+                             activation=activation, fusion_method=fusion_method, residual=residual)
+        self.content_table = None
+        self.cache_propagation = False
+        self._cached = None
+        self.built = True
+
+    def build_weights(self, content_dim=768):
+        self.gnn.gnn_layers.build_layers()
+        self.rs.build_for(self.gnn.gnn_layers.out_dim, content_dim)
+        return self
+
+    def set_content_table(self, table):
+        """Upload the [N, 768] content embeddings once (rows ordered like node ids)."""
+        self.content_table = _rows(table).contiguous()
+
+    def propagate(self):
+        if self.cache_propagation and self._cached is not None:
+            return self._cached
+        emb = self.gnn(None)
+        if self.cache_propagation:
+            self._cached = emb
+        return emb
+
+    def invalidate(self):
+        self._cached = None
+
+    def call(self, inputs, **kwargs):
+        updated_embeddings = self.propagate()
+        return self.embed_recommend(updated_embeddings, inputs)
+
+    def embed_recommend(self, embeddings, inputs):
+        if len(inputs) == 2:
+            if self.content_table is None:
+                raise ValueError("ids-only call needs set_content_table(...) first")
+            u, i = _ids(inputs[0]), _ids(inputs[1])
+            return self.rs.call_sources((embeddings, u), (embeddings, i), (self.content_table, u),
+                                        (self.content_table, i))
+        ug, ig, ub, ib = inputs
+        return self.rs.call_sources((embeddings, _ids(ug)), (embeddings, _ids(ig)), (_rows(ub), None),
+                                    (_rows(ib), None))
+
+    def recommend_top_k(self, n_users, n_items, k=10, users=None, user_block=None):
+        from ..scoring import catalog_top_k
+        return catalog_top_k(self, self.propagate(), n_users, n_items, k, users, user_block)
+
+
+def BasicGNNFactory(name, Parent, GNN):
+    def __init__(self, *args, **kwargs):
+        Parent.__init__(self, **kwargs)
+        self.gnn = self.gnn_class(*args, **kwargs)
+
+    return type(name, (Parent,), {"gnn_class": GNN, "__init__": __init__})
+
+
+class HybridBertTSGNN(HybridBertGNN):
+    pass
+
+
+class HybridBertTWGNN(HybridBertGNN):
+    pass
+
+
+HYBRID_GNNS = [(HybridBertGNN, [GCN, GAT, GraphSage, LightGCN, DGCF, RGCN], None)]
+
+
+def generate_hybrids():
+    for parent, gnns, name_getter in HYBRID_GNNS:
+        for gnn in gnns:
+            name = 'HybridBert' + gnn.__name__
+            globals()[name] = BasicGNNFactory(name, parent, gnn)
+
+
+generate_hybrids()

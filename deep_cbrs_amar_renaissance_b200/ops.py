@@ -1,0 +1,245 @@
+"""Thin tensor -> pointer wrappers over the C ABI (include/cbrs_b200.h).
+
+Every function takes CUDA torch tensors, launches on torch's current stream and
+returns torch tensors.  No CPU path exists: a non-CUDA tensor raises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+# bench instrumentation: kernel launches issued through this module, and (when PROFILE_ON) CUDA
+# events on the launching stream around each propagation call
+LAUNCHES = 0
+PROFILE_ON = False
+PROFILE = []
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise L.CbrsError("expected a CUDA tensor (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise L.CbrsError("expected dtype {}, got {}".format(dtype, t.dtype))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _rowmajor(t):
+    """(tensor, leading dimension) of a 2-D float32 view whose rows are contiguous."""
+    if t.dim() != 2 or t.dtype != torch.float32 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise L.CbrsError("expected a 2-D float32 tensor with unit column stride")
+    return t, (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def check_device():
+    L.check(L.load().cbrs_check_device(), "cbrs_check_device")
+
+
+# ------------------------------------------------------------------ graph build
+def graph_build_csr(row, col, val, n_nodes, flags, rel=None, n_rel=1, self_rel=0):
+    """COO (int32 row/col [, float32 val] [, int32 rel]) -> (rowptr int64, colidx int32, vals float32)."""
+    lib = L.load()
+    dev = row.device
+    nnz = row.numel()
+    cap = nnz + (n_nodes if flags & L.GRAPH_ADD_SELF_LOOPS else 0)
+    rowptr = torch.empty(n_nodes + 1, dtype=torch.int64, device=dev)
+    colidx = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    vals = torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+    ws_bytes = lib.cbrs_graph_build_workspace_bytes(nnz, n_nodes, flags)
+    ws = _ws(ws_bytes, dev)
+    if rel is None and n_rel == 1:
+        rc = lib.cbrs_graph_build_csr(_ptr(row, torch.int32), _ptr(col, torch.int32), _ptr(val, torch.float32), nnz,
+                                      n_nodes, flags, _ptr(rowptr), _ptr(colidx), _ptr(vals), None, _ptr(ws),
+                                      ws.numel(), _stream())
+    else:
+        rc = lib.cbrs_graph_build_csr_rel(_ptr(row, torch.int32), _ptr(col, torch.int32), _ptr(rel, torch.int32),
+                                          _ptr(val, torch.float32), nnz, n_nodes, n_rel, self_rel, flags,
+                                          _ptr(rowptr), _ptr(colidx), _ptr(vals), None, _ptr(ws), ws.numel(),
+                                          _stream())
+    L.check(rc, "cbrs_graph_build_csr")
+    n_out = int(rowptr[-1].item())
+    return rowptr, colidx[:n_out], vals[:n_out]
+
+
+def build_chunks(rowptr, chunk_edges):
+    """Chunk decomposition of a CSR row-pointer (see cbrs_csr_t)."""
+    lib = L.load()
+    dev = rowptr.device
+    n_rows = rowptr.numel() - 1
+    ws = _ws(lib.cbrs_chunks_workspace_bytes(n_rows), dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    L.check(lib.cbrs_chunks_count(_ptr(rowptr, torch.int64), n_rows, chunk_edges, _ptr(counts), _ptr(ws), ws.numel(),
+                                  _stream()), "cbrs_chunks_count")
+    n_chunks, n_heavy, n_slots = (int(v) for v in counts.tolist())
+    chunk_row = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
+    chunk_begin = torch.empty(max(n_chunks, 1), dtype=torch.int64, device=dev)
+    chunk_slot = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
+    heavy_row = torch.empty(max(n_heavy, 1), dtype=torch.int32, device=dev)
+    heavy_slot_ptr = torch.zeros(n_heavy + 1, dtype=torch.int64, device=dev)
+    L.check(lib.cbrs_chunks_fill(_ptr(rowptr), n_rows, chunk_edges, _ptr(chunk_row), _ptr(chunk_begin),
+                                 _ptr(chunk_slot), _ptr(heavy_row), _ptr(heavy_slot_ptr), _ptr(ws), ws.numel(),
+                                 _stream()), "cbrs_chunks_fill")
+    return dict(n_chunks=n_chunks, n_heavy=n_heavy, n_slots=n_slots, chunk_row=chunk_row[:n_chunks],
+                chunk_begin=chunk_begin[:n_chunks], chunk_slot=chunk_slot[:n_chunks], heavy_row=heavy_row[:n_heavy],
+                heavy_slot_ptr=heavy_slot_ptr)
+
+
+# ------------------------------------------------------------------ propagation
+def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None):
+    """out[:, :] = epilogue(A @ x) for the rows held by `csr` (a graph.CsrSlice)."""
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    out, ldy = _rowmajor(out)
+    d = x.shape[1]
+    if out.shape[1] != d or out.shape[0] != csr.n_rows:
+        raise L.CbrsError("spmm: output shape {} does not match [{}, {}]".format(tuple(out.shape), csr.n_rows, d))
+    need = lib.cbrs_spmm_workspace_bytes(ctypes.byref(csr.desc), d)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, x.device)
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(lib.cbrs_spmm_csr(ctypes.byref(csr.desc), _ptr(x), ldx, _ptr(out), ldy, d, agg, _ptr(bias, torch.float32),
+                              1 if relu else 0, L.DTYPE_F32, _ptr(ws), ws.numel(), _stream()), "cbrs_spmm_csr")
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("spmm", e0, e1, csr.nnz))
+    _count(1 + (1 if csr.chunks["n_heavy"] else 0))
+    return out
+
+
+def gat(csr, z, p, q, out, bias=None, relu=True, row_offset=0, workspace=None):
+    lib = L.load()
+    z, ldz = _rowmajor(z)
+    out, ldy = _rowmajor(out)
+    h = z.shape[1]
+    need = lib.cbrs_gat_workspace_bytes(ctypes.byref(csr.desc), h)
+    ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, z.device)
+    L.check(lib.cbrs_gat_csr(ctypes.byref(csr.desc), row_offset, _ptr(z), ldz, _ptr(p, torch.float32),
+                             _ptr(q, torch.float32), _ptr(out), ldy, h, _ptr(bias, torch.float32), 1 if relu else 0,
+                             _ptr(ws), ws.numel(), _stream()), "cbrs_gat_csr")
+    _count(1 + (1 if csr.chunks["n_heavy"] else 0))
+    return out
+
+
+def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_NONE, a_self=None, a_neigh=None,
+          out=None, m=None):
+    """act(rowop([x1[idx1] || x2[idx2]] @ w + b)); returns out (and (p, q) for the attention row-op)."""
+    lib = L.load()
+    x1, ld1 = _rowmajor(x1)
+    f1 = x1.shape[1]
+    f2 = 0
+    ld2 = 0
+    if x2 is not None:
+        x2, ld2 = _rowmajor(x2)
+        f2 = x2.shape[1]
+    if m is None:
+        m = idx1.numel() if idx1 is not None else x1.shape[0]
+    if w.dim() != 2 or w.shape[0] != f1 + f2 or not w.is_contiguous():
+        raise L.CbrsError("dense: kernel must be contiguous [{}, n], got {}".format(f1 + f2, tuple(w.shape)))
+    n = w.shape[1]
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=x1.device)
+    out, ldo = _rowmajor(out)
+    p_out = q_out = None
+    if rowop == L.ROWOP_ATTN:
+        p_out = torch.empty(m, dtype=torch.float32, device=x1.device)
+        q_out = torch.empty(m, dtype=torch.float32, device=x1.device)
+    code = act if isinstance(act, int) else L.ACTS[act]
+    L.check(lib.cbrs_dense(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2, _ptr(idx2, torch.int64), f2,
+                           _ptr(w, torch.float32), _ptr(b, torch.float32), m, n, code, rowop,
+                           _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32), _ptr(p_out), _ptr(q_out),
+                           _ptr(out), ldo, _stream()), "cbrs_dense")
+    _count(2 if (rowop == L.ROWOP_L2NORM and n > 128) else 1)
+    if rowop == L.ROWOP_ATTN:
+        return out, p_out, q_out
+    return out
+
+
+def reduce_layers(hs, coefs=None, divide_by=1.0, out=None):
+    lib = L.load()
+    n_rows, d = hs[0].shape
+    if out is None:
+        out = torch.empty(n_rows, d, dtype=torch.float32, device=hs[0].device)
+    out, ldo = _rowmajor(out)
+    n = len(hs)
+    ptrs = (ctypes.c_void_p * n)(*[h.data_ptr() for h in hs])
+    lds = (ctypes.c_int64 * n)(*[_rowmajor(h)[1] for h in hs])
+    cf = (ctypes.c_float * n)(*[float(c) for c in coefs]) if coefs is not None else None
+    L.check(lib.cbrs_reduce_layers(ptrs, lds, n, cf, float(divide_by), n_rows, d, _ptr(out), ldo, _stream()),
+            "cbrs_reduce_layers")
+    _count(1)
+    return out
+
+
+def gather_rows(x, idx, out=None):
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    m, d = idx.numel(), x.shape[1]
+    if out is None:
+        out = torch.empty(m, d, dtype=torch.float32, device=x.device)
+    out, ldo = _rowmajor(out)
+    L.check(lib.cbrs_gather_rows(_ptr(x), ldx, _ptr(idx, torch.int64), m, d, _ptr(out), ldo, _stream()),
+            "cbrs_gather_rows")
+    _count(1)
+    return out
+
+
+# ------------------------------------------------------------------ top-k
+def topk_rows(scores, k):
+    lib = L.load()
+    scores, ld = _rowmajor(scores)
+    n_users, n_items = scores.shape
+    ids = torch.empty(n_users, k, dtype=torch.int32, device=scores.device)
+    vals = torch.empty(n_users, k, dtype=torch.float32, device=scores.device)
+    L.check(lib.cbrs_topk_rows(_ptr(scores), ld, n_users, n_items, k, _ptr(ids), _ptr(vals), _stream()),
+            "cbrs_topk_rows")
+    _count(1)
+    return ids, vals
+
+
+def topk_pairs(users, scores, n_users, k):
+    """Rows of the pair list kept by the reference's per-user head(k), in (user asc, score desc) order."""
+    lib = L.load()
+    n = users.numel()
+    order = torch.empty(n, dtype=torch.int32, device=users.device)
+    rank = torch.empty(n, dtype=torch.int32, device=users.device)
+    ws = _ws(lib.cbrs_topk_pairs_workspace_bytes(n), users.device)
+    L.check(lib.cbrs_topk_pairs(_ptr(users, torch.int64), _ptr(scores.reshape(-1), torch.float32), n, n_users,
+                                _ptr(order), _ptr(rank), _ptr(ws), ws.numel(), _stream()), "cbrs_topk_pairs")
+    return order[rank < k].to(torch.int64)
+
+
+# ------------------------------------------------------------------ misc
+def synth_bipartite(n_users, n_items, n_edges, seed, device):
+    lib = L.load()
+    row = torch.empty(2 * n_edges, dtype=torch.int32, device=device)
+    col = torch.empty(2 * n_edges, dtype=torch.int32, device=device)
+    L.check(lib.cbrs_synth_bipartite(n_users, n_items, n_edges, seed, _ptr(row), _ptr(col), _stream()),
+            "cbrs_synth_bipartite")
+    return row, col
+
+
+def sort_pairs_u64(keys, payload, key_bits):
+    """In-place stable ascending sort (keys: int64 tensor holding uint64 bit patterns; payload int32)."""
+    lib = L.load()
+    n = keys.numel()
+    ws = _ws(lib.cbrs_sort_workspace_bytes(n), keys.device)
+    L.check(lib.cbrs_sort_pairs_u64(_ptr(keys, torch.int64), _ptr(payload, torch.int32), n, key_bits, _ptr(ws),
+                                    ws.numel(), _stream()), "cbrs_sort_pairs_u64")
+    return keys, payload

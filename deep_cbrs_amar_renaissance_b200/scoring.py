@@ -1,0 +1,86 @@
+"""Full-catalog scoring + per-user top-k (scope row T, catalog form).
+
+The reference only ranks the test pairs (/root/reference/src/experiment.py:197-207);
+scoring every (user, item) is the new capability the north star asks for.  Work that
+depends on one entity only (the towers of BasicRS / HybridCBRS, src/models/basic.py:33-34,
+src/models/hybrid.py:74-77) is hoisted and computed once per user / item; the pairwise
+part runs over blocks of users x all items, the tower rows being gathered inside the
+first pairwise Dense kernel, and each block's [UB, I] scores go through cbrs_topk_rows.
+Users are independent => sharded across ranks with no collective.
+"""
+import torch
+
+from . import ops
+
+_PAIR_BUDGET = 1 << 18  # pairs per block: keeps a block's 64-wide activations L2-resident
+
+
+def _block_indices(cache, ub, n_items, device):
+    key = (ub, n_items)
+    if key not in cache:
+        pu = torch.arange(ub, device=device, dtype=torch.int64).repeat_interleave(n_items)
+        pi = torch.arange(n_items, device=device, dtype=torch.int64).repeat(ub)
+        cache[key] = (pu, pi)
+    return cache[key]
+
+
+def _pair_scorer(model, emb, user_nodes, item_nodes):
+    """Returns f(pu, pi) -> scores [len(pu), 1]; pu / pi index the hoisted per-entity tables."""
+    rs = model.rs
+    if hasattr(rs, "unet"):  # BasicRS
+        if rs.unet.layers:
+            ut = rs.unet.call_sources([(emb, user_nodes)])
+            it = rs.inet.call_sources([(emb, item_nodes)])
+            return lambda pu, pi: rs.clf.call_sources([(ut, pu), (it, pi)])
+        return lambda pu, pi: rs.clf.call_sources([(emb, user_nodes[pu]), (emb, item_nodes[pi])])
+    # HybridCBRS
+    table = model.content_table
+    if table is None:
+        raise ValueError("catalog scoring of a hybrid model needs set_content_table(...)")
+    ug = rs.dense1a.call_sources([(emb, user_nodes)])
+    ig = rs.dense1b.call_sources([(emb, item_nodes)])
+    ub = rs.dense2a.call_sources([(table, user_nodes)])
+    ib = rs.dense2b.call_sources([(table, item_nodes)])
+    if rs.feature_based:
+        def score(pu, pi):
+            x1 = rs.dense3a.call_sources([(ug, pu), (ig, pi)])
+            x2 = rs.dense3b.call_sources([(ub, pu), (ib, pi)])
+            return rs.clf.call_sources([(x1, None), (x2, None)])
+        return score
+    x1 = rs.dense3a.call_sources([(ug, None), (ub, None)])
+    x2 = rs.dense3b.call_sources([(ig, None), (ib, None)])
+    return lambda pu, pi: rs.clf.call_sources([(x1, pu), (x2, pi)])
+
+
+def catalog_scores(model, emb, n_users, n_items, users=None):
+    """Dense [U, n_items] score matrix (tests / small catalogs only)."""
+    dev = emb.device
+    users = torch.arange(n_users, device=dev, dtype=torch.int64) if users is None else users.to(dev, torch.int64)
+    items = torch.arange(n_users, n_users + n_items, device=dev, dtype=torch.int64)
+    score = _pair_scorer(model, emb, users, items)
+    cache = {}
+    ub = max(1, _PAIR_BUDGET // n_items)
+    out = torch.empty(users.numel(), n_items, dtype=torch.float32, device=dev)
+    for u0 in range(0, users.numel(), ub):
+        nb = min(ub, users.numel() - u0)
+        pu, pi = _block_indices(cache, nb, n_items, dev)
+        out[u0:u0 + nb] = score(pu + u0, pi).reshape(nb, n_items)
+    return out
+
+
+def catalog_top_k(model, emb, n_users, n_items, k=10, users=None, user_block=None):
+    dev = emb.device
+    users = torch.arange(n_users, device=dev, dtype=torch.int64) if users is None else users.to(dev, torch.int64)
+    items = torch.arange(n_users, n_users + n_items, device=dev, dtype=torch.int64)
+    score = _pair_scorer(model, emb, users, items)
+    cache = {}
+    ub = user_block or max(1, _PAIR_BUDGET // n_items)
+    ids = torch.empty(users.numel(), k, dtype=torch.int32, device=dev)
+    vals = torch.empty(users.numel(), k, dtype=torch.float32, device=dev)
+    for u0 in range(0, users.numel(), ub):
+        nb = min(ub, users.numel() - u0)
+        pu, pi = _block_indices(cache, nb, n_items, dev)
+        s = score(pu + u0, pi).reshape(nb, n_items)
+        bi, bv = ops.topk_rows(s, k)
+        ids[u0:u0 + nb], vals[u0:u0 + nb] = bi, bv
+    return ids, vals

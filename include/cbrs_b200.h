@@ -1,0 +1,198 @@
+/* cbrs_b200.h - C ABI of the B200 (sm_100a) hot path of Deep_CBRS_Amar_Renaissance.
+ *
+ * Path: graph build -> GNN propagation (GCN / LightGCN / GraphSAGE / GAT / relational)
+ *       -> gather user+item rows (+ content rows) -> dense MLP -> sigmoid -> top-k.
+ *
+ * The reference (pure Python on TensorFlow + Spektral) has no FFI: its "operator
+ * API" is the Python layer / model call convention.  Each entry
+ * point below names the reference lines whose work it replaces; INTEGRATION.md
+ * shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host;
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it,
+ *    never synchronise, never allocate: scratch comes from the caller, sized by
+ *    the matching *_workspace_bytes query (host-only, no CUDA call);
+ *  - returns 0 on success, <0 on error (CBRS_E_*); the message is kept per host
+ *    thread and read with cbrs_last_error();
+ *  - feature matrices are row-major float32 with an explicit leading dimension
+ *    (ld, in elements) so layers write straight into column slices of one
+ *    [N, D_out] buffer (the 'concatenation' reduction costs nothing);
+ *  - row pointers are int64, column ids int32 (2e9 + 1.1e7 edges still fit).
+ */
+#ifndef CBRS_B200_H_
+#define CBRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBRS_OK 0
+#define CBRS_E_INVALID (-1)   /* bad argument */
+#define CBRS_E_WORKSPACE (-2) /* workspace too small */
+#define CBRS_E_CUDA (-3)      /* CUDA runtime error (launch failed, wrong device, ...) */
+#define CBRS_E_UNSUPPORTED (-4)
+
+/* ---- library ---------------------------------------------------------- */
+int cbrs_version(void);
+const char *cbrs_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x (the only target). */
+int cbrs_check_device(void);
+
+/* ---- graph build (rows G1-G3) ------------------------------------------
+ * Replaces, on device: scipy COO->CSR + duplicate summing + spektral gcn_filter
+ * (call sites /root/reference/src/models/gnn.py:283, src/layers/lightgcn_conv.py:58)
+ * and the tf.sparse.reorder of src/utilities/math.py:47-56.
+ * Stable LSD radix sort of (row,col) keys, run-length duplicate sum, row-pointer
+ * scan, symmetric normalisation.  Bit-exact structure vs. the oracle.          */
+#define CBRS_GRAPH_DEDUP_SUM 1      /* sum duplicate (row,col) entries in input order        */
+#define CBRS_GRAPH_ADD_SELF_LOOPS 2 /* M_ii += 1 (entry created if absent); needs DEDUP_SUM  */
+#define CBRS_GRAPH_SYM_NORM 4       /* vals = fl32(fl32(d_i*m_ij)*d_j), d = rowsum^-1/2      */
+#define CBRS_GRAPH_DROP_DIAG 8      /* drop (i,i) entries before anything else (GAT edge set) */
+
+size_t cbrs_graph_build_workspace_bytes(int64_t nnz, int64_t n_nodes, int flags);
+/* Capacity of colidx / vals must be nnz (+ n_nodes with ADD_SELF_LOOPS).
+ * rowptr has n_nodes+1 entries; the output edge count is rowptr[n_nodes]
+ * (also written to *nnz_out, a device int64, if not NULL).
+ * coo_val may be NULL (all ones).                                              */
+int cbrs_graph_build_csr(const int32_t *coo_row, const int32_t *coo_col, const float *coo_val,
+                         int64_t nnz, int64_t n_nodes, int flags, int64_t *rowptr,
+                         int32_t *colidx, float *vals, int64_t *nnz_out, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+/* Relational variant (row R, extension): rel[e] in [0,n_rel) joins the key as
+ * (row, rel, col); the output column id is rel*n_nodes + col so one SpMM over the
+ * stacked per-relation transforms [n_rel*N, H] does the grouped scatter.
+ * Self loops (ADD_SELF_LOOPS) are tagged with relation self_rel.  Normalisation uses the
+ * node degree over ALL relations, so the values equal gcn_filter(A)'s and n_rel = 1
+ * reproduces cbrs_graph_build_csr exactly.                                        */
+int cbrs_graph_build_csr_rel(const int32_t *coo_row, const int32_t *coo_col, const int32_t *coo_rel,
+                             const float *coo_val, int64_t nnz, int64_t n_nodes, int32_t n_rel,
+                             int32_t self_rel, int flags, int64_t *rowptr, int32_t *colidx, float *vals,
+                             int64_t *nnz_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- work decomposition -------------------------------------------------
+ * Rows are cut into chunks of at most chunk_edges edges so that power-law item
+ * rows do not serialise on one warp.  A row with a single chunk is written by
+ * the chunk kernel itself; a row with several ("heavy") parks one partial per
+ * chunk and is summed in ascending chunk order by a second kernel: a fixed
+ * reduction tree, so results do not depend on launch shape or on how rows are
+ * partitioned over GPUs.                                                        */
+typedef struct cbrs_csr {
+    int64_t n_rows;            /* rows held here (a rank's slice in the multi-GPU case)   */
+    int64_t nnz;
+    const int64_t *rowptr;     /* [n_rows+1], offsets into colidx/vals                    */
+    const int32_t *colidx;     /* [nnz] global column ids, ascending inside a row         */
+    const float *vals;         /* [nnz] or NULL (all ones)                                */
+    int32_t chunk_edges;       /* max edges per chunk                                     */
+    int64_t n_chunks;
+    const int32_t *chunk_row;  /* [n_chunks] local row of the chunk                       */
+    const int64_t *chunk_begin;/* [n_chunks] first edge; end = min(begin+chunk_edges,row end) */
+    const int32_t *chunk_slot; /* [n_chunks] partial slot, or -1 when the row has one chunk */
+    int64_t n_heavy;           /* rows with more than one chunk                           */
+    const int32_t *heavy_row;  /* [n_heavy]                                               */
+    const int64_t *heavy_slot_ptr; /* [n_heavy+1] slot range of each heavy row            */
+    int64_t n_slots;
+} cbrs_csr_t;
+
+/* Pass 1: counts.  counts_out (device int64[3]) = {n_chunks, n_heavy, n_slots}. */
+size_t cbrs_chunks_workspace_bytes(int64_t n_rows);
+int cbrs_chunks_count(const int64_t *rowptr, int64_t n_rows, int32_t chunk_edges,
+                      int64_t *counts_out, void *workspace, size_t workspace_bytes, void *stream);
+/* Pass 2: fill (same workspace, untouched since pass 1). */
+int cbrs_chunks_fill(const int64_t *rowptr, int64_t n_rows, int32_t chunk_edges, int32_t *chunk_row,
+                     int64_t *chunk_begin, int32_t *chunk_slot, int32_t *heavy_row,
+                     int64_t *heavy_slot_ptr, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- propagation kernels (rows P1, P2 aggregate, P4) ---------------------
+ * Y[i, 0:D] = epilogue( reduce_j A_ij * X[col_j, 0:D] ), j over row i ascending.
+ * Replaces tf.sparse.sparse_dense_matmul as invoked by spektral GCNConv /
+ * ops.modal_dot (src/layers/lightgcn_conv.py:53) and the gather +
+ * unsorted_segment_mean of GraphSageConv.                                       */
+#define CBRS_AGG_WEIGHTED 0 /* sum of vals*x (vals NULL => sum of x)  */
+#define CBRS_AGG_SUM 1      /* edge values ignored                      */
+#define CBRS_AGG_MEAN 2     /* sum / edge count; empty row -> 0         */
+#define CBRS_DTYPE_F32 0
+#define CBRS_DTYPE_BF16 1   /* X stored bf16, accumulate fp32, Y fp32 or bf16 (same as X) */
+
+size_t cbrs_spmm_workspace_bytes(const cbrs_csr_t *g, int32_t d);
+int cbrs_spmm_csr(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d,
+                  int agg, const float *bias, int relu, int dtype, void *workspace,
+                  size_t workspace_bytes, void *stream);
+
+/* ---- fused GAT layer (row P3) ---------------------------------------------
+ * z [N,H] = X W (from cbrs_dense with CBRS_ROWOP_ATTN), p = z.a_self (rows of this
+ * slice), q = z.a_neigh (all nodes).  One pass per row: leaky-relu(0.2) edge
+ * score, segment max, exp, sum (+1e-9), weighted aggregate, bias, relu.  The
+ * edge set is the raw adjacency minus existing self loops plus (i,i), computed on
+ * the fly; `row_offset` is the global id of local row 0.  Replaces spektral
+ * GATConv._call_single (4 gathers + 3 segment ops).                              */
+size_t cbrs_gat_workspace_bytes(const cbrs_csr_t *g, int32_t h);
+int cbrs_gat_csr(const cbrs_csr_t *g, int64_t row_offset, const float *z, int64_t ldz,
+                 const float *p, const float *q, float *y, int64_t ldy, int32_t h,
+                 const float *bias, int relu, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- dense layer with fused gather + concat (rows P1 transform, P2, S1-S4) --
+ * out[m, 0:n] = act( [ X1[idx1[m], 0:f1] || X2[idx2[m], 0:f2] ] @ W[f1+f2, n] + b )
+ * idx* NULL => identity; X2 NULL => single source.  Keras Dense semantics
+ * (kernel stored [in,out]); replaces tf.nn.embedding_lookup + Concatenate + Dense
+ * of src/models/basic.py:31-37,72-75 and src/models/hybrid.py:72-89,136-140.    */
+#define CBRS_ACT_NONE 0
+#define CBRS_ACT_RELU 1
+#define CBRS_ACT_SIGMOID 2
+#define CBRS_ACT_TANH 3
+#define CBRS_ROWOP_NONE 0
+#define CBRS_ROWOP_L2NORM 1 /* v / sqrt(max(sum v^2, 1e-12)) before act (GraphSageConv)      */
+#define CBRS_ROWOP_ATTN 2   /* also emit p = out.a_self, q = out.a_neigh (GATConv), n <= 128 */
+int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2,
+               int64_t ld2, const int64_t *idx2, int32_t f2, const float *w, const float *b,
+               int64_t m, int32_t n, int act, int rowop, const float *a_self,
+               const float *a_neigh, float *p_out, float *q_out, float *out, int64_t ldo,
+               void *stream);
+
+/* ---- reduction of layer outputs (row P5) ------------------------------------
+ * out = sum_l coef[l] * h_l  ('sum': 1, 'mean': add then divide by L, 'w-sum': w^2).
+ * 'concatenation' and 'last' need no kernel.  src/layers/reduction.py:15-55.    */
+int cbrs_reduce_layers(const float *const *h_host, const int64_t *ld_host, int32_t n_layers,
+                       const float *coef_host, float divide_by, int64_t n_rows, int32_t d,
+                       float *out, int64_t ldo, void *stream);
+
+/* ---- row gather (row S1/S3 when a materialised batch is needed) ------------- */
+int cbrs_gather_rows(const float *x, int64_t ldx, const int64_t *idx, int64_t m, int32_t d,
+                     float *out, int64_t ldo, void *stream);
+
+/* ---- per-user top-k (row T) ---------------------------------------------------
+ * Catalog form: scores [n_users, n_items] row-major -> ids/vals [n_users, k],
+ * descending score, ties to the LOWER item index (== stable sort of the
+ * reference scorer's output).  k <= 128.                                        */
+int cbrs_topk_rows(const float *scores, int64_t ld, int64_t n_users, int32_t n_items, int32_t k,
+                   int32_t *ids_out, float *vals_out, void *stream);
+/* Pair-list form (src/utilities/metrics.py:21-34): stable sort by (user asc,
+ * score desc), first k rows per user.  order_out [n_pairs] = input row of each
+ * sorted position; rank_out [n_pairs] = position inside its user's run (keep rows
+ * with rank < k).                                                               */
+size_t cbrs_topk_pairs_workspace_bytes(int64_t n_pairs);
+int cbrs_topk_pairs(const int64_t *users, const float *scores, int64_t n_pairs, int64_t n_users,
+                    int32_t *order_out, int32_t *rank_out, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* ---- synthetic scaled graph --------------------------------
+ * Counter-based generator: edge e connects user hash_u(seed,e) % n_users with an
+ * item drawn from a capped Zipf(1) popularity; writes BOTH directions, i.e.
+ * 2*n_edges COO entries: (u, U+i) for e < n_edges then (U+i, u).                */
+int cbrs_synth_bipartite(int64_t n_users, int64_t n_items, int64_t n_edges, uint64_t seed,
+                         int32_t *coo_row, int32_t *coo_col, void *stream);
+
+/* ---- primitives exported for tests -------------------------------------------- */
+size_t cbrs_sort_workspace_bytes(int64_t n);
+/* stable ascending sort of 64-bit keys (bits [0,key_bits)) with a 32-bit payload */
+int cbrs_sort_pairs_u64(uint64_t *keys, uint32_t *payload, int64_t n, int key_bits,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBRS_B200_H_ */

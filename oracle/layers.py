@@ -1,0 +1,275 @@
+"""Oracle (TEST INFRASTRUCTURE): layer arithmetic, rows P0-P5, S1-S4, T, R.
+
+float32 throughout.  Sparse products accumulate each output row sequentially
+in ascending column order (scipy csr_matvecs walks the stored order; TF-CPU
+sparse_dense_matmul does the same on its row-major reordered tensor).
+"""
+import numpy as np
+from scipy import sparse
+
+F32 = np.float32
+
+
+def _csr(indptr, indices, data, n_cols=None):
+    n = len(indptr) - 1
+    return sparse.csr_matrix((np.asarray(data, F32), np.asarray(indices), np.asarray(indptr)),
+                             shape=(n, n if n_cols is None else n_cols))
+
+
+def relu(x):
+    return np.maximum(x, F32(0))
+
+
+def sigmoid(x):
+    x = np.asarray(x, F32)
+    return (F32(1) / (F32(1) + np.exp(-x, dtype=F32))).astype(F32)
+
+
+def activation(name):
+    if name is None or name == "linear":
+        return lambda x: x
+    if name == "relu":
+        return relu
+    if name == "sigmoid":
+        return sigmoid
+    if name == "tanh":
+        return lambda x: np.tanh(x, dtype=F32)
+    raise ValueError("activation not restated: {}".format(name))
+
+
+# ----------------------------------------------------------------- Keras Dense
+def dense(x, kernel, bias=None, act=None):
+    """[3P] keras.layers.Dense: act(x @ kernel[in,out] + bias)."""
+    y = np.asarray(x, F32) @ np.asarray(kernel, F32)
+    if bias is not None:
+        y = y + np.asarray(bias, F32)
+    return activation(act)(y.astype(F32))
+
+
+def dense_network(x, layers, act="relu"):
+    """models/dense.py:4-7 - Sequential of Dense(u, activation)."""
+    for k, b in layers:
+        x = dense(x, k, b, act)
+    return x
+
+
+def dense_classifier(x, layers, act="relu"):
+    """models/dense.py:10-17 - hidden Dense(u, act) then Dense(1, sigmoid)."""
+    for k, b in layers[:-1]:
+        x = dense(x, k, b, act)
+    k, b = layers[-1]
+    return dense(x, k, b, "sigmoid")
+
+
+# ------------------------------------------------------------------------- P1
+def gcn_conv(x, a_hat, kernel, bias, act="relu"):
+    """[3P] spektral GCNConv.call: act(A_hat @ (x @ kernel) + bias). Transform first."""
+    z = (np.asarray(x, F32) @ np.asarray(kernel, F32)).astype(F32)
+    y = (a_hat @ z).astype(F32)
+    if bias is not None:
+        y = y + np.asarray(bias, F32)
+    return activation(act)(y)
+
+
+# ------------------------------------------------------------------------- P4
+def lightgcn_conv(x, a_hat):
+    """layers/lightgcn_conv.py:51-54: X' = A_hat X."""
+    return (a_hat @ np.asarray(x, F32)).astype(F32)
+
+
+# ------------------------------------------------------------------------- P2
+def sage_aggregate(x, indptr, indices, aggregate="mean"):
+    """Neighbourhood aggregate over the RAW edge list (values ignored, dups kept)."""
+    n = len(indptr) - 1
+    ones = np.ones(len(indices), F32)
+    a = _csr(indptr, indices, ones)
+    s = (a @ np.asarray(x, F32)).astype(F32)
+    if aggregate == "sum":
+        return s
+    if aggregate == "mean":
+        cnt = np.diff(indptr).astype(F32)
+        out = np.zeros_like(s)
+        nz = cnt > 0
+        out[nz] = s[nz] / cnt[nz, None]
+        return out
+    if aggregate in ("max", "min"):
+        x = np.asarray(x, F32)
+        out = np.zeros((n, x.shape[1]), F32)
+        red = np.maximum if aggregate == "max" else np.minimum
+        for i in range(n):
+            nb = indices[indptr[i]:indptr[i + 1]]
+            if len(nb):
+                out[i] = red.reduce(x[nb], axis=0)
+        return out
+    raise ValueError("aggregate not restated: {}".format(aggregate))
+
+
+def sage_conv(x, indptr, indices, kernel, bias, aggregate="mean", act="relu"):
+    """[3P] spektral GraphSageConv: act(l2_normalize([x || agg] @ kernel + bias)).
+
+    l2_normalize(v) = v * rsqrt(max(sum(v^2), 1e-12)); normalise BEFORE activation.
+    """
+    x = np.asarray(x, F32)
+    agg = sage_aggregate(x, indptr, indices, aggregate)
+    o = (np.concatenate([x, agg], axis=1) @ np.asarray(kernel, F32)).astype(F32)
+    if bias is not None:
+        o = o + np.asarray(bias, F32)
+    ss = np.maximum((o * o).sum(axis=1, keepdims=True, dtype=F32), F32(1e-12))
+    o = (o / np.sqrt(ss, dtype=F32)).astype(F32)
+    return activation(act)(o)
+
+
+# ------------------------------------------------------------------------- P3
+def gat_conv(x, indptr, indices, kernel, attn_self, attn_neigh, bias, act="relu",
+             add_self_loops=True):
+    """[3P] spektral GATConv (1 head, dropout 0), sparse single mode.
+
+    kernel [F,H] (Keras stores [F,1,H]); attn_self / attn_neigh [H].
+    """
+    from .graph import gat_edges
+    x = np.asarray(x, F32)
+    n = x.shape[0]
+    z = (x @ np.asarray(kernel, F32).reshape(x.shape[1], -1)).astype(F32)
+    p = (z * np.asarray(attn_self, F32).reshape(1, -1)).sum(axis=1, dtype=F32)
+    q = (z * np.asarray(attn_neigh, F32).reshape(1, -1)).sum(axis=1, dtype=F32)
+    if add_self_loops:
+        ptr, cols = gat_edges(indptr, indices)
+    else:
+        ptr, cols = np.asarray(indptr), np.asarray(indices)
+    rows = np.repeat(np.arange(n), np.diff(ptr))
+    e = (p[rows] + q[cols]).astype(F32)
+    e = np.where(e > 0, e, F32(0.2) * e).astype(F32)
+    m = np.full(n, -np.inf, F32)
+    np.maximum.at(m, rows, e)
+    w = np.exp(e - m[rows], dtype=F32)
+    s = _csr(ptr, cols, w) @ np.ones((n, 1), F32)
+    alpha = (w / (s[rows, 0] + F32(1e-9))).astype(F32)
+    out = (_csr(ptr, cols, alpha) @ z).astype(F32)
+    if bias is not None:
+        out = out + np.asarray(bias, F32)
+    return activation(act)(out)
+
+
+# ------------------------------------------------------------------------- P5
+def reduce_layers(hs, method="concatenation", w=None):
+    """layers/reduction.py:15-33 (+ WeightedSum :54-55: sum(w^2 * h))."""
+    if method == "concatenation":
+        return np.concatenate(hs, axis=-1)
+    if method == "sum":
+        acc = hs[0].astype(F32)
+        for h in hs[1:]:
+            acc = acc + h
+        return acc
+    if method == "mean":
+        acc = hs[0].astype(F32)
+        for h in hs[1:]:
+            acc = acc + h
+        return (acc / F32(len(hs))).astype(F32)
+    if method == "last":
+        return hs[-1]
+    if method == "w-sum":
+        w = np.ones(len(hs), F32) if w is None else np.asarray(w, F32).ravel()
+        acc = (w[0] * w[0]) * hs[0]
+        for wi, h in zip(w[1:], hs[1:]):
+            acc = acc + (wi * wi) * h
+        return acc.astype(F32)
+    raise ValueError("Reduction method not supported: " + method)
+
+
+# ------------------------------------------------------------------------- P0
+def propagate(kind, emb, graph, layer_weights, final_node="concatenation", aggregate="mean"):
+    """SequentialGNN.call, models/gnn.py:74-84: x=E; hs=[x]; for l: x=layer([x,A]); reduce(hs).
+
+    kind in {'gcn','lightgcn','sage','gat'}; graph = scipy CSR A_hat for
+    gcn/lightgcn, (indptr, indices) of the raw reordered adjacency otherwise.
+    """
+    x = np.asarray(emb, F32)
+    hs = [x]
+    for w in layer_weights:
+        if kind == "gcn":
+            x = gcn_conv(x, graph, w["kernel"], w["bias"])
+        elif kind == "lightgcn":
+            x = lightgcn_conv(x, graph)
+        elif kind == "sage":
+            x = sage_conv(x, graph[0], graph[1], w["kernel"], w["bias"], aggregate)
+        elif kind == "gat":
+            x = gat_conv(x, graph[0], graph[1], w["kernel"], w["attn_self"], w["attn_neigh"], w["bias"])
+        else:
+            raise ValueError(kind)
+        hs.append(x)
+    if kind == "lightgcn":
+        final_node = "mean"  # gnn.py:378
+    return reduce_layers(hs, final_node)
+
+
+# ------------------------------------------------------------------------- R
+def rgcn_conv(x, rel_graphs, kernels, bias, act="relu"):
+    """Relational extension (no reference counterpart).
+
+    out = act(sum_r A_hat_r @ (x @ W_r) + b).  With one relation this is gcn_conv.
+    Relations are summed in ascending r; inside a relation, ascending column.
+    """
+    acc = None
+    for a_r, w_r in zip(rel_graphs, kernels):
+        t = (a_r @ (np.asarray(x, F32) @ np.asarray(w_r, F32)).astype(F32)).astype(F32)
+        acc = t if acc is None else acc + t
+    if bias is not None:
+        acc = acc + np.asarray(bias, F32)
+    return activation(act)(acc)
+
+
+# -------------------------------------------------------------------- S1 + S2
+def basic_rs(emb, u_ids, i_ids, unet, inet, clf, act="relu"):
+    """BasicGNN.embed_recommend + BasicRS.call, models/basic.py:31-37,65-75."""
+    u = dense_network(emb[u_ids], unet, act)
+    i = dense_network(emb[i_ids], inet, act)
+    return dense_classifier(np.concatenate([u, i], axis=1), clf, act)
+
+
+# -------------------------------------------------------------------- S3 + S4
+def hybrid_cbrs(emb, u_ids, i_ids, u_bert, i_bert, w, act="relu", feature_based=True):
+    """HybridBertGNN.embed_recommend + HybridCBRS.call, models/hybrid.py:72-89,130-140.
+
+    w = dict(dense1a, dense1b, dense2a, dense2b, dense3a, dense3b, clf), each a
+    list of (kernel, bias).  concatenate fusion only (layers/fusion.py:51-53).
+    """
+    ug = dense_network(emb[u_ids], w["dense1a"], act)
+    ig = dense_network(emb[i_ids], w["dense1b"], act)
+    ub = dense_network(np.asarray(u_bert, F32), w["dense2a"], act)
+    ib = dense_network(np.asarray(i_bert, F32), w["dense2b"], act)
+    if feature_based:
+        x1 = dense_network(np.concatenate([ug, ig], axis=1), w["dense3a"], act)
+        x2 = dense_network(np.concatenate([ub, ib], axis=1), w["dense3b"], act)
+    else:
+        x1 = dense_network(np.concatenate([ug, ub], axis=1), w["dense3a"], act)
+        x2 = dense_network(np.concatenate([ig, ib], axis=1), w["dense3b"], act)
+    return dense_classifier(np.concatenate([x1, x2], axis=1), w["clf"], act)
+
+
+# ------------------------------------------------------------------------- T
+def top_k_pairs(u_ids, i_ids, scores, k):
+    """Per-user top-k among an explicit pair list.
+
+    Restates utilities/metrics.py:21-34: stable sort by (user asc, score desc)
+    then head(k) per user; ties keep input order (pandas multi-key sort is
+    stable).  Users are returned in ascending order (the reference iterates a
+    Python set, whose order is unspecified).
+    Returns (users [M], items [M], scores [M], input_rows [M]).
+    """
+    u_ids = np.asarray(u_ids)
+    scores = np.asarray(scores).ravel()
+    order = np.lexsort((np.arange(len(scores)), -scores.astype(np.float64), u_ids))
+    su = u_ids[order]
+    start = np.r_[0, np.flatnonzero(su[1:] != su[:-1]) + 1]
+    rank = np.arange(len(su)) - np.repeat(start, np.diff(np.r_[start, len(su)]))
+    sel = order[rank < k]
+    return u_ids[sel], np.asarray(i_ids)[sel], scores[sel], sel
+
+
+def top_k_catalog(score_matrix, k):
+    """Full-catalog top-k (new capability): reference scorer on every
+    (u,i) + stable descending sort => ties go to the lower item index.
+    Returns (ids int32 [U,k], scores float32 [U,k])."""
+    s = np.asarray(score_matrix, F32)
+    order = np.argsort(-s.astype(np.float64), axis=1, kind="stable")[:, :k]
+    return order.astype(np.int32), np.take_along_axis(s, order, axis=1)

@@ -1,0 +1,89 @@
+"""Shared test inputs: seeded graphs, weights, and tolerant comparisons."""
+import numpy as np
+from scipy import sparse
+
+RTOL = 1e-5  # north star: embeddings and scores within 1e-5 relative (fp32)
+
+
+def random_bipartite(n_users, n_items, n_pos, seed=0, n_props=0, n_links=0, dup_links=0):
+    """Symmetrised COO adjacency in the reference's entry order (+ optional property links with duplicates)."""
+    rng = np.random.RandomState(seed)
+    keys = np.unique(rng.randint(0, n_users * n_items, size=n_pos))
+    rng.shuffle(keys)
+    r, c = keys // n_items, keys % n_items + n_users
+    n = n_users + n_items + n_props
+    if n_props:
+        ii = rng.randint(0, n_items, size=n_links) + n_users
+        pp = rng.randint(0, n_props, size=n_links) + n_users + n_items
+        pick = rng.randint(0, n_links, size=dup_links)
+        r = np.concatenate([r, ii, ii[pick]])
+        c = np.concatenate([c, pp, pp[pick]])
+    rows = np.concatenate([r, c]).astype(np.int32)
+    cols = np.concatenate([c, r]).astype(np.int32)
+    return sparse.coo_matrix((np.ones(len(rows), np.float32), (rows, cols)), shape=(n, n), dtype=np.float32)
+
+
+def glorot(rng, shape):
+    lim = np.sqrt(6.0 / (shape[-2] + shape[-1])) if len(shape) > 1 else np.sqrt(3.0 / shape[0])
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def assert_close(got, want, rtol=RTOL, atol=None, what=""):
+    """max |got-want| <= rtol * max|want| (relative to the tensor scale) unless atol is given."""
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, "{}: shape {} vs {}".format(what, got.shape, want.shape)
+    scale = max(np.abs(want).max(), 1e-30) if want.size else 1.0
+    tol = atol if atol is not None else rtol * scale
+    err = np.abs(got - want).max() if want.size else 0.0
+    assert err <= tol, "{}: max abs err {:.3e} > {:.3e} (scale {:.3e})".format(what, err, tol, scale)
+
+
+def assert_topk_equivalent(ids, vals, oracle_scores, k, tol=2e-6):
+    """ids must be bit-identical to the oracle's stable top-k wherever the oracle's score gaps
+    exceed `tol`; inside a near-tie (fp32 exp differs by an ulp between CPU and GPU) the returned
+    item must still carry an oracle score within tol of the oracle's item at that rank."""
+    s = np.asarray(oracle_scores, np.float64)
+    order = np.argsort(-s, axis=1, kind="stable")[:, :k]
+    ref_vals = np.take_along_axis(s, order, axis=1)
+    ids = np.asarray(ids)
+    got_vals = np.take_along_axis(s, ids.astype(np.int64), axis=1)
+    assert np.abs(got_vals - ref_vals).max() <= tol, "top-k scores differ beyond tolerance"
+    assert np.abs(np.asarray(vals, np.float64) - got_vals).max() <= 1e-5, "returned scores differ from the oracle's"
+    sorted_s = -np.sort(-s, axis=1)[:, :k + 1]
+    gaps = sorted_s[:, :-1] - sorted_s[:, 1:]
+    prev_gap = np.concatenate([np.full((len(s), 1), np.inf), gaps[:, :-1]], axis=1)
+    clear = (gaps > tol) & (prev_gap > tol)
+    assert (ids[clear] == order[clear]).all(), "top-k ids differ where the ranking is unambiguous"
+    return float(clear.mean())
+
+
+def export_weights(model):
+    """Model weights as the numpy structures the oracle takes (Keras layouts: kernel [in,out])."""
+    named = [(n, w.detach().cpu().numpy()) for n, w in model.named_weights()]
+    w = dict(named)
+
+    def stack(prefix):
+        ks = sorted({int(n[len(prefix):].split("/")[0]) for n in w if n.startswith(prefix)})
+        return [(w["%s%d/kernel" % (prefix, k)], w["%s%d/bias" % (prefix, k)]) for k in ks]
+
+    out = dict(embeddings=w["gnn/gnn_layers/embeddings"], layers=[])
+    k = 0
+    while any(n.startswith("gnn/gnn_layers/seq_layers.%d/" % k) for n in w):
+        pre = "gnn/gnn_layers/seq_layers.%d/" % k
+        lw = {n[len(pre):]: v for n, v in w.items() if n.startswith(pre)}
+        if "kernel" in lw and lw["kernel"].ndim == 3:  # GATConv stores [F,1,H]
+            lw["kernel"] = lw["kernel"].reshape(lw["kernel"].shape[0], -1)
+        if "attn_kernel_self" in lw:
+            lw["attn_self"] = lw.pop("attn_kernel_self").reshape(-1)
+            lw["attn_neigh"] = lw.pop("attn_kernel_neigh").reshape(-1)
+        out["layers"].append(lw)
+        k += 1
+    n_layers = len(model.gnn.gnn_layers.seq_layers)
+    out["layers"] += [{} for _ in range(n_layers - len(out["layers"]))]  # weight-free LightGCN layers
+    if any(n.startswith("rs/unet/") for n in w) or hasattr(model.rs, "unet"):
+        out.update(unet=stack("rs/unet/layers."), inet=stack("rs/inet/layers."), clf=stack("rs/clf/layers."))
+    else:
+        for name in ("dense1a", "dense1b", "dense2a", "dense2b", "dense3a", "dense3b", "clf"):
+            out[name] = stack("rs/%s/layers." % name)
+    return out

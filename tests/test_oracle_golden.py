@@ -1,0 +1,98 @@
+"""CPU: the oracle and the host-side data code against fixtures produced by the
+REFERENCE's own loaders (tests/golden/make_golden.py).  Rows G0, G1, S0, S3."""
+import os
+
+import numpy as np
+import pytest
+
+from deep_cbrs_amar_renaissance_b200.data import loaders
+from oracle import graph as og
+
+CASES = ["ui_small", "uip_small", "hybrid_small"]
+
+
+def _load(golden_dir, case):
+    root = os.path.join(golden_dir, case)
+    return root, np.load(os.path.join(root, "golden.npz"))
+
+
+def _tsv(path):
+    return np.loadtxt(path, dtype=np.int64, delimiter="\t", ndmin=2)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_id_compaction_and_adjacency(golden_dir, case):
+    root, g = _load(golden_dir, case)
+    train, test, users, items = og.compact_ids(_tsv(os.path.join(root, "train2id.tsv")),
+                                               _tsv(os.path.join(root, "test2id.tsv")))
+    assert np.array_equal(train, g["train_ratings"]) and np.array_equal(test, g["test_ratings"])
+    assert np.array_equal(users, g["users"]) and np.array_equal(items, g["items"])
+    props_path = os.path.join(root, "props2id.tsv")
+    if os.path.exists(props_path):
+        triples, props = og.compact_props(_tsv(props_path), items)
+        adj = og.build_adjacency(train, len(users), len(items), triples, len(props), "unary-uip")
+    else:
+        adj = og.build_adjacency(train, len(users), len(items))
+    assert tuple(adj.shape) == tuple(g["adj_shape"])
+    assert adj.row.dtype == np.int32 and adj.data.dtype == np.float32
+    assert np.array_equal(adj.row, g["adj_row"]) and np.array_equal(adj.col, g["adj_col"])
+    assert np.array_equal(adj.data, g["adj_data"])
+    # duplicate summing == scipy tocsr of the reference's matrix
+    csr = adj.tocsr()
+    assert np.array_equal(csr.indptr, g["csr_indptr"]) and np.array_equal(csr.indices, g["csr_indices"])
+    assert np.array_equal(csr.data, g["csr_data"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_host_loaders_match_reference(golden_dir, case):
+    root, g = _load(golden_dir, case)
+    kw = dict(train_ratings_filepath=os.path.join(root, "train2id.tsv"),
+              test_ratings_filepath=os.path.join(root, "test2id.tsv"), train_batch_size=128, test_batch_size=64)
+    if os.path.exists(os.path.join(root, "props2id.tsv")):
+        kw.update(props_triples_filepath=os.path.join(root, "props2id.tsv"), type_adjacency="unary-uip")
+    hybrid = os.path.exists(os.path.join(root, "user-lastlayer.json"))
+    if hybrid:
+        kw.update(bert_user_filepath=os.path.join(root, "user-lastlayer.json"),
+                  bert_item_filepath=os.path.join(root, "item-lastlayer.json"))
+        train, test = loaders.load_user_item_graph_bert_embeddings(**kw)
+    else:
+        train, test = loaders.load_user_item_graph(**kw)
+    assert np.array_equal(train.ratings, g["train_ratings"]) and np.array_equal(test.ratings, g["test_ratings"])
+    assert np.array_equal(train.users, g["users"]) and np.array_equal(train.items, g["items"])
+    adj = train.adj_matrix
+    assert np.array_equal(adj.row, g["adj_row"]) and np.array_equal(adj.col, g["adj_col"])
+    assert np.array_equal(adj.data, g["adj_data"]) and adj.dtype == np.float32
+    assert len(train) == int(g["n_train_batches"]) and len(test) == int(g["n_test_batches"])
+    # batch contents over two epochs: the gather indices of the hot path
+    for ep in range(2):
+        for b in range(len(train)):
+            x, y = train[b]
+            assert np.array_equal(x[0], g["train_ep%d_b%d_u" % (ep, b)])
+            assert np.array_equal(x[1], g["train_ep%d_b%d_i" % (ep, b)])
+            assert np.array_equal(y, g["train_ep%d_b%d_y" % (ep, b)])
+            if hybrid:
+                assert np.array_equal(x[2], g["train_ep%d_b%d_ub" % (ep, b)])
+                assert np.array_equal(x[3], g["train_ep%d_b%d_ib" % (ep, b)])
+        train.on_epoch_end()
+    for b in range(len(test)):
+        x, y = test[b]
+        assert np.array_equal(x[0], g["test_ep0_b%d_u" % b]) and np.array_equal(x[1], g["test_ep0_b%d_i" % b])
+
+
+def test_unknown_test_id_raises(golden_dir, tmp_path):
+    root, _ = _load(golden_dir, "ui_small")
+    test = _tsv(os.path.join(root, "test2id.tsv")).copy()
+    test[0, 0] = 10 ** 9
+    bad = tmp_path / "test2id.tsv"
+    np.savetxt(bad, test, fmt="%d", delimiter="\t")
+    with pytest.raises(KeyError):
+        loaders.load_user_item_graph(os.path.join(root, "train2id.tsv"), str(bad))
+    with pytest.raises(KeyError):
+        og.compact_ids(_tsv(os.path.join(root, "train2id.tsv")), test)
+
+
+def test_unknown_adjacency_type_raises(golden_dir):
+    root, _ = _load(golden_dir, "ui_small")
+    with pytest.raises(ValueError):
+        loaders.load_user_item_graph(os.path.join(root, "train2id.tsv"), os.path.join(root, "test2id.tsv"),
+                                     type_adjacency="nope")
