@@ -19,6 +19,8 @@ def gcn_filter_torch(row, col, n):
     """scipy graph build (the reference's own code path for this step) -> torch CSR."""
     adj = sparse.coo_matrix((np.ones(len(row), np.float32), (row, col)), shape=(n, n))
     a = og.gcn_filter(adj)
+    import warnings
+    warnings.filterwarnings("ignore", message="Sparse")
     t = torch.sparse_csr_tensor(torch.from_numpy(a.indptr.astype(np.int64)), torch.from_numpy(a.indices.astype(np.int64)),
                                 torch.from_numpy(a.data), size=a.shape)
     return t, a.nnz

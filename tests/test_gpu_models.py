@@ -328,4 +328,4 @@ def test_large_graph_properties():
     # symmetry: x^T (A y) == (A x)^T y in float64
     lhs = (x.double() * ay.double()).sum().item()
     rhs = (ax.double() * y.double()).sum().item()
-    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)  # fp32 outputs, float64 reduction
