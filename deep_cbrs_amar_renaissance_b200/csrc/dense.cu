@@ -169,6 +169,216 @@ __global__ void __launch_bounds__(256) row_l2norm_act_kernel(float *x, int64_t l
     for (int c = lane; c < n; c += 32) x[row * ld + c] = apply_act(x[row * ld + c] * scale, act);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Fast path: K (both sources) a multiple of 16, 16-byte aligned rows, n % 4 == 0.
+// 3-stage cp.async (LDGSTS, L2-only) ring for the A and W tiles, 128 x BN x 16 CTA tile,
+// 8 x TN micro-tile read from shared memory with 128-bit loads along k (A) and n (W):
+// one LDS.128 per 16 FFMA.  Rows of a thread are interleaved (ty + 16 i) and its columns
+// split in two 4-wide groups so neither operand read has a bank conflict.
+constexpr int kFBK = 16, kFStages = 3, kFAS = kFBK + 4;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int BN>
+__global__ void __launch_bounds__(kDenseThreads, 2) dense_fast_kernel(const DenseParams p) {
+    constexpr int TN = BN / 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *As = reinterpret_cast<float *>(smem_raw);                    // [stages][kBM][kFAS]
+    float *Bs = As + kFStages * kBM * kFAS;                             // [stages][kFBK][BN]
+    int64_t *src1 = reinterpret_cast<int64_t *>(Bs + kFStages * kFBK * BN);
+    int64_t *src2 = src1 + kBM;
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int64_t m0 = (int64_t)blockIdx.x * kBM;
+    const int n0 = blockIdx.y * BN;
+    const int K = p.f1 + p.f2;
+    const int KT = K / kFBK;
+
+    if (tid < kBM) {
+        const int64_t m = m0 + tid;
+        int64_t r1 = -1, r2 = -1;
+        if (m < p.m) {
+            r1 = (p.idx1 ? p.idx1[m] : m) * p.ld1;
+            if (p.x2) r2 = (p.idx2 ? p.idx2[m] : m) * p.ld2;
+        }
+        src1[tid] = r1;
+        src2[tid] = r2;
+    }
+    __syncthreads();
+
+    auto load_tile = [&](int stage, int kt) {
+        const int k0 = kt * kFBK;
+        const bool first = k0 < p.f1;
+        const float *base = first ? p.x1 + k0 : p.x2 + (k0 - p.f1);
+        const int64_t *src = first ? src1 : src2;
+        float *as = As + stage * kBM * kFAS;
+#pragma unroll
+        for (int it = 0; it < (kBM * 4) / kDenseThreads; ++it) {
+            const int e = tid + it * kDenseThreads;
+            const int mm = e >> 2, c = e & 3;
+            const int64_t r = src[mm];
+            cp_async16(as + mm * kFAS + c * 4, r >= 0 ? (const void *)(base + r + c * 4) : (const void *)p.x1, r >= 0 ? 16 : 0);
+        }
+        float *bs = Bs + stage * kFBK * BN;
+        constexpr int chunks = kFBK * BN / 4;
+#pragma unroll
+        for (int it = 0; it < (chunks + kDenseThreads - 1) / kDenseThreads; ++it) {
+            const int e = tid + it * kDenseThreads;
+            if (e < chunks) {
+                const int kk = e / (BN / 4), c = e % (BN / 4);
+                const int ng = n0 + c * 4;
+                const bool ok = ng < p.n;
+                cp_async16(bs + kk * BN + c * 4, ok ? (const void *)(p.w + (int64_t)(k0 + kk) * p.n + ng) : (const void *)p.w,
+                           ok ? 16 : 0);
+            }
+        }
+    };
+
+    float acc[kTM][TN];
+#pragma unroll
+    for (int i = 0; i < kTM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < kFStages - 1; ++s) {
+        if (s < KT) load_tile(s, s);
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<kFStages - 2>();
+        __syncthreads();
+        if (kt + kFStages - 1 < KT) load_tile((kt + kFStages - 1) % kFStages, kt + kFStages - 1);
+        cp_async_commit();
+        const float *as = As + (kt % kFStages) * kBM * kFAS;
+        const float *bs = Bs + (kt % kFStages) * kFBK * BN;
+#pragma unroll
+        for (int kq = 0; kq < kFBK / 4; ++kq) {
+            float4 a[kTM];
+#pragma unroll
+            for (int i = 0; i < kTM; ++i) a[i] = *reinterpret_cast<const float4 *>(as + (ty + 16 * i) * kFAS + kq * 4);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float bv[TN];
+                const float *brow = bs + (kq * 4 + kk) * BN;
+                if (TN == 8) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(brow + tx * 4);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(brow + 64 + tx * 4);
+                    bv[0] = b0.x; bv[1 % TN] = b0.y; bv[2 % TN] = b0.z; bv[3 % TN] = b0.w;
+                    bv[4 % TN] = b1.x; bv[5 % TN] = b1.y; bv[6 % TN] = b1.z; bv[7 % TN] = b1.w;
+                } else if (TN == 4) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(brow + tx * 4);
+                    bv[0] = b0.x; bv[1 % TN] = b0.y; bv[2 % TN] = b0.z; bv[3 % TN] = b0.w;
+                } else {
+                    const float2 b0 = *reinterpret_cast<const float2 *>(brow + tx * 2);
+                    bv[0] = b0.x; bv[1 % TN] = b0.y;
+                }
+#pragma unroll
+                for (int i = 0; i < kTM; ++i) {
+                    const float av = kk == 0 ? a[i].x : kk == 1 ? a[i].y : kk == 2 ? a[i].z : a[i].w;
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, bv[j], acc[i][j]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // column of micro-tile slot j
+    auto col_of = [&](int j) -> int {
+        if (TN == 8) return n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        return n0 + tx * TN + j;
+    };
+    const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out) % 16 == 0) && TN >= 4;
+#pragma unroll
+    for (int i = 0; i < kTM; ++i) {
+        const int64_t m = m0 + ty + 16 * i;
+        float ss = 0.f, ps = 0.f, qs = 0.f;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int ng = col_of(j);
+            float v = acc[i][j];
+            if (ng < p.n) {
+                if (p.b) v += __ldg(p.b + ng);
+                if (p.rowop == CBRS_ROWOP_L2NORM) ss = fmaf(v, v, ss);
+                if (p.rowop == CBRS_ROWOP_ATTN) {
+                    ps = fmaf(v, __ldg(p.a_self + ng), ps);
+                    qs = fmaf(v, __ldg(p.a_neigh + ng), qs);
+                }
+            } else {
+                v = 0.f;
+            }
+            acc[i][j] = v;
+        }
+        if (p.rowop != CBRS_ROWOP_NONE) {
+#pragma unroll
+            for (int o = 8; o; o >>= 1) {
+                ss += __shfl_xor_sync(0xffffffffu, ss, o, 16);
+                ps += __shfl_xor_sync(0xffffffffu, ps, o, 16);
+                qs += __shfl_xor_sync(0xffffffffu, qs, o, 16);
+            }
+        }
+        if (m >= p.m) continue;
+        float scale = 1.f;
+        if (p.rowop == CBRS_ROWOP_L2NORM) scale = 1.f / sqrtf(fmaxf(ss, 1e-12f));
+        if (p.rowop == CBRS_ROWOP_ATTN && tx == 0) {
+            p.p_out[m] = ps;
+            p.q_out[m] = qs;
+        }
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = apply_act(acc[i][j] * scale, p.act);
+        float *orow = p.out + m * p.ldo;
+        if (vec_out) {
+#pragma unroll
+            for (int j0 = 0; j0 < TN; j0 += 4) {
+                const int ng = col_of(j0);
+                if (ng < p.n)  // n % 4 == 0: a 4-wide group is entirely in or out
+                    *reinterpret_cast<float4 *>(orow + ng) =
+                        make_float4(acc[i][j0], acc[i][(j0 + 1) % TN], acc[i][(j0 + 2) % TN], acc[i][(j0 + 3) % TN]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int ng = col_of(j);
+                if (ng < p.n) orow[ng] = acc[i][j];
+            }
+        }
+    }
+}
+
+template <int BN>
+static int launch_dense_fast(const DenseParams &p, cudaStream_t s) {
+    constexpr size_t smem = (size_t)kFStages * (kBM * kFAS + kFBK * BN) * sizeof(float) + 2 * kBM * sizeof(int64_t);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dense_fast_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("dense_fast: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return CBRS_E_CUDA;
+        }
+        configured = true;
+    }
+    dim3 grid((unsigned)cdiv(p.m, kBM), (unsigned)cdiv(p.n, BN));
+    dense_fast_kernel<BN><<<grid, kDenseThreads, smem, s>>>(p);
+    CBRS_CHECK_LAUNCH("dense_fast");
+    return CBRS_OK;
+}
+
+static bool fast_ok(const DenseParams &p) {
+    auto al = [](const void *q) { return ((uintptr_t)q % 16) == 0; };
+    if (p.n % 4 || p.n < 32 || p.f1 % kFBK || p.f2 % kFBK || p.ld1 % 4 || !al(p.x1) || !al(p.w)) return false;
+    if (p.x2 && (p.ld2 % 4 || !al(p.x2))) return false;
+    return true;
+}
+
 template <int BN>
 static int launch_dense(const DenseParams &p, cudaStream_t s) {
     dim3 grid((unsigned)cdiv(p.m, kBM), (unsigned)cdiv(p.n, BN));
@@ -200,11 +410,16 @@ extern "C" int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int
     if (rowop == CBRS_ROWOP_L2NORM && n > 128) {  // row spans several column tiles: normalise in a second pass
         p.act = CBRS_ACT_NONE;
         p.rowop = CBRS_ROWOP_NONE;
-        int rc = launch_dense<128>(p, s);
+        int rc = fast_ok(p) ? launch_dense_fast<128>(p, s) : launch_dense<128>(p, s);
         if (rc) return rc;
         row_l2norm_act_kernel<<<(unsigned)cdiv(m * 32, 256), 256, 0, s>>>(out, ldo, m, n, act);
         CBRS_CHECK_LAUNCH("row_l2norm_act");
         return CBRS_OK;
+    }
+    if (fast_ok(p)) {
+        if (n <= 32) return launch_dense_fast<32>(p, s);
+        if (n <= 64) return launch_dense_fast<64>(p, s);
+        return launch_dense_fast<128>(p, s);
     }
     if (n <= 16) return launch_dense<16>(p, s);
     if (n <= 32) return launch_dense<32>(p, s);

@@ -15,6 +15,8 @@
 //    second kernel adds the partials in ascending chunk order (fixed tree).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace cbrs {
 
 struct SpmmParams {
@@ -77,9 +79,9 @@ struct Vec<1> {
 
 constexpr int kSpmmThreads = 256;
 
-template <int G, int VEC>
-__global__ void __launch_bounds__(kSpmmThreads) spmm_chunk_kernel(const SpmmParams p) {
-    constexpr int U = G < 8 ? G : 8;  // independent row loads in flight per group
+template <int G, int VEC, int UMAX = 4, int MINB = 4>
+__global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const SpmmParams p) {
+    constexpr int U = G < UMAX ? G : UMAX;  // independent row loads in flight per group
     const int64_t gid = ((int64_t)blockIdx.x * kSpmmThreads + threadIdx.x) / G;
     if (gid >= p.n_chunks) return;
     const int lane = threadIdx.x & 31;
@@ -168,11 +170,36 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_heavy_kernel(const SpmmPara
     }
 }
 
+// tuning knob (bench/tuning only): CBRS_SPMM_VARIANT selects loads-in-flight x occupancy for the
+// 128-wide fp32 kernel; the default is the measured best
+static int spmm_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CBRS_SPMM_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 template <int G, int VEC>
 static int launch(const SpmmParams &p, cudaStream_t s) {
     const int64_t threads = p.n_chunks * G;
     if (threads > 0) {
-        spmm_chunk_kernel<G, VEC><<<(unsigned)cdiv(threads, kSpmmThreads), kSpmmThreads, 0, s>>>(p);
+        const unsigned grid = (unsigned)cdiv(threads, kSpmmThreads);
+        if (G == 32 && VEC == 4) {
+            // measured on config 5 (profiles/r01_tune_spmm.log): 4 loads in flight x 32 warps/SM beats
+            // 8 x 16 by 1.45x - occupancy, not per-warp MLP, is what saturates HBM here
+            switch (spmm_variant()) {
+                case 1: spmm_chunk_kernel<32, 4, 8, 2><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 2: spmm_chunk_kernel<32, 4, 8, 4><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 3: spmm_chunk_kernel<32, 4, 2, 8><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 4: spmm_chunk_kernel<32, 4, 4, 5><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 5: spmm_chunk_kernel<32, 4, 2, 6><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                default: spmm_chunk_kernel<32, 4, 4, 4><<<grid, kSpmmThreads, 0, s>>>(p); break;
+            }
+        } else {
+            spmm_chunk_kernel<G, VEC><<<grid, kSpmmThreads, 0, s>>>(p);
+        }
         CBRS_CHECK_LAUNCH("spmm_chunk");
     }
     if (p.n_heavy > 0) {

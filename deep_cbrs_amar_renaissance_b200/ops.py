@@ -225,6 +225,23 @@ def topk_pairs(users, scores, n_users, k):
     return order[rank < k].to(torch.int64)
 
 
+def score_catalog_topk(P, Q, w2, b2, w3, b3, k):
+    """Fused BasicRS catalog scorer: P [U,c1] (bias folded in), Q [I,c1] -> (ids int32 [U,k], scores [U,k])."""
+    lib = L.load()
+    P, ldp = _rowmajor(P)
+    Q, ldq = _rowmajor(Q)
+    n_users, c1 = P.shape
+    n_items = Q.shape[0]
+    c2 = w2.shape[1]
+    ids = torch.empty(n_users, k, dtype=torch.int32, device=P.device)
+    vals = torch.empty(n_users, k, dtype=torch.float32, device=P.device)
+    L.check(lib.cbrs_score_catalog_topk(_ptr(P), ldp, _ptr(Q), ldq, n_users, n_items, c1, _ptr(w2, torch.float32),
+                                        _ptr(b2, torch.float32), c2, _ptr(w3, torch.float32), _ptr(b3, torch.float32),
+                                        k, _ptr(ids), _ptr(vals), _stream()), "cbrs_score_catalog_topk")
+    _count(1)
+    return ids, vals
+
+
 # ------------------------------------------------------------------ misc
 def synth_bipartite(n_users, n_items, n_edges, seed, device):
     lib = L.load()

@@ -179,6 +179,19 @@ int cbrs_topk_pairs(const int64_t *users, const float *scores, int64_t n_pairs, 
                     int32_t *order_out, int32_t *rank_out, void *workspace,
                     size_t workspace_bytes, void *stream);
 
+/* ---- fused full-catalog scorer + top-k for the BasicRS classifier (rows S1/S2 + T) ---------
+ * The caller hoists everything that depends on one entity (cbrs_dense):
+ *   P[u,:] = unet(emb[u]) @ W1[:du] + b1  [n_users, c1]     Q[i,:] = inet(emb[i]) @ W1[du:]  [n_items, c1]
+ * (W1 = first classifier kernel, src/models/basic.py:29,35-36).  Per pair the kernel evaluates
+ *   sigmoid( relu( relu(P[u]+Q[i]) @ W2[c1,c2] + b2 ) . w3 + b3 )
+ * and keeps each user's k best (score desc, lower item index on ties); the score matrix is
+ * never written.  fp32 FFMA (parity 1e-5 with the reference scorer).  c1 % 4 == 0, c1 <= 256,
+ * c2 <= 128, k <= 128.  ids_out / scores_out: [n_users, k], -1 / -inf past the catalog size. */
+int cbrs_score_catalog_topk(const float *P, int64_t ldp, const float *Q, int64_t ldq, int64_t n_users,
+                            int32_t n_items, int32_t c1, const float *w2, const float *b2, int32_t c2,
+                            const float *w3, const float *b3, int32_t k, int32_t *ids_out,
+                            float *scores_out, void *stream);
+
 /* ---- synthetic scaled graph --------------------------------
  * Counter-based generator: edge e connects user hash_u(seed,e) % n_users with an
  * item drawn from a capped Zipf(1) popularity; writes BOTH directions, i.e.

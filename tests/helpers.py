@@ -51,11 +51,13 @@ def assert_topk_equivalent(ids, vals, oracle_scores, k, tol=2e-6):
     assert np.abs(got_vals - ref_vals).max() <= tol, "top-k scores differ beyond tolerance"
     assert np.abs(np.asarray(vals, np.float64) - got_vals).max() <= 1e-5, "returned scores differ from the oracle's"
     sorted_s = -np.sort(-s, axis=1)[:, :k + 1]
+    if sorted_s.shape[1] < k + 1:  # k == catalog size: nothing ranks below the last slot
+        sorted_s = np.concatenate([sorted_s, np.full((len(s), 1), -np.inf)], axis=1)
     gaps = sorted_s[:, :-1] - sorted_s[:, 1:]
     prev_gap = np.concatenate([np.full((len(s), 1), np.inf), gaps[:, :-1]], axis=1)
     clear = (gaps > tol) & (prev_gap > tol)
     assert (ids[clear] == order[clear]).all(), "top-k ids differ where the ranking is unambiguous"
-    return float(clear.mean())
+    return float(clear.mean()) if clear.size else 1.0
 
 
 def export_weights(model):

@@ -333,6 +333,36 @@ def test_top_k_predictions_frame(dev):
     assert df['scores'].tolist() == [0.9, 0.1, 0.8, 0.8, 0.5]
 
 
+@pytest.mark.parametrize("n_users,n_items,c1,c2,k", [(1, 1, 4, 1, 1), (37, 3706, 64, 64, 10), (50, 1000, 48, 48, 5),
+                                                      (16, 333, 64, 128, 128), (70, 2049, 128, 96, 10),
+                                                      (5, 7, 64, 64, 10), (33, 40000, 64, 64, 10)])
+def test_fused_catalog_scorer_matches_oracle(dev, n_users, n_items, c1, c2, k):
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from tests.helpers import assert_topk_equivalent
+    rng = np.random.RandomState(n_items + c2)
+    P = rng.standard_normal((n_users, c1)).astype(np.float32)
+    Q = rng.standard_normal((n_items, c1)).astype(np.float32)
+    if n_items > 100:
+        Q[50:60] = Q[40:50]  # exact duplicates: exact score ties, lower index must win
+    w2, b2 = glorot(rng, (c1, c2)), rng.standard_normal(c2).astype(np.float32) * 0.1
+    w3, b3 = glorot(rng, (c2, 1)).reshape(-1), np.array([0.05], np.float32)
+    ids, vals = ops.score_catalog_topk(_t(P, dev), _t(Q, dev), _t(w2, dev), _t(b2, dev), _t(w3, dev), _t(b3, dev), k)
+    h1 = np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1)
+    h2 = np.maximum(h1 @ w2 + b2, 0)
+    scores = ol.sigmoid(h2 @ w3 + b3).reshape(n_users, n_items)
+    kk = min(k, n_items)
+    ids_np, vals_np = ids.cpu().numpy(), vals.cpu().numpy()
+    assert (ids_np[:, kk:] == -1).all()
+    assert_topk_equivalent(ids_np[:, :kk], vals_np[:, :kk], scores, kk)
+    if n_items > 100:  # among exactly tied duplicates the lower index comes first
+        for u in range(n_users):
+            pos = {int(i): r for r, i in enumerate(ids_np[u, :kk])}
+            for a in range(40, 50):
+                if a in pos and a + 10 in pos:
+                    assert pos[a] < pos[a + 10]
+                assert not (a + 10 in pos and a not in pos)
+
+
 # ------------------------------------------------------------------ synthetic generator
 def _splitmix(x):
     x = (x + np.uint64(0x9E3779B97F4A7C15))

@@ -228,7 +228,8 @@ def test_catalog_top_k_matches_oracle():
     model((np.array([0]), np.array([n_users])))
     _randomise(model, 5)
     model.cache_propagation = True
-    ids, vals = model.recommend_top_k(n_users, n_items, k)
+    ids, vals = model.recommend_top_k(n_users, n_items, k)                 # fused kernel
+    ids_g, vals_g = model.recommend_top_k(n_users, n_items, k, fused=False)  # generic pair pipeline
     w = export_weights(model)
     emb = ol.propagate("gcn", w["embeddings"], og.gcn_filter(adj), w["layers"])
     uu = np.repeat(np.arange(n_users), n_items)
@@ -238,9 +239,10 @@ def test_catalog_top_k_matches_oracle():
     assert clear > 0.95
     dense_scores = catalog_scores(model, model.propagate(), n_users, n_items).cpu().numpy()
     assert_close(dense_scores, oracle_scores, what="catalog scores")
-    # top-k of OUR score matrix is bit-exact with a stable sort of it
+    # the generic path's top-k is bit-exact with a stable sort of its own score matrix
     want_ids, want_vals = ol.top_k_catalog(dense_scores, k)
-    assert np.array_equal(ids.cpu().numpy(), want_ids) and np.array_equal(vals.cpu().numpy(), want_vals)
+    assert np.array_equal(ids_g.cpu().numpy(), want_ids) and np.array_equal(vals_g.cpu().numpy(), want_vals)
+    assert_topk_equivalent(ids_g.cpu().numpy(), vals_g.cpu().numpy(), oracle_scores, k)
     # a user subset gives the same rows
     sub = torch.tensor([5, 17, 399], device="cuda")
     ids2, _ = model.recommend_top_k(n_users, n_items, k, users=sub)
