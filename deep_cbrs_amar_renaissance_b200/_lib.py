@@ -52,6 +52,9 @@ _SIGS = {
     "cbrs_topk_pairs": (c_int, [P, P, c_int64, c_int64, P, P, P, c_size_t, P]),
     "cbrs_score_catalog_topk": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, c_int32, P, P, c_int32,
                                         P, P, P]),
+    "cbrs_score_catalog_topk_bf16_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "cbrs_score_catalog_topk_bf16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, c_int32, P, P,
+                                             c_int32, P, P, P, c_size_t, P]),
     "cbrs_synth_bipartite": (c_int, [c_int64, c_int64, c_int64, c_uint64, P, P, P]),
     "cbrs_sort_workspace_bytes": (c_size_t, [c_int64]),
     "cbrs_sort_pairs_u64": (c_int, [P, P, c_int64, c_int, P, c_size_t, P]),

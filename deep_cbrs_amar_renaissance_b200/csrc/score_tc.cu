@@ -1,0 +1,277 @@
+// bf16 tensor-core catalog scorer + per-user top-k (tcgen05 / TMEM), sm_100a.
+//
+// Same contract as cbrs_score_catalog_topk (score.cu) - BasicRS classifier with the first
+// layer hoisted into P[u] + Q[i] (/root/reference/src/models/basic.py:31-37) - but the
+// per-pair GEMM relu(P[u]+Q[i]) @ W2 runs on the 5th-generation tensor cores:
+//   * a tile is 128 (user,item) pairs = 4 users x 32 items; thread t produces row t of the
+//     A operand, h1 = relu(P[u]+Q[i]) rounded to bf16, straight into shared memory in the
+//     canonical K-major SWIZZLE_128B layout (16-byte chunk c of row r at chunk c ^ (r & 7));
+//   * W2^T (bf16, K-major, pre-swizzled once by a prep kernel) stays resident in shared memory;
+//   * one thread issues ceil(c1/16) tcgen05.mma (M=128, N=c2, K=16) into a TMEM accumulator and
+//     commits to an mbarrier;
+//   * every thread reads its own accumulator row back with tcgen05.ld (warp w owns TMEM lanes
+//     32w..32w+31), applies bias + relu + the output layer + sigmoid and feeds the running
+//     per-user top-k lists (same candidate-list scheme as the fp32 kernel).
+// There is no warp specialisation inside a CTA: 4+ CTAs are resident per SM (TMEM: 64 of 512
+// columns each) and the SM overlaps one CTA's MMA with the others' producer / epilogue phases.
+// Precision: h1 and W2 are bf16, accumulation fp32 => scores differ from the fp32 path by
+// O(1e-3); the parity tests compare against a bf16-rounding oracle (tolerance stated there).
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace cbrs {
+
+struct ScoreTcParams {
+    const float *P; int64_t ldp;
+    const float *Q; int64_t ldq;
+    int64_t n_users; int32_t n_items;
+    int32_t c1, c2;
+    const uint8_t *w2_image;  // [KB][n_pad][128 B] bf16, swizzled
+    const float *b2, *w3, *b3;
+    int32_t k;
+    int32_t *ids_out; float *scores_out;
+};
+
+constexpr int kTcThreads = 128;
+constexpr int kTcTU = 32;  // users per CTA
+constexpr int kTcTI = 32;  // items per tile
+
+__device__ __forceinline__ uint32_t tcs_orderable(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float tcs_from_orderable(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__device__ void tcs_compact(unsigned long long *c, int *cnt, unsigned long long *thr, int k, int lane) {
+    const int n = *cnt;
+    const int keep = n < k ? n : k;
+    for (int r = 0; r < keep; ++r) {
+        unsigned long long best = 0ull;
+        int bi = -1;
+        for (int i = r + lane; i < n; i += 32) {
+            const unsigned long long v = c[i];
+            if (v > best) { best = v; bi = i; }
+        }
+        unsigned long long m = best;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = t > m ? t : m;
+        }
+        if (best == m && bi >= 0) {
+            c[bi] = c[r];
+            c[r] = m;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        *cnt = keep;
+        *thr = (keep == k) ? c[k - 1] : 0ull;
+    }
+    __syncwarp();
+}
+
+// W2 [c1, c2] fp32 (Keras [in,out]) -> B operand image: element (n, k) = bf16(W2[k][n]), K-major, SWIZZLE_128B
+__global__ void score_tc_prep_kernel(const float *__restrict__ w2, int c1, int c2, int n_pad, int kb_count,
+                                     uint8_t *__restrict__ image) {
+    const int total = kb_count * n_pad * 64;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int kb = e / (n_pad * 64), rem = e % (n_pad * 64);
+        const int n = rem / 64, kk = rem % 64;
+        const int kg = kb * 64 + kk;
+        const float v = (n < c2 && kg < c1) ? w2[(int64_t)kg * c2 + n] : 0.f;
+        const uint32_t off = (uint32_t)kb * n_pad * 128 + tc::sw128_offset(n, kk >> 3) + (kk & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16 *>(image + off) = __float2bfloat16_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads) score_tc_kernel(const ScoreTcParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    const int c1 = p.c1;
+    const int kb_count = (c1 + 63) / 64;
+    const int c1p = kb_count * 64;
+    const int n_pad = (p.c2 + 15) / 16 * 16;
+    const int cap = 2 * p.k + kTcTI;
+    // carve shared memory (operand tiles first: SWIZZLE_128B needs 1024-byte alignment)
+    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *As = base;                                   // [kb][128][128 B]
+    unsigned char *Bs = As + kb_count * 16384;                  // [kb][n_pad][128 B]
+    float *Ps = reinterpret_cast<float *>(Bs + kb_count * n_pad * 128);  // [TU][c1p]
+    float2 *bw = reinterpret_cast<float2 *>(Ps + kTcTU * c1p);  // [n_pad] (b2, w3)
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(bw + n_pad);  // [TU][cap]
+    unsigned long long *thr = cand + kTcTU * cap;               // [TU]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + kTcTU);
+    int *cnt = reinterpret_cast<int *>(mbar + 1);               // [TU]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(cnt + kTcTU);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t u0 = (int64_t)blockIdx.x * kTcTU;
+    const float b3 = __ldg(p.b3);
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < n_pad) tmem_cols <<= 1;
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (tid == 0) {
+        tc::mbar_init(mbar, 1);
+        tc::fence_mbar_init();
+    }
+    {   // resident operands
+        const int4 *src = reinterpret_cast<const int4 *>(p.w2_image);
+        int4 *dst = reinterpret_cast<int4 *>(Bs);
+        for (int e = tid; e < kb_count * n_pad * 8; e += kTcThreads) dst[e] = __ldg(src + e);
+        for (int e = tid; e < n_pad; e += kTcThreads)
+            bw[e] = e < p.c2 ? make_float2(__ldg(p.b2 + e), __ldg(p.w3 + e)) : make_float2(0.f, 0.f);
+        for (int e = tid; e < kTcTU * c1p; e += kTcThreads) {
+            const int ul = e / c1p, kk = e % c1p;
+            Ps[e] = (kk < c1 && u0 + ul < p.n_users) ? __ldg(p.P + (u0 + ul) * p.ldp + kk) : 0.f;
+        }
+        if (tid < kTcTU) { cnt[tid] = 0; thr[tid] = 0ull; }
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's lane quadrant
+    const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs);
+    const uint32_t idesc = tc::idesc_bf16_f32(128, n_pad);
+    const int k_steps = (c1 + 15) / 16;       // MMAs per tile (K = 16 each)
+    const int chunks = k_steps * 2;           // 16-byte chunks a producer row writes
+    uint32_t phase = 0;
+
+    for (int t0 = 0; t0 < p.n_items; t0 += kTcTI) {
+        for (int ul = warp; ul < kTcTU; ul += kTcThreads / 32)   // user ul is always handled by warp ul % 4
+            if (cnt[ul] > cap - kTcTI) tcs_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
+        const int item = t0 + lane;
+        const bool item_ok = item < p.n_items;
+        const float *qrow = p.Q + (int64_t)(item_ok ? item : 0) * p.ldq;
+        for (int pass = 0; pass < kTcTU / 4; ++pass) {
+            const int ul = pass * 4 + warp;
+            // ---- producer: row `tid` of the A tile ------------------------------------------
+            const float *prow = Ps + ul * c1p;
+#pragma unroll 2
+            for (int cg = 0; cg < chunks; ++cg) {
+                const int kk = cg * 8;
+                uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+                if (kk < c1 && item_ok) {
+                    const float4 q0 = ldg4(qrow + kk), q1 = ldg4(qrow + kk + 4);
+                    const float4 p0 = *reinterpret_cast<const float4 *>(prow + kk);
+                    const float4 p1 = *reinterpret_cast<const float4 *>(prow + kk + 4);
+                    packed.x = tc::pack_bf16x2(fmaxf(p0.x + q0.x, 0.f), fmaxf(p0.y + q0.y, 0.f));
+                    packed.y = tc::pack_bf16x2(fmaxf(p0.z + q0.z, 0.f), fmaxf(p0.w + q0.w, 0.f));
+                    packed.z = tc::pack_bf16x2(fmaxf(p1.x + q1.x, 0.f), fmaxf(p1.y + q1.y, 0.f));
+                    packed.w = tc::pack_bf16x2(fmaxf(p1.z + q1.z, 0.f), fmaxf(p1.w + q1.w, 0.f));
+                }
+                *reinterpret_cast<uint4 *>(As + (cg >> 3) * 16384 + tc::sw128_offset(tid, cg & 7)) = packed;
+            }
+            tc::fence_proxy_async_smem();   // my generic-proxy stores -> visible to the tensor core
+            tc::tc_fence_before_sync();     // my previous tcgen05.ld -> ordered before the next MMA
+            __syncthreads();
+            // ---- MMA: one thread ---------------------------------------------------------------
+            if (tid == 0) {
+                tc::tc_fence_after_sync();
+                for (int s = 0; s < k_steps; ++s) {
+                    const uint32_t koff = (uint32_t)(s & 3) * 32;  // 16 bf16 = 32 bytes inside the swizzle atom
+                    const uint64_t da = tc::smem_desc_sw128(a_addr + (s >> 2) * 16384 + koff);
+                    const uint64_t db = tc::smem_desc_sw128(b_addr + (s >> 2) * n_pad * 128 + koff);
+                    tc::mma_bf16_ss(tmem_base, da, db, idesc, s > 0 ? 1u : 0u);
+                }
+                tc::mma_commit(mbar);
+            }
+            tc::mbar_wait(mbar, phase);
+            phase ^= 1u;
+            tc::tc_fence_after_sync();
+            // ---- epilogue: accumulator row `tid` -> logit -> sigmoid -> candidate ----------------
+            float logit = 0.f;
+            for (int cb = 0; cb < n_pad; cb += 16) {
+                uint32_t v[16];
+                tc::tmem_ld16(tmem_row + (uint32_t)cb, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float2 t = bw[cb + j];
+                    logit = fmaf(fmaxf(__uint_as_float(v[j]) + t.x, 0.f), t.y, logit);
+                }
+            }
+            const int64_t user = u0 + ul;
+            if (item_ok && user < p.n_users) {
+                const float score = 1.f / (1.f + expf(-(logit + b3)));
+                const unsigned long long key =
+                    ((unsigned long long)tcs_orderable(score) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)item);
+                if (key > thr[ul]) {
+                    const int pos = atomicAdd(cnt + ul, 1);
+                    cand[ul * cap + pos] = key;
+                }
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc::tc_fence_after_sync();
+        tc::tmem_dealloc(tmem_base, tmem_cols);
+    }
+    for (int ul = warp; ul < kTcTU; ul += kTcThreads / 32) {
+        tcs_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
+        const int64_t user = u0 + ul;
+        if (user >= p.n_users) continue;
+        const int n = cnt[ul];
+        for (int r = lane; r < p.k; r += 32) {
+            const int64_t o = user * p.k + r;
+            if (r < n) {
+                const unsigned long long key = cand[ul * cap + r];
+                p.ids_out[o] = (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+                p.scores_out[o] = tcs_from_orderable((uint32_t)(key >> 32));
+            } else {
+                p.ids_out[o] = -1;
+                p.scores_out[o] = -INFINITY;
+            }
+        }
+    }
+}
+
+static size_t score_tc_smem(int c1, int c2, int k) {
+    const int kb = (c1 + 63) / 64, n_pad = (c2 + 15) / 16 * 16, cap = 2 * k + kTcTI;
+    return 1024 + (size_t)kb * 16384 + (size_t)kb * n_pad * 128 + (size_t)kTcTU * kb * 64 * 4 + (size_t)n_pad * 8 +
+           (size_t)kTcTU * cap * 8 + kTcTU * 8 + 8 + kTcTU * 4 + 16;
+}
+
+}  // namespace cbrs
+
+using namespace cbrs;
+
+extern "C" size_t cbrs_score_catalog_topk_bf16_workspace_bytes(int32_t c1, int32_t c2) {
+    const int kb = (c1 + 63) / 64, n_pad = (c2 + 15) / 16 * 16;
+    return align_up((size_t)kb * n_pad * 128);
+}
+
+extern "C" int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const float *Q, int64_t ldq, int64_t n_users,
+                                            int32_t n_items, int32_t c1, const float *w2, const float *b2, int32_t c2,
+                                            const float *w3, const float *b3, int32_t k, int32_t *ids_out,
+                                            float *scores_out, void *workspace, size_t workspace_bytes, void *stream) {
+    CBRS_REQUIRE(P && Q && w2 && b2 && w3 && b3 && ids_out && scores_out, CBRS_E_INVALID, "score_catalog_bf16: null argument");
+    CBRS_REQUIRE(n_users >= 0 && n_items > 0 && k > 0 && k <= 128, CBRS_E_INVALID, "score_catalog_bf16: n_users=%lld n_items=%d k=%d",
+                 (long long)n_users, n_items, k);
+    CBRS_REQUIRE(c1 >= 8 && c1 % 8 == 0 && c1 <= 256 && c2 > 0 && c2 <= 256, CBRS_E_UNSUPPORTED,
+                 "score_catalog_bf16: classifier widths c1=%d (multiple of 8, <= 256), c2=%d (<= 256)", c1, c2);
+    CBRS_REQUIRE(ldp >= c1 && ldq >= c1 && ldq % 4 == 0 && ((uintptr_t)Q % 16) == 0, CBRS_E_INVALID,
+                 "score_catalog_bf16: Q must be 16-byte aligned with ldq %% 4 == 0");
+    const size_t need = cbrs_score_catalog_topk_bf16_workspace_bytes(c1, c2);
+    CBRS_REQUIRE(workspace && workspace_bytes >= need && ((uintptr_t)workspace % 16) == 0, CBRS_E_WORKSPACE,
+                 "score_catalog_bf16: workspace %zu < %zu bytes", workspace_bytes, need);
+    if (n_users == 0) return CBRS_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int kb = (c1 + 63) / 64, n_pad = (c2 + 15) / 16 * 16;
+    score_tc_prep_kernel<<<32, 256, 0, s>>>(w2, c1, c2, n_pad, kb, (uint8_t *)workspace);
+    CBRS_CHECK_LAUNCH("score_tc_prep");
+    const size_t smem = score_tc_smem(c1, c2, k);
+    CBRS_REQUIRE(smem <= 220 * 1024, CBRS_E_UNSUPPORTED, "score_catalog_bf16: needs %zu bytes of shared memory", smem);
+    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "score_catalog_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    ScoreTcParams p{P, ldp, Q, ldq, n_users, n_items, c1, c2, (const uint8_t *)workspace, b2, w3, b3, k, ids_out, scores_out};
+    score_tc_kernel<<<(unsigned)cdiv(n_users, kTcTU), kTcThreads, smem, s>>>(p);
+    CBRS_CHECK_LAUNCH("score_tc");
+    return CBRS_OK;
+}

@@ -101,13 +101,22 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const Sp
         const float *xcol = p.x + (col_ok ? col : 0);
         Vec<VEC> acc;
         acc.zero();
+        // (col,val) of the next G edges are fetched while the current G rows are in flight
+        int c_next = 0;
+        float v_next = 0.f;
+        if (b + lg < e) {
+            c_next = ld_stream_i32(p.colidx + b + lg);
+            v_next = weighted ? ld_stream_f32(p.vals + b + lg) : 1.f;
+        }
         for (int64_t base = b; base < e; base += G) {
-            const int64_t idx = base + lg;
-            int c = 0;
-            float v = 0.f;
-            if (idx < e) {
-                c = ld_stream_i32(p.colidx + idx);
-                v = weighted ? ld_stream_f32(p.vals + idx) : 1.f;
+            const int c = c_next;
+            const float v = v_next;
+            const int64_t nidx = base + G + lg;
+            c_next = 0;
+            v_next = 0.f;
+            if (nidx < e) {
+                c_next = ld_stream_i32(p.colidx + nidx);
+                v_next = weighted ? ld_stream_f32(p.vals + nidx) : 1.f;
             }
             const int cnt = (e - base < G) ? (int)(e - base) : G;
 #pragma unroll

@@ -118,9 +118,9 @@ class HybridBertGNN(Model, abc.ABC):
         return self.rs.call_sources((embeddings, _ids(ug)), (embeddings, _ids(ig)), (_rows(ub), None),
                                     (_rows(ib), None))
 
-    def recommend_top_k(self, n_users, n_items, k=10, users=None, user_block=None, fused=True):
+    def recommend_top_k(self, n_users, n_items, k=10, users=None, user_block=None, fused=True, precision="fp32"):
         from ..scoring import catalog_top_k
-        return catalog_top_k(self, self.propagate(), n_users, n_items, k, users, user_block, fused)
+        return catalog_top_k(self, self.propagate(), n_users, n_items, k, users, user_block, fused, precision)
 
 
 def BasicGNNFactory(name, Parent, GNN):

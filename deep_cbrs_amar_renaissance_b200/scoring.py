@@ -68,7 +68,7 @@ def catalog_scores(model, emb, n_users, n_items, users=None):
     return out
 
 
-def _fused_basic(model, emb, users, items, k):
+def _fused_basic(model, emb, users, items, k, precision="fp32"):
     """BasicRS with two hidden classifier layers -> the fused kernel (cbrs_score_catalog_topk)."""
     rs = model.rs
     if not hasattr(rs, "unet") or len(rs.clf.layers) != 3 or k > 128:
@@ -76,7 +76,7 @@ def _fused_basic(model, emb, users, items, k):
     l1, l2, l3 = rs.clf.layers
     if l1.activation != "relu" or l2.activation != "relu" or l3.units != 1:
         return None
-    if l1.units % 4 or l1.units > 256 or l2.units > 128:
+    if l1.units % 8 or l1.units > 256 or l2.units > 128:
         return None
     if rs.unet.layers:
         ut = rs.unet.call_sources([(emb, users)])
@@ -90,15 +90,15 @@ def _fused_basic(model, emb, users, items, k):
     l3.build_for(l2.units)
     P = ops.dense(u_src[0], l1.kernel[:du], l1.bias, None, idx1=u_src[1])   # bias folded into the user half
     Q = ops.dense(i_src[0], l1.kernel[du:], None, None, idx1=i_src[1])
-    return ops.score_catalog_topk(P, Q, l2.kernel, l2.bias, l3.kernel.reshape(-1), l3.bias, k)
+    return ops.score_catalog_topk(P, Q, l2.kernel, l2.bias, l3.kernel.reshape(-1), l3.bias, k, precision)
 
 
-def catalog_top_k(model, emb, n_users, n_items, k=10, users=None, user_block=None, fused=True):
+def catalog_top_k(model, emb, n_users, n_items, k=10, users=None, user_block=None, fused=True, precision="fp32"):
     dev = emb.device
     users = torch.arange(n_users, device=dev, dtype=torch.int64) if users is None else users.to(dev, torch.int64)
     items = torch.arange(n_users, n_users + n_items, device=dev, dtype=torch.int64)
     if fused:
-        out = _fused_basic(model, emb, users, items, k)
+        out = _fused_basic(model, emb, users, items, k, precision)
         if out is not None:
             return out
     score = _pair_scorer(model, emb, users, items)

@@ -49,7 +49,7 @@ def assert_topk_equivalent(ids, vals, oracle_scores, k, tol=2e-6):
     ids = np.asarray(ids)
     got_vals = np.take_along_axis(s, ids.astype(np.int64), axis=1)
     assert np.abs(got_vals - ref_vals).max() <= tol, "top-k scores differ beyond tolerance"
-    assert np.abs(np.asarray(vals, np.float64) - got_vals).max() <= 1e-5, "returned scores differ from the oracle's"
+    assert np.abs(np.asarray(vals, np.float64) - got_vals).max() <= max(tol, 1e-5), "returned scores differ from the oracle's"
     sorted_s = -np.sort(-s, axis=1)[:, :k + 1]
     if sorted_s.shape[1] < k + 1:  # k == catalog size: nothing ranks below the last slot
         sorted_s = np.concatenate([sorted_s, np.full((len(s), 1), -np.inf)], axis=1)

@@ -363,6 +363,41 @@ def test_fused_catalog_scorer_matches_oracle(dev, n_users, n_items, c1, c2, k):
                 assert not (a + 10 in pos and a not in pos)
 
 
+def _bf16_round(x):
+    """round-to-nearest-even fp32 -> bf16 -> fp32 (numpy)"""
+    u = np.asarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("n_users,n_items,c1,c2,k", [(37, 3706, 64, 64, 10), (50, 1000, 48, 48, 5), (5, 7, 64, 64, 10),
+                                                      (40, 333, 128, 128, 20), (130, 2049, 64, 32, 10),
+                                                      (33, 500, 8, 16, 3), (20, 700, 72, 80, 10)])
+def test_tensor_core_catalog_scorer_matches_bf16_oracle(dev, n_users, n_items, c1, c2, k):
+    """tcgen05 path: operands rounded to bf16, fp32 accumulate.  Oracle = the same rounding in numpy;
+    tolerance 2e-5 on scores (fp32 summation order inside the MMA is unspecified)."""
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from tests.helpers import assert_topk_equivalent
+    rng = np.random.RandomState(n_items + c2)
+    P = rng.standard_normal((n_users, c1)).astype(np.float32)
+    Q = rng.standard_normal((n_items, c1)).astype(np.float32)
+    w2, b2 = glorot(rng, (c1, c2)), rng.standard_normal(c2).astype(np.float32) * 0.1
+    w3, b3 = glorot(rng, (c2, 1)).reshape(-1), np.array([0.05], np.float32)
+    ids, vals = ops.score_catalog_topk(_t(P, dev), _t(Q, dev), _t(w2, dev), _t(b2, dev), _t(w3, dev), _t(b3, dev), k,
+                                       precision="bf16")
+    h1 = _bf16_round(np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1))
+    h2 = np.maximum(h1.astype(np.float64) @ _bf16_round(w2).astype(np.float64) + b2, 0).astype(np.float32)
+    scores = ol.sigmoid(h2 @ w3 + b3).reshape(n_users, n_items)
+    kk = min(k, n_items)
+    ids_np, vals_np = ids.cpu().numpy(), vals.cpu().numpy()
+    assert (ids_np[:, kk:] == -1).all()
+    assert_topk_equivalent(ids_np[:, :kk], vals_np[:, :kk], scores, kk, tol=2e-5)
+    # and it stays within bf16 distance of the exact fp32 scorer
+    exact = ol.sigmoid(np.maximum(np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1) @ w2 + b2, 0) @ w3 + b3)
+    got_exact = np.take_along_axis(exact.reshape(n_users, n_items), ids_np[:, :kk].astype(np.int64), axis=1)
+    assert np.abs(got_exact - vals_np[:, :kk]).max() < 2e-2
+
+
 # ------------------------------------------------------------------ synthetic generator
 def _splitmix(x):
     x = (x + np.uint64(0x9E3779B97F4A7C15))
