@@ -106,6 +106,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(scale, world):
+    """dram bytes per SpMM launch from the committed ncu --set full capture (same workload, 1 GPU only)."""
+    if scale != "c5" or world != 1:
+        return None
+    try:
+        return json.load(open(os.path.join(REPO, "profiles", "r01_spmm_ncu.json")))["traffic_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def workload_config(scale, gpus):
     n_users, n_items, n_edges = SCALES[scale]
     return {"workload": "%s scaled synthetic bipartite graph, BasicGCN %d layers dim %d fp32, concatenation, "
@@ -269,7 +279,7 @@ def run_b200(args):
     alg_bytes = local_nnz * (8 + DIM * 4) + (rows_local / calls_per_layer) * (DIM * 4 + 8)
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "spmm_chunk_kernel<32,4> (+heavy-row merge)", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(args.scale, world),
                 "peak_source": peak_src, "launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_edge": 8 + DIM * 4, "launches_timed": len(spmm_ms),
                 "share_of_step": (sum(spmm_ms) / args.steps) / ms_per_step if spmm_ms else None}
@@ -281,6 +291,11 @@ def run_b200(args):
     users = torch.arange(u_lo, u_lo + cu, device=dev)
     cat_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users), 1, 1)
     pairs_per_s = world * cu * n_items / (cat_ms * 1e-3)
+    # bf16 tensor-core scorer (tcgen05): more users per launch so the grid fills the chip
+    cu_tc = min(args.catalog_users * 8, u_hi - u_lo)
+    users_tc = torch.arange(u_lo, u_lo + cu_tc, device=dev)
+    tc_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users_tc, precision="bf16"), 1, 1)
+    pairs_tc = world * cu_tc * n_items / (tc_ms * 1e-3)
     model.cache_propagation = False
     model.invalidate()
 
@@ -298,7 +313,10 @@ def run_b200(args):
                 "d2h_bytes_per_step": PAIR_BATCH * 4, "ms_per_step": ms_e2e / args.steps},
         "roofline": roofline,
         "pairs": {"value": pairs_per_s, "unit": "pairs/s", "what": "full-catalog BasicRS scoring + top-10, %d users x %d items per rank" % (cu, n_items),
-                  "ms": cat_ms},
+                  "ms": cat_ms,
+                  "bf16_tcgen05": {"value": pairs_tc, "unit": "pairs/s", "users_per_rank": cu_tc, "ms": tc_ms,
+                                   "tensor_flops_per_pair": 2 * CLF_UNITS[0] * CLF_UNITS[1],
+                                   "frac_of_bf16_peak": pairs_tc / world * 2 * CLF_UNITS[0] * CLF_UNITS[1] / 1e12 / (peaks.get("bf16_tflops_sustained") or 1398.0)}},
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

@@ -33,7 +33,7 @@ struct ScoreTcParams {
 };
 
 constexpr int kTcThreads = 128;
-constexpr int kTcTU = 32;  // users per CTA
+constexpr int kTcTU = 16;  // users per CTA (4 passes of 4 users per item tile)
 constexpr int kTcTI = 32;  // items per tile
 
 __device__ __forceinline__ uint32_t tcs_orderable(float f) {
@@ -87,16 +87,21 @@ __global__ void score_tc_prep_kernel(const float *__restrict__ w2, int c1, int c
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads) score_tc_kernel(const ScoreTcParams p) {
-    extern __shared__ unsigned char smem_raw[];
+// QREG: the classifier's first width fits one 64-wide K block, so a thread keeps its item's Q row
+// (64 floats) in registers for all passes of a tile and refills it while the last pass's MMA and
+// epilogue are in flight; otherwise Q chunks are re-read (L1) in every pass.
+template <bool QREG>
+__global__ void __launch_bounds__(kTcThreads, QREG ? 4 : 3) score_tc_kernel(const ScoreTcParams p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
     const int c1 = p.c1;
     const int kb_count = (c1 + 63) / 64;
     const int c1p = kb_count * 64;
     const int n_pad = (p.c2 + 15) / 16 * 16;
     const int cap = 2 * p.k + kTcTI;
     // carve shared memory (operand tiles first: SWIZZLE_128B needs 1024-byte alignment)
-    unsigned char *base = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char *As = base;                                   // [kb][128][128 B]
+    // (pointers are derived from the __shared__ array without integer round-trips so that the
+    //  compiler keeps them in the shared address space: LDS/STS, not generic LD/ST)
+    unsigned char *As = smem_raw;                               // [kb][128][128 B]
     unsigned char *Bs = As + kb_count * 16384;                  // [kb][n_pad][128 B]
     float *Ps = reinterpret_cast<float *>(Bs + kb_count * n_pad * 128);  // [TU][c1p]
     float2 *bw = reinterpret_cast<float2 *>(Ps + kTcTU * c1p);  // [n_pad] (b2, w3)
@@ -136,10 +141,24 @@ __global__ void __launch_bounds__(kTcThreads) score_tc_kernel(const ScoreTcParam
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's lane quadrant
     const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs);
+    if ((a_addr & 1023u) != 0u) __trap();  // the runtime honours the declared alignment; fail loudly if not
     const uint32_t idesc = tc::idesc_bf16_f32(128, n_pad);
     const int k_steps = (c1 + 15) / 16;       // MMAs per tile (K = 16 each)
     const int chunks = k_steps * 2;           // 16-byte chunks a producer row writes
     uint32_t phase = 0;
+
+    float4 qreg[QREG ? 16 : 1];
+    auto load_q = [&](int t0) {
+        if (QREG) {
+            const int it = t0 + lane;
+            const bool ok = it < p.n_items;
+            const float *qr = p.Q + (int64_t)(ok ? it : 0) * p.ldq;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                qreg[QREG ? j : 0] = (ok && j * 4 < c1) ? ldg4(qr + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    load_q(0);
 
     for (int t0 = 0; t0 < p.n_items; t0 += kTcTI) {
         for (int ul = warp; ul < kTcTU; ul += kTcThreads / 32)   // user ul is always handled by warp ul % 4
@@ -151,20 +170,39 @@ __global__ void __launch_bounds__(kTcThreads) score_tc_kernel(const ScoreTcParam
             const int ul = pass * 4 + warp;
             // ---- producer: row `tid` of the A tile ------------------------------------------
             const float *prow = Ps + ul * c1p;
-#pragma unroll 2
-            for (int cg = 0; cg < chunks; ++cg) {
-                const int kk = cg * 8;
-                uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-                if (kk < c1 && item_ok) {
-                    const float4 q0 = ldg4(qrow + kk), q1 = ldg4(qrow + kk + 4);
-                    const float4 p0 = *reinterpret_cast<const float4 *>(prow + kk);
-                    const float4 p1 = *reinterpret_cast<const float4 *>(prow + kk + 4);
-                    packed.x = tc::pack_bf16x2(fmaxf(p0.x + q0.x, 0.f), fmaxf(p0.y + q0.y, 0.f));
-                    packed.y = tc::pack_bf16x2(fmaxf(p0.z + q0.z, 0.f), fmaxf(p0.w + q0.w, 0.f));
-                    packed.z = tc::pack_bf16x2(fmaxf(p1.x + q1.x, 0.f), fmaxf(p1.y + q1.y, 0.f));
-                    packed.w = tc::pack_bf16x2(fmaxf(p1.z + q1.z, 0.f), fmaxf(p1.w + q1.w, 0.f));
+            if (QREG) {
+#pragma unroll
+                for (int cg = 0; cg < 8; ++cg) {
+                    if (cg < chunks) {
+                        const float4 q0 = qreg[QREG ? 2 * cg : 0], q1 = qreg[QREG ? 2 * cg + 1 : 0];
+                        const float4 p0 = *reinterpret_cast<const float4 *>(prow + cg * 8);
+                        const float4 p1 = *reinterpret_cast<const float4 *>(prow + cg * 8 + 4);
+                        uint4 packed;
+                        packed.x = tc::pack_bf16x2(fmaxf(p0.x + q0.x, 0.f), fmaxf(p0.y + q0.y, 0.f));
+                        packed.y = tc::pack_bf16x2(fmaxf(p0.z + q0.z, 0.f), fmaxf(p0.w + q0.w, 0.f));
+                        packed.z = tc::pack_bf16x2(fmaxf(p1.x + q1.x, 0.f), fmaxf(p1.y + q1.y, 0.f));
+                        packed.w = tc::pack_bf16x2(fmaxf(p1.z + q1.z, 0.f), fmaxf(p1.w + q1.w, 0.f));
+                        if (!item_ok) packed = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4 *>(As + tc::sw128_offset(tid, cg)) = packed;
+                    }
                 }
-                *reinterpret_cast<uint4 *>(As + (cg >> 3) * 16384 + tc::sw128_offset(tid, cg & 7)) = packed;
+                if (pass == kTcTU / 4 - 1) load_q(t0 + kTcTI);  // refill under this pass's MMA + epilogue
+            } else {
+#pragma unroll 2
+                for (int cg = 0; cg < chunks; ++cg) {
+                    const int kk = cg * 8;
+                    uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+                    if (kk < c1 && item_ok) {
+                        const float4 q0 = ldg4(qrow + kk), q1 = ldg4(qrow + kk + 4);
+                        const float4 p0 = *reinterpret_cast<const float4 *>(prow + kk);
+                        const float4 p1 = *reinterpret_cast<const float4 *>(prow + kk + 4);
+                        packed.x = tc::pack_bf16x2(fmaxf(p0.x + q0.x, 0.f), fmaxf(p0.y + q0.y, 0.f));
+                        packed.y = tc::pack_bf16x2(fmaxf(p0.z + q0.z, 0.f), fmaxf(p0.w + q0.w, 0.f));
+                        packed.z = tc::pack_bf16x2(fmaxf(p1.x + q1.x, 0.f), fmaxf(p1.y + q1.y, 0.f));
+                        packed.w = tc::pack_bf16x2(fmaxf(p1.z + q1.z, 0.f), fmaxf(p1.w + q1.w, 0.f));
+                    }
+                    *reinterpret_cast<uint4 *>(As + (cg >> 3) * 16384 + tc::sw128_offset(tid, cg & 7)) = packed;
+                }
             }
             tc::fence_proxy_async_smem();   // my generic-proxy stores -> visible to the tensor core
             tc::tc_fence_before_sync();     // my previous tcgen05.ld -> ordered before the next MMA
@@ -185,21 +223,29 @@ __global__ void __launch_bounds__(kTcThreads) score_tc_kernel(const ScoreTcParam
             tc::tc_fence_after_sync();
             // ---- epilogue: accumulator row `tid` -> logit -> sigmoid -> candidate ----------------
             float logit = 0.f;
-            for (int cb = 0; cb < n_pad; cb += 16) {
-                uint32_t v[16];
-                tc::tmem_ld16(tmem_row + (uint32_t)cb, v);
+            for (int cb = 0; cb < n_pad; cb += 32) {
+                uint32_t v0[16], v1[16];
+                tc::tmem_ld16(tmem_row + (uint32_t)cb, v0);
+                if (cb + 16 < n_pad) tc::tmem_ld16(tmem_row + (uint32_t)cb + 16, v1);
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float2 t = bw[cb + j];
-                    logit = fmaf(fmaxf(__uint_as_float(v[j]) + t.x, 0.f), t.y, logit);
+                    logit = fmaf(fmaxf(__uint_as_float(v0[j]) + t.x, 0.f), t.y, logit);
+                }
+                if (cb + 16 < n_pad) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float2 t = bw[cb + 16 + j];
+                        logit = fmaf(fmaxf(__uint_as_float(v1[j]) + t.x, 0.f), t.y, logit);
+                    }
                 }
             }
             const int64_t user = u0 + ul;
             if (item_ok && user < p.n_users) {
-                const float score = 1.f / (1.f + expf(-(logit + b3)));
+                // candidates are ranked by the logit (sigmoid is monotonic); the sigmoid is applied to the k winners
                 const unsigned long long key =
-                    ((unsigned long long)tcs_orderable(score) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)item);
+                    ((unsigned long long)tcs_orderable(logit + b3) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)item);
                 if (key > thr[ul]) {
                     const int pos = atomicAdd(cnt + ul, 1);
                     cand[ul * cap + pos] = key;
@@ -223,7 +269,7 @@ __global__ void __launch_bounds__(kTcThreads) score_tc_kernel(const ScoreTcParam
             if (r < n) {
                 const unsigned long long key = cand[ul * cap + r];
                 p.ids_out[o] = (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
-                p.scores_out[o] = tcs_from_orderable((uint32_t)(key >> 32));
+                p.scores_out[o] = 1.f / (1.f + expf(-tcs_from_orderable((uint32_t)(key >> 32))));
             } else {
                 p.ids_out[o] = -1;
                 p.scores_out[o] = -INFINITY;
@@ -268,10 +314,15 @@ extern "C" int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const f
     CBRS_CHECK_LAUNCH("score_tc_prep");
     const size_t smem = score_tc_smem(c1, c2, k);
     CBRS_REQUIRE(smem <= 220 * 1024, CBRS_E_UNSUPPORTED, "score_catalog_bf16: needs %zu bytes of shared memory", smem);
-    cudaError_t e = cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "score_catalog_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     ScoreTcParams p{P, ldp, Q, ldq, n_users, n_items, c1, c2, (const uint8_t *)workspace, b2, w3, b3, k, ids_out, scores_out};
-    score_tc_kernel<<<(unsigned)cdiv(n_users, kTcTU), kTcThreads, smem, s>>>(p);
+    const bool qreg = c1 <= 64;
+    cudaError_t e = qreg ? cudaFuncSetAttribute(score_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                         : cudaFuncSetAttribute(score_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "score_catalog_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (qreg)
+        score_tc_kernel<true><<<(unsigned)cdiv(n_users, kTcTU), kTcThreads, smem, s>>>(p);
+    else
+        score_tc_kernel<false><<<(unsigned)cdiv(n_users, kTcTU), kTcThreads, smem, s>>>(p);
     CBRS_CHECK_LAUNCH("score_tc");
     return CBRS_OK;
 }
