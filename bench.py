@@ -260,6 +260,9 @@ def run_b200(args):
     clocks = sampler.stop(t0, t1) if sampler else None
     spmm_ms = [a.elapsed_time(b) for (name, a, b, _) in ops.PROFILE if name == "spmm"]
     spmm_edges = [meta for (name, _, _, meta) in ops.PROFILE if name == "spmm"]
+    breakdown = {}
+    for (name, a, b, _) in ops.PROFILE:
+        breakdown[name] = breakdown.get(name, 0.0) + a.elapsed_time(b) / args.steps
     ms_per_step = ms / args.steps
     value = LAYERS * nnz_total / (ms_per_step * 1e-3)
 
@@ -309,6 +312,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.scale, world),
         "edges_per_s_per_gpu": value / world, "nnz_a_hat": nnz_total, "heavy_rows": heavy,
         "graph_build_s": build_s, "gpu_launches": launches, "clocks": clocks,
+        "step_breakdown_ms": breakdown,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": 2 * PAIR_BATCH * 8,
                 "d2h_bytes_per_step": PAIR_BATCH * 4, "ms_per_step": ms_e2e / args.steps},
         "roofline": roofline,

@@ -65,8 +65,11 @@ class RowPartition:
     After the last layer only the node types in `final_types` (default: everything but users)
     are exchanged, because scoring is sharded by user."""
 
-    def __init__(self, n_rows_by_type, group=None, final_types=None):
+    def __init__(self, n_rows_by_type, group=None, final_types=None, col_splits=4):
         self.group = group
+        import os
+        self.col_splits = int(os.environ.get("CBRS_COL_SPLITS", col_splits))  # GCN: the all-gather of column block s+1 overlaps the SpMM of block s
+        self._comm = None
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.ranges = block_ranges(n_rows_by_type, self.world)
@@ -99,8 +102,50 @@ class RowPartition:
         return self._bufs[key]
 
     def _exchange(self, x, types=None):
+        from . import ops
         ranges = self.ranges if types is None else [[rg[t] for t in types] for rg in self.ranges]
+        if ops.PROFILE_ON:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            exchange_rows(x, ranges, self.group)
+            e1.record()
+            ops.PROFILE.append(("exchange", e0, e1, x.numel() * 4))
+            return x
         return exchange_rows(x, ranges, self.group)
+
+    def _pipelined_ok(self, layer):
+        return self.col_splits > 1 and layer.channels % (4 * self.col_splits) == 0
+
+    def _gcn_pipelined(self, layer, l, x_full, out, graph, relu):
+        """GCN layer with the exchange hidden behind the sparse kernel: Z = X W is produced and
+        all-gathered in `col_splits` column blocks on a side stream, and the SpMM of block s runs
+        while block s+1 is still on the wire.  Columns are independent, so the bits are the same
+        as the unsplit layer's."""
+        from . import ops
+        n, dev = x_full.shape[0], x_full.device
+        S, hs = self.col_splits, layer.channels // self.col_splits
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        zs = [self._buf(("zs", l, s), n, hs, dev) for s in range(S)]
+        ready = []
+        for s in range(S):
+            w_s = layer.kernel[:, s * hs:(s + 1) * hs].contiguous()
+            for a, b in self.mine:
+                ops.dense(x_full[a:b], w_s, out=zs[s][a:b])
+            produced = torch.cuda.Event()
+            produced.record(main)
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(produced)
+                self._exchange(zs[s])
+                done = torch.cuda.Event()
+                done.record(self._comm)
+            ready.append(done)
+        for s in range(S):
+            main.wait_event(ready[s])
+            bias = layer.bias[s * hs:(s + 1) * hs] if layer.bias is not None else None
+            for sl in self.csr_slices("norm", graph):
+                ops.spmm(sl, zs[s], out[sl.row_offset:sl.row_offset + sl.n_rows, s * hs:(s + 1) * hs], bias=bias, relu=relu)
 
     def propagate(self, seq):
         """SequentialGNN.call on the partition.  Returns [N, D_out]; rows of other ranks' users
@@ -114,13 +159,28 @@ class RowPartition:
         graph = seq.adj_matrix
         x_full, x_full_valid = emb, True   # the layer input; valid on all rows?
         hs = [emb]
+        # with 'concatenation' and layers that exchange their own operand (GCN/RGCN/GAT) the outputs go
+        # straight into column slices of one [N, D_out] buffer, as on a single GPU
+        concat = seq.final_node == 'concatenation' and all(isinstance(ly, (GCNConv, RGCNConv, GATConv))
+                                                           for ly in seq.seq_layers)
+        if concat:
+            cbuf = self._buf(("concat",), n, sum(widths), dev)
+            for a, b in self.mine:
+                cbuf[a:b, :widths[0]].copy_(emb[a:b])
+            off = widths[0]
         for l, layer in enumerate(seq.seq_layers):
             if not layer.built:
                 layer.build([(n, widths[l]), None])
                 layer.built = True
-            out = self._buf(("h", l), n, widths[l + 1], dev)  # own rows valid
+            if concat:
+                out = cbuf[:, off:off + widths[l + 1]]
+                off += widths[l + 1]
+            else:
+                out = self._buf(("h", l), n, widths[l + 1], dev)  # own rows valid
             relu = getattr(layer, "activation", None) == "relu"
-            if isinstance(layer, (GCNConv, RGCNConv)):
+            if isinstance(layer, GCNConv) and self._pipelined_ok(layer):
+                self._gcn_pipelined(layer, l, x_full, out, graph, relu)
+            elif isinstance(layer, (GCNConv, RGCNConv)):
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
                 z = self._buf(("z", l), len(kernels) * n, layer.channels, dev)
                 for r, w in enumerate(kernels):
@@ -154,7 +214,7 @@ class RowPartition:
                 raise NotImplementedError("no partitioned form for {}".format(type(layer).__name__))
             x_full, x_full_valid = out, False
             hs.append(out)
-        red = seq.reduce(hs)
+        red = cbuf if concat else seq.reduce(hs)
         if self.final_types:
             red = red if red.is_contiguous() else red.contiguous()
             self._exchange(red, self.final_types)

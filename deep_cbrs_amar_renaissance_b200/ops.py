@@ -161,11 +161,17 @@ def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_
         p_out = torch.empty(m, dtype=torch.float32, device=x1.device)
         q_out = torch.empty(m, dtype=torch.float32, device=x1.device)
     code = act if isinstance(act, int) else L.ACTS[act]
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(lib.cbrs_dense(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2, _ptr(idx2, torch.int64), f2,
                            _ptr(w, torch.float32), _ptr(b, torch.float32), m, n, code, rowop,
                            _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32), _ptr(p_out), _ptr(q_out),
                            _ptr(out), ldo, _stream()), "cbrs_dense")
     _count(2 if (rowop == L.ROWOP_L2NORM and n > 128) else 1)
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("dense", e0, e1, m * n))
     if rowop == L.ROWOP_ATTN:
         return out, p_out, q_out
     return out
