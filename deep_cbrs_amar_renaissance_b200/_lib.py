@@ -5,7 +5,7 @@ is raised.  PyTorch is used by the callers for device memory and streams only.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcbrs_b200.so")
@@ -55,6 +55,18 @@ _SIGS = {
     "cbrs_score_catalog_topk_bf16_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "cbrs_score_catalog_topk_bf16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, c_int32, P, P,
                                              c_int32, P, P, P, c_size_t, P]),
+    "cbrs_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "cbrs_peer_free": (c_int, [P]),
+    "cbrs_peer_export": (c_int, [P, P]),
+    "cbrs_peer_open": (c_int, [P, POINTER(c_void_p)]),
+    "cbrs_peer_close": (c_int, [P]),
+    "cbrs_peer_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_uint64, P, c_double, P]),
+    "cbrs_spmm_csr_bcast": (c_int, [POINTER(CsrDesc), P, c_int64, P, c_int64, c_int32, c_int, P, c_int, c_int,
+                                    POINTER(c_void_p), c_int, P, c_size_t, P]),
+    "cbrs_gat_csr_bcast": (c_int, [POINTER(CsrDesc), c_int64, P, c_int64, P, P, P, c_int64, c_int32, P, c_int,
+                                   POINTER(c_void_p), c_int, P, c_size_t, P]),
+    "cbrs_dense_bcast": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int, c_int,
+                                 P, P, P, P, P, c_int64, POINTER(c_void_p), POINTER(c_void_p), c_int, P]),
     "cbrs_synth_bipartite": (c_int, [c_int64, c_int64, c_int64, c_uint64, P, P, P]),
     "cbrs_sort_workspace_bytes": (c_size_t, [c_int64]),
     "cbrs_sort_pairs_u64": (c_int, [P, P, c_int64, c_int, P, c_size_t, P]),
@@ -66,6 +78,7 @@ AGG_WEIGHTED, AGG_SUM, AGG_MEAN = 0, 1, 2
 DTYPE_F32, DTYPE_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 ROWOP_NONE, ROWOP_L2NORM, ROWOP_ATTN = 0, 1, 2
+MAX_PEERS, IPC_HANDLE_BYTES = 8, 64
 ACTS = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID, "tanh": ACT_TANH}
 
 _lib = None

@@ -22,6 +22,10 @@ struct DenseParams {
     int act; int rowop;
     const float *a_self; const float *a_neigh; float *p_out; float *q_out;
     float *out; int64_t ldo;
+    // multi-GPU: finished rows (and the attention logit q) are also stored into these peer-mapped copies
+    float *out_peer[CBRS_MAX_PEERS - 1];
+    float *q_peer[CBRS_MAX_PEERS - 1];
+    int n_peer;
 };
 
 constexpr int kBM = 128, kBK = 32, kTM = 8;
@@ -147,11 +151,16 @@ __global__ void __launch_bounds__(kDenseThreads) dense_kernel(const DenseParams 
         if (p.rowop == CBRS_ROWOP_ATTN && tx == 0) {
             p.p_out[m] = ps;
             p.q_out[m] = qs;
+            for (int q = 0; q < p.n_peer; ++q) p.q_peer[q][m] = qs;
         }
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const int ng = n0 + tx * TN + j;
-            if (ng < p.n) p.out[m * p.ldo + ng] = apply_act(acc[i][j] * scale, p.act);
+            if (ng < p.n) {
+                const float v = apply_act(acc[i][j] * scale, p.act);
+                p.out[m * p.ldo + ng] = v;
+                for (int q = 0; q < p.n_peer; ++q) p.out_peer[q][m * p.ldo + ng] = v;
+            }
         }
     }
 }
@@ -332,23 +341,27 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_fast_kernel(const Dens
         if (p.rowop == CBRS_ROWOP_ATTN && tx == 0) {
             p.p_out[m] = ps;
             p.q_out[m] = qs;
+            for (int q = 0; q < p.n_peer; ++q) p.q_peer[q][m] = qs;
         }
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = apply_act(acc[i][j] * scale, p.act);
-        float *orow = p.out + m * p.ldo;
-        if (vec_out) {
+        // copy -1 is the local output; 0 .. n_peer-1 are the peers' (same layout, NVLink stores)
+        for (int q = -1; q < p.n_peer; ++q) {
+            float *orow = (q < 0 ? p.out : p.out_peer[q]) + m * p.ldo;
+            if (vec_out) {
 #pragma unroll
-            for (int j0 = 0; j0 < TN; j0 += 4) {
-                const int ng = col_of(j0);
-                if (ng < p.n)  // n % 4 == 0: a 4-wide group is entirely in or out
-                    *reinterpret_cast<float4 *>(orow + ng) =
-                        make_float4(acc[i][j0], acc[i][(j0 + 1) % TN], acc[i][(j0 + 2) % TN], acc[i][(j0 + 3) % TN]);
-            }
-        } else {
+                for (int j0 = 0; j0 < TN; j0 += 4) {
+                    const int ng = col_of(j0);
+                    if (ng < p.n)  // n % 4 == 0: a 4-wide group is entirely in or out
+                        *reinterpret_cast<float4 *>(orow + ng) =
+                            make_float4(acc[i][j0], acc[i][(j0 + 1) % TN], acc[i][(j0 + 2) % TN], acc[i][(j0 + 3) % TN]);
+                }
+            } else {
 #pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                const int ng = col_of(j);
-                if (ng < p.n) orow[ng] = acc[i][j];
+                for (int j = 0; j < TN; ++j) {
+                    const int ng = col_of(j);
+                    if (ng < p.n) orow[ng] = acc[i][j];
+                }
             }
         }
     }
@@ -391,11 +404,17 @@ static int launch_dense(const DenseParams &p, cudaStream_t s) {
 
 using namespace cbrs;
 
-extern "C" int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2, int64_t ld2,
-                          const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m, int32_t n,
-                          int act, int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out,
-                          float *out, int64_t ldo, void *stream) {
+static int dense_impl(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2, int64_t ld2,
+                      const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m, int32_t n, int act,
+                      int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out, float *out,
+                      int64_t ldo, void *const *out_peers_host, void *const *q_peers_host, int n_peers, void *stream) {
     CBRS_REQUIRE(x1 && w && out, CBRS_E_INVALID, "dense: null argument");
+    CBRS_REQUIRE(n_peers >= 0 && n_peers < CBRS_MAX_PEERS && (n_peers == 0 || out_peers_host), CBRS_E_INVALID,
+                 "dense: n_peers=%d (at most %d peer copies)", n_peers, CBRS_MAX_PEERS - 1);
+    CBRS_REQUIRE(n_peers == 0 || rowop != CBRS_ROWOP_ATTN || q_peers_host, CBRS_E_INVALID,
+                 "dense: the attention row-op with peers needs q_peers");
+    CBRS_REQUIRE(n_peers == 0 || !(rowop == CBRS_ROWOP_L2NORM && n > 128), CBRS_E_UNSUPPORTED,
+                 "dense: the two-pass l2-normalise (n > 128) has no peer form");
     CBRS_REQUIRE(m >= 0 && n > 0 && f1 > 0 && f2 >= 0 && ld1 >= f1 && ldo >= n, CBRS_E_INVALID,
                  "dense: m=%lld n=%d f1=%d f2=%d ld1=%lld ldo=%lld", (long long)m, n, f1, f2, (long long)ld1, (long long)ldo);
     CBRS_REQUIRE((x2 == nullptr) == (f2 == 0), CBRS_E_INVALID, "dense: second source and f2 disagree");
@@ -407,6 +426,14 @@ extern "C" int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int
     if (m == 0) return CBRS_OK;
     cudaStream_t s = (cudaStream_t)stream;
     DenseParams p{x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out, out, ldo};
+    p.n_peer = n_peers;
+    for (int q = 0; q < CBRS_MAX_PEERS - 1; ++q) {
+        p.out_peer[q] = q < n_peers ? (float *)out_peers_host[q] : nullptr;
+        p.q_peer[q] = (q < n_peers && q_peers_host) ? (float *)q_peers_host[q] : nullptr;
+        if (q < n_peers)
+            CBRS_REQUIRE(p.out_peer[q] && ((uintptr_t)p.out_peer[q] % 16) == ((uintptr_t)out % 16), CBRS_E_INVALID,
+                         "dense: peer copy %d is null or aligned differently from the local output", q);
+    }
     if (rowop == CBRS_ROWOP_L2NORM && n > 128) {  // row spans several column tiles: normalise in a second pass
         p.act = CBRS_ACT_NONE;
         p.rowop = CBRS_ROWOP_NONE;
@@ -425,4 +452,21 @@ extern "C" int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int
     if (n <= 32) return launch_dense<32>(p, s);
     if (n <= 64) return launch_dense<64>(p, s);
     return launch_dense<128>(p, s);
+}
+
+extern "C" int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2, int64_t ld2,
+                          const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m, int32_t n,
+                          int act, int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out,
+                          float *out, int64_t ldo, void *stream) {
+    return dense_impl(x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out, out,
+                      ldo, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int cbrs_dense_bcast(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2,
+                                int64_t ld2, const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m,
+                                int32_t n, int act, int rowop, const float *a_self, const float *a_neigh, float *p_out,
+                                float *q_out, float *out, int64_t ldo, void *const *out_peers_host,
+                                void *const *q_peers_host, int n_peers, void *stream) {
+    return dense_impl(x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out, out,
+                      ldo, out_peers_host, q_peers_host, n_peers, stream);
 }

@@ -37,6 +37,8 @@ struct GatParams {
     const int32_t *heavy_row;
     const int64_t *heavy_slot_ptr;
     int64_t n_heavy;
+    float *y_peer[CBRS_MAX_PEERS - 1];  // multi-GPU: peer-mapped copies of y (same layout)
+    int n_peer;
 };
 
 constexpr int kGatThreads = 256;
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_chunk_kernel(const GatParams 
                 if (p.bias) o += __ldg(p.bias + col + t);
                 if (p.relu) o = fmaxf(o, 0.f);
                 p.y[(int64_t)row * p.ldy + col + t] = o;
+                for (int r = 0; r < p.n_peer; ++r) p.y_peer[r][(int64_t)row * p.ldy + col + t] = o;
             }
         }
     }
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_heavy_kernel(const GatParams 
         if (p.bias) o += __ldg(p.bias + col);
         if (p.relu) o = fmaxf(o, 0.f);
         p.y[(int64_t)row * p.ldy + col] = o;
+        for (int r = 0; r < p.n_peer; ++r) p.y_peer[r][(int64_t)row * p.ldy + col] = o;
     }
 }
 
@@ -222,10 +226,12 @@ extern "C" size_t cbrs_gat_workspace_bytes(const cbrs_csr_t *g, int32_t h) {
     return align_up((size_t)g->n_slots * (size_t)h * sizeof(float)) + align_up((size_t)g->n_slots * 2 * sizeof(float)) + 256;
 }
 
-extern "C" int cbrs_gat_csr(const cbrs_csr_t *g, int64_t row_offset, const float *z, int64_t ldz, const float *pvec,
-                            const float *qvec, float *y, int64_t ldy, int32_t h, const float *bias, int relu,
-                            void *workspace, size_t workspace_bytes, void *stream) {
+static int gat_impl(const cbrs_csr_t *g, int64_t row_offset, const float *z, int64_t ldz, const float *pvec,
+                    const float *qvec, float *y, int64_t ldy, int32_t h, const float *bias, int relu,
+                    void *const *y_peers_host, int n_peers, void *workspace, size_t workspace_bytes, void *stream) {
     CBRS_REQUIRE(g && z && pvec && qvec && y, CBRS_E_INVALID, "gat: null argument");
+    CBRS_REQUIRE(n_peers >= 0 && n_peers < CBRS_MAX_PEERS && (n_peers == 0 || y_peers_host), CBRS_E_INVALID,
+                 "gat: n_peers=%d (at most %d peer copies)", n_peers, CBRS_MAX_PEERS - 1);
     CBRS_REQUIRE(h > 0 && ldz >= h && ldy >= h && row_offset >= 0, CBRS_E_INVALID, "gat: h=%d ldz=%lld ldy=%lld", h,
                  (long long)ldz, (long long)ldy);
     CBRS_REQUIRE(g->n_rows >= 0 && g->n_chunks >= 0 && g->chunk_edges > 0, CBRS_E_INVALID, "gat: bad graph descriptor");
@@ -244,7 +250,27 @@ extern "C" int cbrs_gat_csr(const cbrs_csr_t *g, int64_t row_offset, const float
     p.chunk_slot = g->chunk_slot; p.n_chunks = g->n_chunks; p.chunk_edges = g->chunk_edges; p.row_offset = row_offset;
     p.z = z; p.ldz = ldz; p.p = pvec; p.q = qvec; p.y = y; p.ldy = ldy; p.h = h; p.bias = bias; p.relu = relu;
     p.heavy_row = g->heavy_row; p.heavy_slot_ptr = g->heavy_slot_ptr; p.n_heavy = g->n_heavy;
+    p.n_peer = n_peers;
+    for (int r = 0; r < CBRS_MAX_PEERS - 1; ++r) {
+        p.y_peer[r] = r < n_peers ? (float *)y_peers_host[r] : nullptr;
+        if (r < n_peers) CBRS_REQUIRE(p.y_peer[r], CBRS_E_INVALID, "gat: peer copy %d is null", r);
+    }
     const bool vec4 = (h % 4 == 0) && (ldz % 4 == 0) && ((uintptr_t)z % 16 == 0);
     cudaStream_t s = (cudaStream_t)stream;
     return vec4 ? dispatch_g<4>(h / 4, p, s) : dispatch_g<1>(h, p, s);
+}
+
+extern "C" int cbrs_gat_csr(const cbrs_csr_t *g, int64_t row_offset, const float *z, int64_t ldz, const float *pvec,
+                            const float *qvec, float *y, int64_t ldy, int32_t h, const float *bias, int relu,
+                            void *workspace, size_t workspace_bytes, void *stream) {
+    return gat_impl(g, row_offset, z, ldz, pvec, qvec, y, ldy, h, bias, relu, nullptr, 0, workspace, workspace_bytes,
+                    stream);
+}
+
+extern "C" int cbrs_gat_csr_bcast(const cbrs_csr_t *g, int64_t row_offset, const float *z, int64_t ldz,
+                                  const float *pvec, const float *qvec, float *y, int64_t ldy, int32_t h,
+                                  const float *bias, int relu, void *const *y_peers_host, int n_peers, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
+    return gat_impl(g, row_offset, z, ldz, pvec, qvec, y, ldy, h, bias, relu, y_peers_host, n_peers, workspace,
+                    workspace_bytes, stream);
 }

@@ -40,6 +40,9 @@ struct SpmmParams {
     const int32_t *heavy_row;
     const int64_t *heavy_slot_ptr;
     int64_t n_heavy;
+    // multi-GPU: every finished row is also stored into these peer-mapped copies of y (NVLink)
+    float *y_peer[CBRS_MAX_PEERS - 1];
+    int n_peer;
 };
 
 template <int VEC>
@@ -148,6 +151,7 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const Sp
             }
             acc.epilogue(p.bias ? p.bias + col : nullptr, p.relu);
             acc.store(p.y + (int64_t)row * p.ldy + col);
+            for (int q = 0; q < p.n_peer; ++q) acc.store(p.y_peer[q] + (int64_t)row * p.ldy + col);
         }
     }
 }
@@ -176,6 +180,7 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_heavy_kernel(const SpmmPara
         }
         acc.epilogue(p.bias ? p.bias + col : nullptr, p.relu);
         acc.store(p.y + (int64_t)row * p.ldy + col);
+        for (int q = 0; q < p.n_peer; ++q) acc.store(p.y_peer[q] + (int64_t)row * p.ldy + col);
     }
 }
 
@@ -237,10 +242,12 @@ extern "C" size_t cbrs_spmm_workspace_bytes(const cbrs_csr_t *g, int32_t d) {
     return align_up((size_t)g->n_slots * (size_t)d * sizeof(float)) + 256;
 }
 
-extern "C" int cbrs_spmm_csr(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d, int agg,
-                             const float *bias, int relu, int dtype, void *workspace, size_t workspace_bytes,
-                             void *stream) {
+static int spmm_impl(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d, int agg,
+                     const float *bias, int relu, int dtype, void *const *y_peers_host, int n_peers, void *workspace,
+                     size_t workspace_bytes, void *stream) {
     CBRS_REQUIRE(g && x && y, CBRS_E_INVALID, "spmm: null argument");
+    CBRS_REQUIRE(n_peers >= 0 && n_peers < CBRS_MAX_PEERS && (n_peers == 0 || y_peers_host), CBRS_E_INVALID,
+                 "spmm: n_peers=%d (at most %d peer copies)", n_peers, CBRS_MAX_PEERS - 1);
     CBRS_REQUIRE(dtype == CBRS_DTYPE_F32, CBRS_E_UNSUPPORTED, "spmm: only float32 features are built in this round");
     CBRS_REQUIRE(d > 0 && ldx >= d && ldy >= d, CBRS_E_INVALID, "spmm: d=%d ldx=%lld ldy=%lld", d, (long long)ldx,
                  (long long)ldy);
@@ -260,9 +267,29 @@ extern "C" int cbrs_spmm_csr(const cbrs_csr_t *g, const void *x, int64_t ldx, vo
     p.x = (const float *)x; p.ldx = ldx; p.y = (float *)y; p.ldy = ldy; p.d = d; p.agg = agg;
     p.bias = bias; p.relu = relu; p.partial = (float *)workspace;
     p.heavy_row = g->heavy_row; p.heavy_slot_ptr = g->heavy_slot_ptr; p.n_heavy = g->n_heavy;
-    const bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
-                      ((uintptr_t)y % 16 == 0) && ((uintptr_t)workspace % 16 == 0) &&
-                      (!bias || (uintptr_t)bias % 16 == 0);
+    bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
+                ((uintptr_t)y % 16 == 0) && ((uintptr_t)workspace % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
+    p.n_peer = n_peers;
+    for (int q = 0; q < CBRS_MAX_PEERS - 1; ++q) {
+        p.y_peer[q] = q < n_peers ? (float *)y_peers_host[q] : nullptr;
+        if (q < n_peers) {
+            CBRS_REQUIRE(p.y_peer[q], CBRS_E_INVALID, "spmm: peer copy %d is null", q);
+            vec4 = vec4 && ((uintptr_t)p.y_peer[q] % 16 == 0);
+        }
+    }
     cudaStream_t s = (cudaStream_t)stream;
     return vec4 ? dispatch_g<4>(d / 4, p, s) : dispatch_g<1>(d, p, s);
+}
+
+extern "C" int cbrs_spmm_csr(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d, int agg,
+                             const float *bias, int relu, int dtype, void *workspace, size_t workspace_bytes,
+                             void *stream) {
+    return spmm_impl(g, x, ldx, y, ldy, d, agg, bias, relu, dtype, nullptr, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cbrs_spmm_csr_bcast(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d,
+                                   int agg, const float *bias, int relu, int dtype, void *const *y_peers_host,
+                                   int n_peers, void *workspace, size_t workspace_bytes, void *stream) {
+    return spmm_impl(g, x, ldx, y, ldy, d, agg, bias, relu, dtype, y_peers_host, n_peers, workspace, workspace_bytes,
+                     stream);
 }

@@ -8,7 +8,20 @@ column ids), and the layer outputs are exchanged with an all-gather.  Every row'
 order is rank-independent (ascending columns, fixed chunk tree), so the G-rank result equals
 the 1-rank result bit for bit.  Scoring is sharded by user with items replicated: no
 collective.
+
+Two exchange mechanisms (RowPartition(exchange=...)):
+  "peer" (default on GPUs): the operand buffers are symmetric peer-mapped allocations
+         (PeerHeap, CUDA IPC over NVLink/NVSwitch) and the kernel that PRODUCES an operand
+         stores every finished row into all ranks' copies (cbrs_dense_bcast /
+         cbrs_spmm_csr_bcast / cbrs_gat_csr_bcast); a one-CTA flag barrier
+         (cbrs_peer_barrier) is the only thing between producer and consumer.  No NCCL call
+         on the data path.
+  "nccl": producer kernel, then an all-gather (the baseline; also what the gloo CPU tests
+         exercise).
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -53,6 +66,111 @@ def exchange_rows(x, ranges, group=None):
     return x
 
 
+class SymmetricBuffer:
+    """One allocation of a PeerHeap: the same number of bytes on every rank, all copies mapped here."""
+
+    def __init__(self, heap, nbytes, ptrs):
+        self.heap, self.nbytes, self.ptrs = heap, nbytes, ptrs  # ptrs[r] = address of rank r's copy
+        self.local = ptrs[heap.rank]
+        self._iface = type("_Raw", (), {})()
+        self._iface.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4",
+                                                "data": (self.local, False), "version": 2}
+        self.flat = torch.as_tensor(self._iface, device=torch.device("cuda", torch.cuda.current_device()))
+        if self.flat.data_ptr() != self.local:
+            raise RuntimeError("torch copied the symmetric buffer instead of viewing it")
+
+    def matrix(self, n, w):
+        """float32 [n, w] view of the local copy"""
+        return self.flat[:n * w].view(n, w)
+
+    def peer_addrs(self, view):
+        """addresses, in every OTHER rank's copy, of `view` (a view into the local copy)"""
+        off = view.data_ptr() - self.local
+        if off < 0 or off >= self.nbytes:
+            raise ValueError("view does not live in this symmetric buffer")
+        return [p + off for r, p in enumerate(self.ptrs) if r != self.heap.rank]
+
+
+class PeerHeap:
+    """Symmetric peer-mapped allocations for the ranks of one box + the flag barrier.
+    alloc() is collective: every rank calls it in the same order with the same size."""
+
+    def __init__(self, group=None):
+        from . import _lib as L
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > L.MAX_PEERS:
+            raise L.CbrsError("peer exchange supports up to {} ranks (one NVSwitch box)".format(L.MAX_PEERS))
+        self._lib = L.load()
+        self._owned, self._opened = [], []
+        self.flags = self.alloc(L.MAX_PEERS * 8)
+        self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.epoch = 0
+        self.barrier()
+        self.check()
+
+    def alloc(self, nbytes):
+        from . import _lib as L
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        ptr = ctypes.c_void_p()
+        L.check(self._lib.cbrs_peer_alloc(nbytes, ctypes.byref(ptr)), "cbrs_peer_alloc")
+        self._owned.append(ptr.value)
+        handle = (ctypes.c_ubyte * L.IPC_HANDLE_BYTES)()
+        L.check(self._lib.cbrs_peer_export(ptr, handle), "cbrs_peer_export")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (nbytes, bytes(handle)), group=self.group)
+        ptrs = []
+        for r, (nb, h) in enumerate(handles):
+            if nb != nbytes:
+                raise L.CbrsError("symmetric allocation sizes differ: rank {} asked for {} bytes, rank {} for {}"
+                                  .format(self.rank, nbytes, r, nb))
+            if r == self.rank:
+                ptrs.append(ptr.value)
+                continue
+            q = ctypes.c_void_p()
+            L.check(self._lib.cbrs_peer_open((ctypes.c_ubyte * L.IPC_HANDLE_BYTES).from_buffer_copy(h),
+                                             ctypes.byref(q)), "cbrs_peer_open")
+            self._opened.append(q.value)
+            ptrs.append(q.value)
+        return SymmetricBuffer(self, nbytes, ptrs)
+
+    def barrier(self):
+        """Stream-ordered rendezvous of all ranks (cbrs_peer_barrier) on torch's current stream."""
+        from . import _lib as L
+        from . import ops
+        self.epoch += 1
+        arr = (ctypes.c_void_p * self.world)(*self.flags.ptrs)
+        if ops.PROFILE_ON:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        L.check(self._lib.cbrs_peer_barrier(arr, self.world, self.rank, self.epoch,
+                                            ctypes.c_void_p(self.status.data_ptr()), 30.0,
+                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                "cbrs_peer_barrier")
+        ops._count(1)
+        if ops.PROFILE_ON:
+            e1.record()
+            ops.PROFILE.append(("barrier", e0, e1, None))
+
+    def check(self):
+        """Synchronises; raises if any barrier so far timed out."""
+        from . import _lib as L
+        if int(self.status.item()) != 0:
+            raise L.CbrsError("peer barrier timed out: a rank did not arrive within 30 s")
+
+    def close(self):
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for q in self._opened:
+            self._lib.cbrs_peer_close(ctypes.c_void_p(q))
+        self._opened = []
+        dist.barrier(group=self.group)
+        for q in self._owned:
+            self._lib.cbrs_peer_free(ctypes.c_void_p(q))
+        self._owned = []
+
+
 class RowPartition:
     """Attach to a SequentialGNN to run its layer loop on this rank's row blocks.
 
@@ -65,9 +183,15 @@ class RowPartition:
     After the last layer only the node types in `final_types` (default: everything but users)
     are exchanged, because scoring is sharded by user."""
 
-    def __init__(self, n_rows_by_type, group=None, final_types=None, col_splits=4):
+    def __init__(self, n_rows_by_type, group=None, final_types=None, col_splits=1, exchange=None):
         self.group = group
-        import os
+        exchange = exchange or os.environ.get("CBRS_EXCHANGE") or ("peer" if torch.cuda.is_available() else "nccl")
+        if exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange = exchange
+        self.heap = PeerHeap(group) if exchange == "peer" else None
+        self._sym = {}
+        self.n_rows_by_type = list(n_rows_by_type)
         self.col_splits = int(os.environ.get("CBRS_COL_SPLITS", col_splits))  # GCN: the all-gather of column block s+1 overlaps the SpMM of block s
         self._comm = None
         self.world = dist.get_world_size(group)
@@ -81,6 +205,13 @@ class RowPartition:
     def attach(self, seq_gnn):
         seq_gnn.partition = self
         return self
+
+    def close(self):
+        """Unmap and free the symmetric buffers (collective)."""
+        self._sym.clear()
+        if self.heap is not None:
+            self.heap.close()
+            self.heap = None
 
     def csr_slices(self, view_name, graph):
         if view_name not in self._slices:
@@ -147,9 +278,133 @@ class RowPartition:
             for sl in self.csr_slices("norm", graph):
                 ops.spmm(sl, zs[s], out[sl.row_offset:sl.row_offset + sl.n_rows, s * hs:(s + 1) * hs], bias=bias, relu=relu)
 
+    # ------------------------------------------------------------------ peer exchange
+    def _symbuf(self, key, n, w):
+        """symmetric [n, w] float32 buffer -> (SymmetricBuffer, local matrix view)"""
+        if key not in self._sym:
+            sb = self.heap.alloc(n * w * 4)
+            self._sym[key] = (sb, sb.matrix(n, w))
+        return self._sym[key]
+
+    def _type_of(self, a):
+        base = 0
+        for t, cnt in enumerate(self.n_rows_by_type):
+            if base <= a < base + cnt or (cnt == 0 and a == base):
+                return t
+            base += cnt
+        return len(self.n_rows_by_type) - 1
+
+    def _propagate_peer(self, seq):
+        """The layer loop with the all-gather fused into the producing kernels (module docstring).
+
+        Who needs what: the sparse kernel of a layer gathers rows of its operand from ANY rank, so
+        the operand's producer stores its rows everywhere; a layer OUTPUT is needed remotely only on
+        the rows of `final_types` (scoring is sharded by user, items are replicated), so the kernel
+        that finishes those rows stores them everywhere too.  One flag barrier separates producers
+        from consumers; the first one also keeps a fast rank from overwriting buffers a slow rank is
+        still reading from the previous call."""
+        from . import _lib as L
+        from . import ops
+        from .layers import GATConv, GCNConv, GraphSageConv, LightGCNConv, RGCNConv
+        heap = self.heap
+        emb = seq.embeddings
+        n = emb.shape[0]
+        widths = seq._widths()
+        graph = seq.adj_matrix
+        layers = seq.seq_layers
+        concat = seq.final_node == 'concatenation'
+        final = set(self.final_types)
+        type_lo = [sum(self.n_rows_by_type[:t]) for t in range(len(self.n_rows_by_type))]
+
+        def is_final(a):
+            return self._type_of(a) in final
+
+        heap.barrier()
+        if concat:
+            csb, cbuf = self._symbuf(("concat",), n, sum(widths))
+        # layer 0 input: the replicated embedding table; valid on every row of every rank
+        h0 = cbuf[:, :widths[0]] if concat else emb
+        if concat:
+            for a, b in self.mine:
+                cbuf[a:b, :widths[0]].copy_(emb[a:b])
+            for t in final:
+                cbuf[type_lo[t]:type_lo[t] + self.n_rows_by_type[t], :widths[0]].copy_(
+                    emb[type_lo[t]:type_lo[t] + self.n_rows_by_type[t]])
+        x_full, hs = emb, [h0]
+        off = widths[0]
+        for l, layer in enumerate(layers):
+            if not layer.built:
+                layer.build([(n, widths[l]), None])
+                layer.built = True
+            h = layer.channels if hasattr(layer, "channels") else widths[l]
+            if concat:
+                osb, out = csb, cbuf[:, off:off + widths[l + 1]]
+                off += widths[l + 1]
+            else:
+                osb, out = self._symbuf(("h", l), n, widths[l + 1])
+            relu = getattr(layer, "activation", None) == "relu"
+            nxt = layers[l + 1] if l + 1 < len(layers) else None
+            # the next layer's sparse kernel gathers from this output directly -> every row travels
+            everywhere = isinstance(nxt, (GraphSageConv, LightGCNConv))
+
+            def out_peers(view, a):
+                return osb.peer_addrs(view) if (everywhere or is_final(a)) else None
+
+            if isinstance(layer, (GCNConv, RGCNConv)):
+                kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
+                zsb, z = self._symbuf(("z", l), len(kernels) * n, layer.channels)
+                for r, w in enumerate(kernels):
+                    for a, b in self.mine:
+                        zv = z[r * n + a:r * n + b]
+                        ops.dense(x_full[a:b], w, out=zv, peers=zsb.peer_addrs(zv))
+                heap.barrier()
+                for sl in self.csr_slices("norm", graph):
+                    ov = out[sl.row_offset:sl.row_offset + sl.n_rows]
+                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, peers=out_peers(ov, sl.row_offset))
+            elif isinstance(layer, GATConv):
+                zsb, z = self._symbuf(("z", l), n, layer.channels)
+                qsb, q = self._symbuf(("q", l), n, 1)
+                p = self._buf(("p", l), n, 1, emb.device)
+                for a, b in self.mine:
+                    zv, qv = z[a:b], q[a:b, 0]
+                    _, pp, _ = ops.dense(x_full[a:b], layer.kernel.reshape(widths[l], layer.channels),
+                                         rowop=L.ROWOP_ATTN, a_self=layer.attn_kernel_self.reshape(-1),
+                                         a_neigh=layer.attn_kernel_neighs.reshape(-1), out=zv, q_out=qv,
+                                         peers=zsb.peer_addrs(zv), q_peers=qsb.peer_addrs(qv))
+                    p[a:b, 0].copy_(pp)
+                heap.barrier()
+                for sl in self.csr_slices("raw", graph):
+                    ov = out[sl.row_offset:sl.row_offset + sl.n_rows]
+                    ops.gat(sl, z, p.reshape(-1), q.reshape(-1), ov, bias=layer.bias, relu=relu,
+                            row_offset=sl.row_offset, peers=out_peers(ov, sl.row_offset))
+            elif isinstance(layer, LightGCNConv):
+                if l > 0:
+                    heap.barrier()  # x_full = previous output, pushed everywhere by its producer
+                for sl in self.csr_slices("norm", graph):
+                    ov = out[sl.row_offset:sl.row_offset + sl.n_rows]
+                    ops.spmm(sl, x_full, ov, peers=out_peers(ov, sl.row_offset))
+            elif isinstance(layer, GraphSageConv):
+                if l > 0:
+                    heap.barrier()
+                for sl in self.csr_slices("raw", graph):
+                    a, b = sl.row_offset, sl.row_offset + sl.n_rows
+                    agg = self._buf(("agg", l, a), sl.n_rows, widths[l], emb.device)
+                    ops.spmm(sl, x_full, agg, agg=L.AGG_MEAN if layer.aggregate == "mean" else L.AGG_SUM)
+                    ov = out[a:b]
+                    ops.dense(x_full[a:b], layer.kernel, layer.bias, layer.activation, x2=agg, rowop=L.ROWOP_L2NORM,
+                              out=ov, peers=out_peers(ov, a))
+            else:
+                raise NotImplementedError("no partitioned form for {}".format(type(layer).__name__))
+            x_full = out
+            hs.append(out)
+        heap.barrier()  # the final-type rows stored by the other ranks have landed
+        return cbuf if concat else seq.reduce(hs)
+
     def propagate(self, seq):
         """SequentialGNN.call on the partition.  Returns [N, D_out]; rows of other ranks' users
         are NOT valid unless final_types covers type 0."""
+        if self.heap is not None:
+            return self._propagate_peer(seq)
         from . import _lib as L
         from . import ops
         from .layers import GATConv, GCNConv, GraphSageConv, LightGCNConv, RGCNConv

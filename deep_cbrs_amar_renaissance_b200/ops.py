@@ -101,8 +101,15 @@ def build_chunks(rowptr, chunk_edges):
 
 
 # ------------------------------------------------------------------ propagation
-def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None):
-    """out[:, :] = epilogue(A @ x) for the rows held by `csr` (a graph.CsrSlice)."""
+def _ptr_array(addresses):
+    """host array of device addresses for the *_bcast entry points"""
+    return (ctypes.c_void_p * max(len(addresses), 1))(*addresses)
+
+
+def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None, peers=None):
+    """out[:, :] = epilogue(A @ x) for the rows held by `csr` (a graph.CsrSlice).
+    peers: device addresses of the same `out` view in the other ranks' symmetric buffers; every
+    finished row is stored there too (cbrs_spmm_csr_bcast)."""
     lib = L.load()
     x, ldx = _rowmajor(x)
     out, ldy = _rowmajor(out)
@@ -114,32 +121,48 @@ def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None)
     if PROFILE_ON:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    L.check(lib.cbrs_spmm_csr(ctypes.byref(csr.desc), _ptr(x), ldx, _ptr(out), ldy, d, agg, _ptr(bias, torch.float32),
-                              1 if relu else 0, L.DTYPE_F32, _ptr(ws), ws.numel(), _stream()), "cbrs_spmm_csr")
+    if peers:
+        L.check(lib.cbrs_spmm_csr_bcast(ctypes.byref(csr.desc), _ptr(x), ldx, _ptr(out), ldy, d, agg,
+                                        _ptr(bias, torch.float32), 1 if relu else 0, L.DTYPE_F32, _ptr_array(peers),
+                                        len(peers), _ptr(ws), ws.numel(), _stream()), "cbrs_spmm_csr_bcast")
+    else:
+        L.check(lib.cbrs_spmm_csr(ctypes.byref(csr.desc), _ptr(x), ldx, _ptr(out), ldy, d, agg,
+                                  _ptr(bias, torch.float32), 1 if relu else 0, L.DTYPE_F32, _ptr(ws), ws.numel(),
+                                  _stream()), "cbrs_spmm_csr")
     if PROFILE_ON:
         e1.record()
-        PROFILE.append(("spmm", e0, e1, csr.nnz))
+        # algorithmic bytes of this launch: nnz*(4 col + 4 val + d*4 row) + rows*(d*4 out + 8 rowptr)
+        PROFILE.append(("spmm", e0, e1, {"nnz": csr.nnz, "rows": csr.n_rows, "d": d,
+                                         "bytes": csr.nnz * (8 + 4 * d) + csr.n_rows * (4 * d + 8)}))
     _count(1 + (1 if csr.chunks["n_heavy"] else 0))
     return out
 
 
-def gat(csr, z, p, q, out, bias=None, relu=True, row_offset=0, workspace=None):
+def gat(csr, z, p, q, out, bias=None, relu=True, row_offset=0, workspace=None, peers=None):
     lib = L.load()
     z, ldz = _rowmajor(z)
     out, ldy = _rowmajor(out)
     h = z.shape[1]
     need = lib.cbrs_gat_workspace_bytes(ctypes.byref(csr.desc), h)
     ws = workspace if workspace is not None and workspace.numel() >= need else _ws(need, z.device)
-    L.check(lib.cbrs_gat_csr(ctypes.byref(csr.desc), row_offset, _ptr(z), ldz, _ptr(p, torch.float32),
-                             _ptr(q, torch.float32), _ptr(out), ldy, h, _ptr(bias, torch.float32), 1 if relu else 0,
-                             _ptr(ws), ws.numel(), _stream()), "cbrs_gat_csr")
+    if peers:
+        L.check(lib.cbrs_gat_csr_bcast(ctypes.byref(csr.desc), row_offset, _ptr(z), ldz, _ptr(p, torch.float32),
+                                       _ptr(q, torch.float32), _ptr(out), ldy, h, _ptr(bias, torch.float32),
+                                       1 if relu else 0, _ptr_array(peers), len(peers), _ptr(ws), ws.numel(),
+                                       _stream()), "cbrs_gat_csr_bcast")
+    else:
+        L.check(lib.cbrs_gat_csr(ctypes.byref(csr.desc), row_offset, _ptr(z), ldz, _ptr(p, torch.float32),
+                                 _ptr(q, torch.float32), _ptr(out), ldy, h, _ptr(bias, torch.float32),
+                                 1 if relu else 0, _ptr(ws), ws.numel(), _stream()), "cbrs_gat_csr")
     _count(1 + (1 if csr.chunks["n_heavy"] else 0))
     return out
 
 
 def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_NONE, a_self=None, a_neigh=None,
-          out=None, m=None):
-    """act(rowop([x1[idx1] || x2[idx2]] @ w + b)); returns out (and (p, q) for the attention row-op)."""
+          out=None, m=None, peers=None, q_out=None, q_peers=None):
+    """act(rowop([x1[idx1] || x2[idx2]] @ w + b)); returns out (and (p, q) for the attention row-op).
+    peers / q_peers: device addresses of the same `out` (and q) views in the other ranks' symmetric
+    buffers; finished rows are stored there too (cbrs_dense_bcast)."""
     lib = L.load()
     x1, ld1 = _rowmajor(x1)
     f1 = x1.shape[1]
@@ -156,18 +179,29 @@ def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_
     if out is None:
         out = torch.empty(m, n, dtype=torch.float32, device=x1.device)
     out, ldo = _rowmajor(out)
-    p_out = q_out = None
+    p_out = None
+    if rowop != L.ROWOP_ATTN:
+        q_out = None
     if rowop == L.ROWOP_ATTN:
         p_out = torch.empty(m, dtype=torch.float32, device=x1.device)
-        q_out = torch.empty(m, dtype=torch.float32, device=x1.device)
+        if q_out is None:
+            q_out = torch.empty(m, dtype=torch.float32, device=x1.device)
     code = act if isinstance(act, int) else L.ACTS[act]
     if PROFILE_ON:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    L.check(lib.cbrs_dense(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2, _ptr(idx2, torch.int64), f2,
-                           _ptr(w, torch.float32), _ptr(b, torch.float32), m, n, code, rowop,
-                           _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32), _ptr(p_out), _ptr(q_out),
-                           _ptr(out), ldo, _stream()), "cbrs_dense")
+    if peers:
+        L.check(lib.cbrs_dense_bcast(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2,
+                                     _ptr(idx2, torch.int64), f2, _ptr(w, torch.float32), _ptr(b, torch.float32), m, n,
+                                     code, rowop, _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32),
+                                     _ptr(p_out), _ptr(q_out), _ptr(out), ldo, _ptr_array(peers),
+                                     _ptr_array(q_peers) if q_peers else None, len(peers), _stream()),
+                "cbrs_dense_bcast")
+    else:
+        L.check(lib.cbrs_dense(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2, _ptr(idx2, torch.int64), f2,
+                               _ptr(w, torch.float32), _ptr(b, torch.float32), m, n, code, rowop,
+                               _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32), _ptr(p_out), _ptr(q_out),
+                               _ptr(out), ldo, _stream()), "cbrs_dense")
     _count(2 if (rowop == L.ROWOP_L2NORM and n > 128) else 1)
     if PROFILE_ON:
         e1.record()

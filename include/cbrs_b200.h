@@ -209,6 +209,44 @@ int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const float *Q, in
 int cbrs_synth_bipartite(int64_t n_users, int64_t n_items, int64_t n_edges, uint64_t seed,
                          int32_t *coo_row, int32_t *coo_col, void *stream);
 
+/* ---- peer memory + fused producer -> all-gather kernels (multi-GPU extension) -----
+ * One process per GPU.  Every rank allocates the same ("symmetric") buffers with
+ * cbrs_peer_alloc, exports an IPC handle (CBRS_IPC_HANDLE_BYTES opaque bytes, exchanged by
+ * the host, e.g. torch.distributed.all_gather_object) and maps its peers' copies with
+ * cbrs_peer_open.  The *_bcast kernels store every finished output row into the local
+ * buffer AND into the n_peers peer-mapped copies (same layout; plain stores over
+ * NVLink/NVSwitch), so the all-gather of a layer's operand happens inside the kernel that
+ * produces it.  cbrs_peer_barrier is the stream-ordered rendezvous that follows: rank r
+ * publishes `epoch` (monotonically increasing, same on all ranks) into slot r of every
+ * rank's flag array and waits until all slots of its own array reach `epoch`; *status
+ * (device int32, zeroed by the caller) becomes 1 if a peer did not arrive within
+ * timeout_s.  The reference has no multi-device code; these calls replace the
+ * all-gather + barrier a NCCL-based port would issue per layer.                           */
+#define CBRS_MAX_PEERS 8
+#define CBRS_IPC_HANDLE_BYTES 64
+int cbrs_peer_alloc(size_t bytes, void **ptr_out); /* cudaMalloc'd (IPC-exportable), zero-filled */
+int cbrs_peer_free(void *ptr);
+int cbrs_peer_export(void *ptr, unsigned char *handle_host);
+int cbrs_peer_open(const unsigned char *handle_host, void **ptr_out);
+int cbrs_peer_close(void *ptr);
+/* flags_peers_host[r] = rank r's flag array (uint64[CBRS_MAX_PEERS], peer-mapped; own for r == my_rank) */
+int cbrs_peer_barrier(void *const *flags_peers_host, int n_ranks, int my_rank, uint64_t epoch,
+                      int32_t *status, double timeout_s, void *stream);
+/* cbrs_spmm_csr + stores into y_peers_host[0..n_peers) (each the peer's address of the same y view) */
+int cbrs_spmm_csr_bcast(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d,
+                        int agg, const float *bias, int relu, int dtype, void *const *y_peers_host,
+                        int n_peers, void *workspace, size_t workspace_bytes, void *stream);
+int cbrs_gat_csr_bcast(const cbrs_csr_t *g, int64_t row_offset, const float *z, int64_t ldz, const float *p,
+                       const float *q, float *y, int64_t ldy, int32_t h, const float *bias, int relu,
+                       void *const *y_peers_host, int n_peers, void *workspace, size_t workspace_bytes,
+                       void *stream);
+/* cbrs_dense + stores of out (and q for the attention row-op) into the peers' copies */
+int cbrs_dense_bcast(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2,
+                     int64_t ld2, const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m,
+                     int32_t n, int act, int rowop, const float *a_self, const float *a_neigh, float *p_out,
+                     float *q_out, float *out, int64_t ldo, void *const *out_peers_host,
+                     void *const *q_peers_host, int n_peers, void *stream);
+
 /* ---- primitives exported for tests -------------------------------------------- */
 size_t cbrs_sort_workspace_bytes(int64_t n);
 /* stable ascending sort of 64-bit keys (bits [0,key_bits)) with a 32-bit payload */

@@ -39,10 +39,27 @@ def main():
             seq = model.gnn.gnn_layers
             model((u, i))
             full = model.gnn(None).clone()
-            RowPartition(sizes, final_types=[0, 1, 2]).attach(seq)
-            part = model.gnn(None)
-            assert torch.equal(part, full), "%s even=%s: partitioned result differs" % (name, even)
-            seq.partition = None
+            for exchange in ("peer", "nccl"):
+                part = RowPartition(sizes, final_types=[0, 1, 2], exchange=exchange).attach(seq)
+                for rep in range(3):  # repeated calls reuse the symmetric buffers
+                    got = model.gnn(None)
+                    torch.cuda.synchronize()
+                    assert torch.equal(got, full), "%s even=%s %s rep %d: partitioned result differs" % (
+                        name, even, exchange, rep)
+                if part.heap is not None:
+                    part.heap.check()
+                part.close()
+                seq.partition = None
+                # items only: user rows of other ranks are not exchanged, own rows and item rows must match
+                part = RowPartition(sizes, final_types=[1], exchange=exchange).attach(seq)
+                got = model.gnn(None)
+                torch.cuda.synchronize()
+                lo, hi = sizes[0], sizes[0] + sizes[1]
+                assert torch.equal(got[lo:hi], full[lo:hi]), "%s %s: item rows differ" % (name, exchange)
+                for a, b in part.mine:
+                    assert torch.equal(got[a:b], full[a:b]), "%s %s: own rows differ" % (name, exchange)
+                part.close()
+                seq.partition = None
             if rank == 0:
                 print("ok", name, "even" if even else "ragged", flush=True)
     # user-sharded catalog top-k: each rank ranks its own users with replicated item rows
