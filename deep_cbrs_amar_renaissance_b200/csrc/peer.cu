@@ -126,6 +126,17 @@ extern "C" int cbrs_peer_close(void *ptr) {
     return CBRS_OK;
 }
 
+extern "C" int cbrs_peer_copy(void *dst, const void *src, size_t bytes, void *stream) {
+    CBRS_REQUIRE(dst && src, CBRS_E_INVALID, "peer_copy: null argument");
+    if (bytes == 0) return CBRS_OK;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        set_error("peer_copy: %s", cudaGetErrorString(e));
+        return CBRS_E_CUDA;
+    }
+    return CBRS_OK;
+}
+
 extern "C" int cbrs_peer_barrier(void *const *flags_peers_host, int n_ranks, int my_rank, uint64_t epoch,
                                  int32_t *status, double timeout_s, void *stream) {
     CBRS_REQUIRE(flags_peers_host && status, CBRS_E_INVALID, "peer_barrier: null argument");

@@ -183,13 +183,22 @@ class RowPartition:
     After the last layer only the node types in `final_types` (default: everything but users)
     are exchanged, because scoring is sharded by user."""
 
-    def __init__(self, n_rows_by_type, group=None, final_types=None, col_splits=1, exchange=None):
+    def __init__(self, n_rows_by_type, group=None, final_types=None, col_splits=1, exchange=None, pipeline=None,
+                 row_blocks=None):
         self.group = group
         exchange = exchange or os.environ.get("CBRS_EXCHANGE") or ("peer" if torch.cuda.is_available() else "nccl")
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.exchange = exchange
         self.heap = PeerHeap(group) if exchange == "peer" else None
+        # peer exchange of a GCN stack: "off" = transform+stores, barrier, sparse kernel, in order;
+        # "kernel" = the next layer's fused transform+stores of row block b runs on a high-priority side
+        # stream while the sparse kernel works on block b+1; "ce" = same, but the rows travel by copy engine
+        self.pipeline = pipeline or os.environ.get("CBRS_PIPELINE", "off")
+        if self.pipeline not in ("off", "kernel", "ce"):
+            raise ValueError("pipeline must be 'off', 'kernel' or 'ce'")
+        self.row_blocks = int(row_blocks or os.environ.get("CBRS_ROW_BLOCKS", "1" if self.pipeline == "off" else "2"))
+        self._side = None
         self._sym = {}
         self.n_rows_by_type = list(n_rows_by_type)
         self.col_splits = int(os.environ.get("CBRS_COL_SPLITS", col_splits))  # GCN: the all-gather of column block s+1 overlaps the SpMM of block s
@@ -214,9 +223,23 @@ class RowPartition:
             self.heap = None
 
     def csr_slices(self, view_name, graph):
+        """This rank's rows of a CSR view: one slice per owned node-type block, each cut further into
+        `row_blocks` pieces of about equal edge count (the pipelined GCN overlaps the exchange of
+        piece b's transform with the sparse kernel of piece b+1)."""
         if view_name not in self._slices:
             full = getattr(graph, view_name)
-            self._slices[view_name] = [full.row_slice(a, b) for a, b in self.mine]
+            out = []
+            for a, b in self.mine:
+                cuts = [a, b]
+                if self.row_blocks > 1 and b - a >= self.row_blocks:
+                    rp = full.rowptr[a:b + 1]
+                    lo, hi = int(rp[0].item()), int(rp[-1].item())
+                    targets = torch.tensor([lo + (hi - lo) * k // self.row_blocks for k in range(1, self.row_blocks)],
+                                           dtype=rp.dtype, device=rp.device)
+                    mids = (torch.searchsorted(rp, targets) + a).tolist()
+                    cuts = sorted(set([a] + [min(max(m, a), b) for m in mids] + [b]))
+                out.extend(full.row_slice(c0, c1) for c0, c1 in zip(cuts[:-1], cuts[1:]) if c1 > c0)
+            self._slices[view_name] = out
         return self._slices[view_name]
 
     def release_full_views(self, graph):
@@ -332,6 +355,7 @@ class RowPartition:
                     emb[type_lo[t]:type_lo[t] + self.n_rows_by_type[t]])
         x_full, hs = emb, [h0]
         off = widths[0]
+        z_ahead = False  # this layer's transform was already produced and exchanged by the previous layer
         for l, layer in enumerate(layers):
             if not layer.built:
                 layer.build([(n, widths[l]), None])
@@ -353,14 +377,44 @@ class RowPartition:
             if isinstance(layer, (GCNConv, RGCNConv)):
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
                 zsb, z = self._symbuf(("z", l), len(kernels) * n, layer.channels)
-                for r, w in enumerate(kernels):
-                    for a, b in self.mine:
-                        zv = z[r * n + a:r * n + b]
-                        ops.dense(x_full[a:b], w, out=zv, peers=zsb.peer_addrs(zv))
-                heap.barrier()
+                if not z_ahead:
+                    for r, w in enumerate(kernels):
+                        for a, b in self.mine:
+                            zv = z[r * n + a:r * n + b]
+                            ops.dense(x_full[a:b], w, out=zv, peers=zsb.peer_addrs(zv))
+                    heap.barrier()
+                # software pipeline: while the sparse kernel works on row block b+1, the NEXT layer's transform
+                # of block b is computed and stored into every rank's copy on a side stream
+                z_ahead = self.pipeline != "off" and isinstance(nxt, GCNConv)
+                if z_ahead:
+                    if not nxt.built:
+                        nxt.build([(n, widths[l + 1]), None])
+                        nxt.built = True
+                    nsb, nz = self._symbuf(("z", l + 1), n, nxt.channels)
+                    if self._side is None:
+                        self._side = torch.cuda.Stream(device=emb.device, priority=-1)
+                    main = torch.cuda.current_stream(emb.device)
                 for sl in self.csr_slices("norm", graph):
-                    ov = out[sl.row_offset:sl.row_offset + sl.n_rows]
-                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, peers=out_peers(ov, sl.row_offset))
+                    a, b = sl.row_offset, sl.row_offset + sl.n_rows
+                    ov = out[a:b]
+                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, peers=out_peers(ov, a))
+                    if z_ahead:
+                        done = torch.cuda.Event()
+                        done.record(main)
+                        with torch.cuda.stream(self._side):
+                            self._side.wait_event(done)
+                            zv = nz[a:b]
+                            if self.pipeline == "ce":
+                                ops.dense(ov, nxt.kernel, out=zv)
+                                for addr in nsb.peer_addrs(zv):
+                                    ops.peer_copy(addr, zv)
+                            else:
+                                ops.dense(ov, nxt.kernel, out=zv, peers=nsb.peer_addrs(zv))
+                if z_ahead:
+                    pushed = torch.cuda.Event()
+                    pushed.record(self._side)
+                    main.wait_event(pushed)
+                    heap.barrier()
             elif isinstance(layer, GATConv):
                 zsb, z = self._symbuf(("z", l), n, layer.channels)
                 qsb, q = self._symbuf(("q", l), n, 1)

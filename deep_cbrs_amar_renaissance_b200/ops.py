@@ -240,6 +240,20 @@ def gather_rows(x, idx, out=None):
     return out
 
 
+def peer_copy(dst_addr, src):
+    """copy-engine transfer of a contiguous tensor into a peer-mapped address (cbrs_peer_copy)"""
+    if not src.is_contiguous():
+        raise L.CbrsError("peer_copy: source must be contiguous")
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(L.load().cbrs_peer_copy(ctypes.c_void_p(dst_addr), _ptr(src), src.numel() * src.element_size(), _stream()),
+            "cbrs_peer_copy")
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("peer_copy", e0, e1, src.numel() * src.element_size()))
+
+
 # ------------------------------------------------------------------ top-k
 def topk_rows(scores, k):
     lib = L.load()

@@ -229,6 +229,9 @@ int cbrs_peer_free(void *ptr);
 int cbrs_peer_export(void *ptr, unsigned char *handle_host);
 int cbrs_peer_open(const unsigned char *handle_host, void **ptr_out);
 int cbrs_peer_close(void *ptr);
+/* copy-engine transfer into a peer-mapped buffer (no SMs): the alternative to the fused stores when the
+ * producer's rows should travel while ANOTHER kernel owns the SMs */
+int cbrs_peer_copy(void *dst, const void *src, size_t bytes, void *stream);
 /* flags_peers_host[r] = rank r's flag array (uint64[CBRS_MAX_PEERS], peer-mapped; own for r == my_rank) */
 int cbrs_peer_barrier(void *const *flags_peers_host, int n_ranks, int my_rank, uint64_t epoch,
                       int32_t *status, double timeout_s, void *stream);
