@@ -68,6 +68,20 @@ _SIGS = {
                                    POINTER(c_void_p), c_int, P, c_size_t, P]),
     "cbrs_dense_bcast": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int, c_int,
                                  P, P, P, P, P, c_int64, POINTER(c_void_p), POINTER(c_void_p), c_int, P]),
+    "cbrs_act_grad": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int, P, c_int64, P]),
+    "cbrs_dense_grad_w_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "cbrs_dense_grad_w": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, c_int64, c_int64, c_int32, P, P,
+                                  P, c_size_t, P]),
+    "cbrs_transpose_f32": (c_int, [P, c_int32, c_int32, P, P]),
+    "cbrs_scatter_add_rows_workspace_bytes": (c_size_t, [c_int64]),
+    "cbrs_scatter_add_rows": (c_int, [P, c_int64, P, c_int64, c_int32, c_int64, P, c_int64, P, c_size_t, P]),
+    "cbrs_l2norm_act": (c_int, [P, c_int64, c_int64, c_int32, c_int, P, c_int64, P]),
+    "cbrs_l2norm_relu_grad": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int, P, c_int64, P]),
+    "cbrs_scale_rows_inv_degree": (c_int, [P, c_int64, P, c_int64, c_int32, P, c_int64, P]),
+    "cbrs_axpby2d": (c_int, [P, c_int64, c_float, P, c_int64, c_float, c_int64, c_int32, P, c_int64, P]),
+    "cbrs_bce": (c_int, [P, P, c_int64, P, P, P, P]),
+    "cbrs_sum_squares": (c_int, [P, c_int64, c_float, P, c_int, P]),
+    "cbrs_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_float, P]),
     "cbrs_synth_bipartite": (c_int, [c_int64, c_int64, c_int64, c_uint64, P, P, P]),
     "cbrs_sort_workspace_bytes": (c_size_t, [c_int64]),
     "cbrs_sort_pairs_u64": (c_int, [P, P, c_int64, c_int, P, c_size_t, P]),

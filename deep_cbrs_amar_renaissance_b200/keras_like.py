@@ -145,14 +145,34 @@ def _shape_of(x):
     return tuple(x.shape) if hasattr(x, "shape") else None
 
 
-class Model(Layer):
-    """compile / predict / evaluate / summary as the reference's Experimenter calls them.
+class History:
+    """What keras `fit` returns: `.history[name]` = one value per epoch."""
 
-    fit() (the training step: backward kernels, BCE + L2, Adam) is row (f)-1 of the
-    scope table, scheduled after the forward path; it raises until then."""
+    def __init__(self):
+        self.history = {}
+        self.epoch = []
+
+
+class Model(Layer):
+    """compile / fit / predict / evaluate / summary as the reference's Experimenter calls them
+    (/root/reference/src/experiment.py:155-197)."""
+
+    loss = optimizer = metrics = None
+    shuffle_seed = 42  # Keras shuffles the batch order of a Sequence with an unseeded RNG; ours is seeded
 
     def compile(self, loss=None, optimizer=None, metrics=None):
+        if loss not in (None, "binary_crossentropy", "BinaryCrossentropy"):
+            raise NotImplementedError("loss '{}': the reference trains with binary_crossentropy "
+                                      "(config.yaml:50)".format(loss))
         self.loss, self.optimizer, self.metrics = loss, optimizer, metrics
+        self._adam = None
+
+    def train_on_batch(self, x, y):
+        """One optimiser step; returns (loss incl. l2 penalty, #correct) as device scalars."""
+        from . import training
+        if getattr(self, "_adam", None) is None:
+            self._adam = training.Adam.from_config(self.optimizer)
+        return training.train_step(self, self._adam, x, y)
 
     def predict(self, sequence):
         outs = []
@@ -174,9 +194,55 @@ class Model(Layer):
             n += len(y)
         return [loss / max(n, 1), acc / max(n, 1)]
 
-    def fit(self, sequence, epochs=1, workers=1, callbacks=None):
-        raise NotImplementedError("training (backward kernels + Adam) is scheduled after the forward hot path; "
-                                  "see DESIGN.md 'what comes next'")
+    def fit(self, sequence, epochs=1, workers=1, callbacks=None, shuffle=True, verbose=0):
+        """Keras `fit` over a `Sequence` (/root/reference/src/experiment.py:183-188): per epoch every batch
+        once, in shuffled batch order, `sequence.on_epoch_end()` after the last one (the reference's
+        datasets reshuffle their rows there, src/data/datasets.py:205-213); callbacks receive the Keras
+        hooks the reference's own callbacks implement (src/utilities/keras.py:43-90).  `workers` is accepted
+        and ignored (batches are index slices of an in-memory array)."""
+        callbacks = list(callbacks or [])
+        hist = History()
+
+        def fire(name, *args):
+            for cb in callbacks:
+                fn = getattr(cb, name, None)
+                if fn is not None:
+                    fn(*args)
+
+        for cb in callbacks:
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            else:
+                cb.model = self
+        rng = np.random.RandomState(self.shuffle_seed)
+        fire("on_train_begin", {})
+        logs = {}
+        for epoch in range(int(epochs)):
+            fire("on_epoch_begin", epoch, {})
+            order = rng.permutation(len(sequence)) if shuffle else np.arange(len(sequence))
+            losses, corrects, sizes = [], [], []
+            for step, b in enumerate(order):
+                x, y = sequence[int(b)]
+                fire("on_train_batch_begin", step, {})
+                loss, correct = self.train_on_batch(x, y)
+                losses.append(loss)
+                corrects.append(correct)
+                sizes.append(len(y))
+                fire("on_train_batch_end", step, {})
+            n = float(sum(sizes))
+            lv = torch.cat(losses).double().cpu().numpy()
+            cv = torch.cat(corrects).double().cpu().numpy()
+            logs = {"loss": float((lv * np.asarray(sizes)).sum() / n), "accuracy": float(cv.sum() / n)}
+            for k, v in logs.items():
+                hist.history.setdefault(k, []).append(v)
+            hist.epoch.append(epoch)
+            if hasattr(sequence, "on_epoch_end"):
+                sequence.on_epoch_end()
+            if verbose:
+                print("epoch {}: {}".format(epoch + 1, logs))
+            fire("on_epoch_end", epoch, logs)
+        fire("on_train_end", logs)
+        return hist
 
     def summary(self, print_fn=print, expand_nested=True):
         print_fn("Model: {}".format(type(self).__name__))

@@ -330,3 +330,152 @@ def sort_pairs_u64(keys, payload, key_bits):
     L.check(lib.cbrs_sort_pairs_u64(_ptr(keys, torch.int64), _ptr(payload, torch.int32), n, key_bits, _ptr(ws),
                                     ws.numel(), _stream()), "cbrs_sort_pairs_u64")
     return keys, payload
+
+
+# ------------------------------------------------------------------ training step (scope row (f)-1)
+def act_grad(dout, out, act):
+    """dPre = dOut * act'(out)"""
+    lib = L.load()
+    dout, ldd = _rowmajor(dout)
+    out, ldo = _rowmajor(out)
+    rows, d = out.shape
+    dpre = torch.empty(rows, d, dtype=torch.float32, device=out.device)
+    code = act if isinstance(act, int) else L.ACTS[act]
+    L.check(lib.cbrs_act_grad(_ptr(dout), ldd, _ptr(out), ldo, rows, d, code, _ptr(dpre), d, _stream()), "cbrs_act_grad")
+    _count(1)
+    return dpre
+
+
+def dense_grad_w(x1, dpre, x2=None, idx1=None, idx2=None, want_bias=True):
+    """(dW [f1+f2, n], db [n] or None) of out = [x1[idx1] || x2[idx2]] @ W + b given dPre [m, n]"""
+    lib = L.load()
+    x1, ld1 = _rowmajor(x1)
+    f1, f2, ld2 = x1.shape[1], 0, 0
+    if x2 is not None:
+        x2, ld2 = _rowmajor(x2)
+        f2 = x2.shape[1]
+    dpre, ldd = _rowmajor(dpre)
+    m, n = dpre.shape
+    dw = torch.empty(f1 + f2, n, dtype=torch.float32, device=dpre.device)
+    db = torch.empty(n, dtype=torch.float32, device=dpre.device) if want_bias else None
+    ws = _ws(lib.cbrs_dense_grad_w_workspace_bytes(m, f1 + f2, n), dpre.device)
+    L.check(lib.cbrs_dense_grad_w(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2, _ptr(idx2, torch.int64), f2,
+                                  _ptr(dpre), ldd, m, n, _ptr(dw), _ptr(db), _ptr(ws), ws.numel(), _stream()),
+            "cbrs_dense_grad_w")
+    _count(3 if want_bias else 2)
+    return dw, db
+
+
+def colsum(x):
+    """column sums of a [m, n] matrix in the fixed slab order of cbrs_dense_grad_w (its db output)"""
+    _, db = dense_grad_w(x[:, :1], x, want_bias=True)
+    return db
+
+
+def transpose(w):
+    lib = L.load()
+    if w.dim() != 2 or not w.is_contiguous():
+        raise L.CbrsError("transpose: expected a contiguous 2-D tensor")
+    out = torch.empty(w.shape[1], w.shape[0], dtype=torch.float32, device=w.device)
+    L.check(lib.cbrs_transpose_f32(_ptr(w, torch.float32), w.shape[0], w.shape[1], _ptr(out), _stream()),
+            "cbrs_transpose_f32")
+    _count(1)
+    return out
+
+
+def scatter_add_rows(src, idx, dst):
+    """dst[idx[m]] += src[m] (duplicates added in ascending m)"""
+    lib = L.load()
+    src, lds = _rowmajor(src)
+    dst, ldd = _rowmajor(dst)
+    m, d = src.shape
+    ws = _ws(lib.cbrs_scatter_add_rows_workspace_bytes(m), src.device)
+    L.check(lib.cbrs_scatter_add_rows(_ptr(src), lds, _ptr(idx, torch.int64), m, d, dst.shape[0], _ptr(dst), ldd,
+                                      _ptr(ws), ws.numel(), _stream()), "cbrs_scatter_add_rows")
+    _count(4)
+    return dst
+
+
+def l2norm_act(v, relu=True, out=None):
+    lib = L.load()
+    v, ldv = _rowmajor(v)
+    rows, d = v.shape
+    if out is None:
+        out = torch.empty(rows, d, dtype=torch.float32, device=v.device)
+    out, ldo = _rowmajor(out)
+    L.check(lib.cbrs_l2norm_act(_ptr(v), ldv, rows, d, 1 if relu else 0, _ptr(out), ldo, _stream()), "cbrs_l2norm_act")
+    _count(1)
+    return out
+
+
+def l2norm_relu_grad(v, dout, relu=True):
+    lib = L.load()
+    v, ldv = _rowmajor(v)
+    dout, ldd = _rowmajor(dout)
+    rows, d = v.shape
+    dv = torch.empty(rows, d, dtype=torch.float32, device=v.device)
+    L.check(lib.cbrs_l2norm_relu_grad(_ptr(v), ldv, _ptr(dout), ldd, rows, d, 1 if relu else 0, _ptr(dv), d, _stream()),
+            "cbrs_l2norm_relu_grad")
+    _count(1)
+    return dv
+
+
+def scale_rows_inv_degree(x, rowptr):
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    rows, d = x.shape
+    out = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+    L.check(lib.cbrs_scale_rows_inv_degree(_ptr(x), ldx, _ptr(rowptr, torch.int64), rows, d, _ptr(out), d, _stream()),
+            "cbrs_scale_rows_inv_degree")
+    _count(1)
+    return out
+
+
+def axpby(a, ca=1.0, b=None, cb=1.0, out=None):
+    """out = ca*a + cb*b on 2-D (possibly strided) views"""
+    lib = L.load()
+    a, lda = _rowmajor(a)
+    ldb = 0
+    if b is not None:
+        b, ldb = _rowmajor(b)
+    rows, d = a.shape
+    if out is None:
+        out = torch.empty(rows, d, dtype=torch.float32, device=a.device)
+    out, ldo = _rowmajor(out)
+    L.check(lib.cbrs_axpby2d(_ptr(a), lda, float(ca), _ptr(b), ldb, float(cb), rows, d, _ptr(out), ldo, _stream()),
+            "cbrs_axpby2d")
+    _count(1)
+    return out
+
+
+def bce(p, y, want_grad=True):
+    """Keras binary cross-entropy of probabilities p vs labels y (float32 [n]):
+    (loss [1], dLoss/dp [n] or None, correct-count [1])"""
+    lib = L.load()
+    p = p.reshape(-1)
+    n = p.numel()
+    loss = torch.empty(1, dtype=torch.float32, device=p.device)
+    correct = torch.empty(1, dtype=torch.float32, device=p.device)
+    dp = torch.empty(n, dtype=torch.float32, device=p.device) if want_grad else None
+    L.check(lib.cbrs_bce(_ptr(p, torch.float32), _ptr(y, torch.float32), n, _ptr(loss), _ptr(dp), _ptr(correct),
+                         _stream()), "cbrs_bce")
+    _count(1)
+    return loss, dp, correct
+
+
+def sum_squares(w, scale, out, accumulate=True):
+    lib = L.load()
+    L.check(lib.cbrs_sum_squares(_ptr(w, torch.float32), w.numel(), float(scale), _ptr(out, torch.float32),
+                                 1 if accumulate else 0, _stream()), "cbrs_sum_squares")
+    _count(1)
+    return out
+
+
+def adam_step(w, g, m, v, lr_t, beta1, beta2, eps, l2=0.0):
+    lib = L.load()
+    if not (w.is_contiguous() and g.is_contiguous()):
+        raise L.CbrsError("adam_step: weight and gradient must be contiguous")
+    L.check(lib.cbrs_adam_step(_ptr(w, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32),
+                               _ptr(v, torch.float32), w.numel(), float(lr_t), float(beta1), float(beta2), float(eps),
+                               float(l2), _stream()), "cbrs_adam_step")
+    _count(1)

@@ -1,0 +1,399 @@
+"""The training step of the hot path (scope row (f)-1): forward with saved activations,
+explicit backward through scorer, lookup, reduction and GNN layers, loss, l2 penalty, Adam.
+
+The reference trains through Keras `fit` (/root/reference/src/experiment.py:155-188):
+`model.compile(loss='binary_crossentropy', optimizer=Adam(...))`, one `model(batch)` per batch
+with TensorFlow autograd behind it, the l2 penalties registered at src/models/gnn.py:239-246
+and :293-294 added to the loss.  Here the same derivatives are spelled out as kernel calls
+(csrc/train.cu for the new ones; the sparse backward is the forward SpMM because every
+adjacency is symmetric, and dX = dPre W^T is the forward dense kernel on W^T).
+
+A tiny tape keeps the order: every forward helper appends a closure that, given the gradient
+of its output, accumulates the gradients of its inputs (`Node.grad`) and of its weights
+(`Tape.wgrads`).  Nothing here touches torch.autograd.
+"""
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .layers import GATConv, GCNConv, GraphSageConv, LightGCNConv, RGCNConv
+
+
+class Node:
+    """A value on the tape: matrix `x` (optionally seen through the row index `idx`, i.e. the
+    value is x[idx]) and the gradient w.r.t. that value once backward has reached it."""
+    __slots__ = ("x", "idx", "grad", "needs_grad")
+
+    def __init__(self, x, idx=None, needs_grad=True):
+        self.x, self.idx, self.grad, self.needs_grad = x, idx, None, needs_grad
+
+    def add_grad(self, g):
+        if not self.needs_grad:
+            return
+        self.grad = g if self.grad is None else ops.axpby(self.grad, 1.0, g, 1.0)
+
+
+class Tape:
+    def __init__(self):
+        self.ops = []
+        self.wgrads = {}   # id(weight) -> gradient tensor (same shape, contiguous)
+        self.weights = {}  # id(weight) -> weight
+
+    def wgrad(self, w, g):
+        if w is None or g is None:
+            return
+        g = g.reshape(w.shape)
+        k = id(w)
+        self.weights[k] = w
+        self.wgrads[k] = g if k not in self.wgrads else ops.axpby(self.wgrads[k].reshape(g.shape[0], -1), 1.0,
+                                                                   g.reshape(g.shape[0], -1), 1.0).reshape(w.shape)
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+
+
+# ------------------------------------------------------------------ Dense stacks
+def dense_train(tape, layer, srcs):
+    """Keras Dense on one or two (possibly row-indexed) sources, recorded on the tape."""
+    s1 = srcs[0]
+    s2 = srcs[1] if len(srcs) > 1 else None
+    f1 = s1.x.shape[1]
+    layer.build_for(f1 + (s2.x.shape[1] if s2 is not None else 0))
+    out = ops.dense(s1.x, layer.kernel, layer.bias, layer.activation, x2=s2.x if s2 is not None else None,
+                    idx1=s1.idx, idx2=s2.idx if s2 is not None else None)
+    node = Node(out)
+
+    def bwd():
+        if node.grad is None:
+            return
+        dpre = ops.act_grad(node.grad, out, layer.activation)
+        dw, db = ops.dense_grad_w(s1.x, dpre, x2=s2.x if s2 is not None else None, idx1=s1.idx,
+                                  idx2=s2.idx if s2 is not None else None, want_bias=layer.bias is not None)
+        tape.wgrad(layer.kernel, dw)
+        tape.wgrad(layer.bias, db)
+        if s1.needs_grad or (s2 is not None and s2.needs_grad):
+            da = ops.dense(dpre, ops.transpose(layer.kernel))
+            s1.add_grad(da[:, :f1])
+            if s2 is not None:
+                s2.add_grad(da[:, f1:])
+
+    tape.ops.append(bwd)
+    return node
+
+
+def stack_train(tape, stack, srcs):
+    """DenseStack (models.Sequential of Dense) -> list of output nodes (the inputs themselves when
+    the stack is empty, as in BasicRS with dense_units=[])."""
+    if not stack.layers:
+        return list(srcs)
+    node = dense_train(tape, stack.layers[0], srcs)
+    for layer in stack.layers[1:]:
+        node = dense_train(tape, layer, [node])
+    return [node]
+
+
+def basic_rs_train(tape, rs, u_src, i_src):
+    """BasicRS.call (/root/reference/src/models/basic.py:31-37)"""
+    u = stack_train(tape, rs.unet, [u_src])
+    i = stack_train(tape, rs.inet, [i_src])
+    return stack_train(tape, rs.clf, u + i)[0]
+
+
+def hybrid_rs_train(tape, rs, ug, ig, ub, ib):
+    """HybridCBRS.call (/root/reference/src/models/hybrid.py:72-89), concatenate fusion"""
+    for name in ("dense1a", "dense1b", "dense2a", "dense2b", "dense3a", "dense3b"):
+        if not getattr(rs, name).layers:
+            raise NotImplementedError("training a HybridCBRS with an empty '%s' stack" % name)
+    ug = stack_train(tape, rs.dense1a, [ug])[0]
+    ig = stack_train(tape, rs.dense1b, [ig])[0]
+    ub = stack_train(tape, rs.dense2a, [ub])[0]
+    ib = stack_train(tape, rs.dense2b, [ib])[0]
+    if rs.feature_based:
+        x1 = stack_train(tape, rs.dense3a, [ug, ig])[0]
+        x2 = stack_train(tape, rs.dense3b, [ub, ib])[0]
+    else:
+        x1 = stack_train(tape, rs.dense3a, [ug, ub])[0]
+        x2 = stack_train(tape, rs.dense3b, [ig, ib])[0]
+    return stack_train(tape, rs.clf, [x1, x2])[0]
+
+
+# ------------------------------------------------------------------ GNN layers
+def _gcn_train(tape, layer, x_node, graph, out):
+    """GCNConv / RGCNConv: y = act(A_hat (x W) + b).  Backward: dPre = dY*act'(y); db = colsum dPre;
+    dZ = A_hat dPre (A_hat symmetric; for the relational operator the per-relation blocks of its
+    transpose are the same operator on the stacked layout, see below); dW = x^T dZ; dx = dZ W^T."""
+    x = x_node.x
+    csr = graph.norm
+    n = x.shape[0]
+    relational = isinstance(layer, RGCNConv)
+    if relational:
+        raise NotImplementedError("training the relational extension needs the transposed per-relation operator")
+    kernels = layer.kernels if relational else [layer.kernel]
+    z = torch.empty(len(kernels) * n, layer.channels, dtype=torch.float32, device=x.device)
+    for r, w in enumerate(kernels):
+        ops.dense(x, w, out=z[r * n:(r + 1) * n])
+    y = ops.spmm(csr, z, out, bias=layer.bias, relu=layer.activation == "relu")
+    node = Node(y)
+
+    def bwd():
+        if node.grad is None:
+            return
+        dpre = ops.act_grad(node.grad, y, layer.activation)
+        if layer.bias is not None:
+            tape.wgrad(layer.bias, ops.colsum(dpre))
+        dz = torch.empty(n, layer.channels, dtype=torch.float32, device=x.device)
+        ops.spmm(csr, dpre, dz)
+        dw, _ = ops.dense_grad_w(x, dz, want_bias=False)
+        tape.wgrad(layer.kernel, dw)
+        x_node.add_grad(ops.dense(dz, ops.transpose(layer.kernel)))
+
+    tape.ops.append(bwd)
+    return node
+
+
+def _lightgcn_train(tape, layer, x_node, graph, out):
+    csr = graph.norm
+    y = ops.spmm(csr, x_node.x, out)
+    node = Node(y)
+
+    def bwd():
+        if node.grad is None:
+            return
+        dx = torch.empty_like(y) if y.is_contiguous() else torch.empty(y.shape, dtype=torch.float32, device=y.device)
+        g = node.grad if node.grad.stride(1) == 1 else node.grad.contiguous()
+        ops.spmm(csr, g, dx)
+        x_node.add_grad(dx)
+
+    tape.ops.append(bwd)
+    return node
+
+
+def _sage_train(tape, layer, x_node, graph, out):
+    """GraphSageConv: agg = mean/sum over the raw edge list; v = [x || agg] W + b; out = relu(v / |v|).
+    Training keeps v (the fused inference epilogue does not), so the epilogue is its own kernel."""
+    x = x_node.x
+    csr = graph.raw
+    f = x.shape[1]
+    mean = layer.aggregate == "mean"
+    agg = torch.empty(csr.n_rows, f, dtype=torch.float32, device=x.device)
+    ops.spmm(csr, x, agg, agg=L.AGG_MEAN if mean else L.AGG_SUM)
+    v = ops.dense(x, layer.kernel, layer.bias, None, x2=agg)
+    relu = layer.activation == "relu"
+    y = ops.l2norm_act(v, relu=relu, out=out)
+    node = Node(y)
+
+    def bwd():
+        if node.grad is None:
+            return
+        dv = ops.l2norm_relu_grad(v, node.grad, relu=relu)
+        dw, db = ops.dense_grad_w(x, dv, x2=agg, want_bias=layer.bias is not None)
+        tape.wgrad(layer.kernel, dw)
+        tape.wgrad(layer.bias, db)
+        da = ops.dense(dv, ops.transpose(layer.kernel))
+        dagg = da[:, f:]
+        t = ops.scale_rows_inv_degree(dagg, csr.rowptr) if mean else dagg.contiguous()
+        dxa = torch.empty(csr.n_rows, f, dtype=torch.float32, device=x.device)
+        ops.spmm(csr, t, dxa, agg=L.AGG_SUM)  # A^T = A: the raw edge list holds both directions of every edge
+        x_node.add_grad(ops.axpby(da[:, :f], 1.0, dxa, 1.0))
+
+    tape.ops.append(bwd)
+    return node
+
+
+def gnn_train(tape, seq):
+    """SequentialGNN.call (/root/reference/src/models/gnn.py:74-84) on the tape -> Node of [N, D_out]."""
+    emb = seq.embeddings
+    n = emb.shape[0]
+    widths = seq._widths()
+    graph = seq.adj_matrix
+    if seq.partition is not None:
+        raise NotImplementedError("training runs on one GPU (the row partition covers the forward path)")
+    concat = seq.final_node == 'concatenation'
+    if seq.final_node not in ('concatenation', 'mean', 'sum', 'last'):
+        raise NotImplementedError("training with final_node='%s'" % seq.final_node)
+    buf = torch.empty(n, sum(widths), dtype=torch.float32, device=emb.device) if concat else None
+    e_node = Node(emb)
+    nodes = [e_node]
+    off = widths[0]
+    if concat:
+        buf[:, :widths[0]].copy_(emb)
+    x_node = e_node
+    for layer, w in zip(seq.seq_layers, widths[1:]):
+        if not layer.built:
+            layer.build([(n, x_node.x.shape[1]), None])
+            layer.built = True
+        out = buf[:, off:off + w] if concat else torch.empty(n, w, dtype=torch.float32, device=emb.device)
+        off += w
+        if isinstance(layer, (GCNConv, RGCNConv)):
+            x_node = _gcn_train(tape, layer, x_node, graph, out)
+        elif isinstance(layer, LightGCNConv):
+            x_node = _lightgcn_train(tape, layer, x_node, graph, out)
+        elif isinstance(layer, GraphSageConv):
+            x_node = _sage_train(tape, layer, x_node, graph, out)
+        elif isinstance(layer, GATConv):
+            raise NotImplementedError("GATConv backward (edge-softmax gradient) is not built yet; GCN, GraphSage "
+                                      "and LightGCN train")
+        else:
+            raise NotImplementedError("no training form for {}".format(type(layer).__name__))
+        nodes.append(x_node)
+    k1 = len(nodes)
+    if concat:
+        red = buf
+    elif seq.final_node == 'last':
+        red = nodes[-1].x
+    else:
+        red = ops.reduce_layers([nd.x for nd in nodes], divide_by=float(k1) if seq.final_node == 'mean' else 1.0)
+    red_node = Node(red)
+
+    def bwd_reduce():
+        g = red_node.grad
+        if g is None:
+            return
+        if concat:
+            o = 0
+            for nd, w in zip(nodes, widths):
+                nd.add_grad(g[:, o:o + w])
+                o += w
+        elif seq.final_node == 'last':
+            nodes[-1].add_grad(g)
+        else:
+            gs = ops.axpby(g, 1.0 / k1) if seq.final_node == 'mean' else g
+            for nd in nodes:
+                nd.add_grad(gs)
+
+    # order on the tape: embeddings sink first (runs last), then the layers (appended above, already
+    # in forward order), then the reduction (runs first)
+    def bwd_embeddings():
+        if e_node.grad is not None:
+            g = e_node.grad
+            tape.wgrad(emb, g if g.is_contiguous() else g.contiguous())
+
+    tape.ops.insert(0, bwd_embeddings)
+    tape.ops.append(bwd_reduce)
+    return red_node
+
+
+def lookup_train(tape, table_node, ids_list):
+    """tf.nn.embedding_lookup of the propagated table for each id vector
+    (/root/reference/src/models/basic.py:72-75) -> one indexed Node per id vector."""
+    srcs = [Node(table_node.x, idx) for idx in ids_list]
+
+    def bwd():
+        g = None
+        for s in srcs:
+            if s.grad is None:
+                continue
+            if g is None:
+                g = torch.zeros(table_node.x.shape, dtype=torch.float32, device=table_node.x.device)
+            ops.scatter_add_rows(s.grad, s.idx, g)
+        if g is not None:
+            table_node.add_grad(g)
+
+    tape.ops.append(bwd)
+    return srcs
+
+
+# ------------------------------------------------------------------ optimiser
+class Adam:
+    """keras.optimizers.Adam(learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7)
+    (/root/reference/config.yaml:52-56; Keras defaults for what the file leaves out)."""
+
+    def __init__(self, learning_rate=1e-3, beta_1=0.9, beta_2=0.999, epsilon=1e-7, **kwargs):
+        self.learning_rate, self.beta_1, self.beta_2, self.epsilon = (float(learning_rate), float(beta_1),
+                                                                      float(beta_2), float(epsilon))
+        self.iterations = 0
+        self._state = {}
+
+    @classmethod
+    def from_config(cls, cfg):
+        if isinstance(cfg, Adam):
+            return cfg
+        if cfg is None or isinstance(cfg, str):
+            if cfg not in (None, "adam", "Adam"):
+                raise NotImplementedError("optimizer '%s' (the reference's configs use Adam)" % cfg)
+            return cls()
+        if isinstance(cfg, dict):
+            cfg = dict(cfg)
+            cfg.pop("name", None)
+            return cls(**cfg)
+        get = lambda k, d: float(getattr(cfg, k, d))  # a keras-like optimizer object
+        return cls(get("learning_rate", 1e-3), get("beta_1", 0.9), get("beta_2", 0.999), get("epsilon", 1e-7))
+
+    def apply(self, weights, grads, l2s):
+        self.iterations += 1
+        t = self.iterations
+        lr_t = self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+        for w, g, l2 in zip(weights, grads, l2s):
+            st = self._state.get(id(w))
+            if st is None:
+                st = self._state[id(w)] = (torch.zeros_like(w), torch.zeros_like(w))
+            ops.adam_step(w, g if g.is_contiguous() else g.contiguous(), st[0], st[1], lr_t, self.beta_1, self.beta_2,
+                          self.epsilon, l2)
+
+
+# ------------------------------------------------------------------ one step
+def forward_backward(model, inputs, y):
+    """Forward with saved activations, loss, backward.  Returns (tape, loss [1], correct [1], probs)."""
+    from .models.basic import BasicGNN, _ids
+    from .models.hybrid import HybridBertGNN, _rows
+    tape = Tape()
+    red = gnn_train(tape, model.gnn.gnn_layers)
+    if isinstance(model, BasicGNN):
+        u, i = _ids(inputs[0]), _ids(inputs[1])
+        model.rs.build_for(red.x.shape[1])
+        us, is_ = lookup_train(tape, red, [u, i])
+        p = basic_rs_train(tape, model.rs, us, is_)
+    elif isinstance(model, HybridBertGNN):
+        if len(inputs) == 2:
+            if model.content_table is None:
+                raise ValueError("ids-only call needs set_content_table(...) first")
+            u, i = _ids(inputs[0]), _ids(inputs[1])
+            ub, ib = Node(model.content_table, u, needs_grad=False), Node(model.content_table, i, needs_grad=False)
+        else:
+            u, i = _ids(inputs[0]), _ids(inputs[1])
+            ub, ib = Node(_rows(inputs[2]), None, needs_grad=False), Node(_rows(inputs[3]), None, needs_grad=False)
+        model.rs.build_for(red.x.shape[1], ub.x.shape[1])
+        us, is_ = lookup_train(tape, red, [u, i])
+        p = hybrid_rs_train(tape, model.rs, us, is_, ub, ib)
+    else:
+        raise NotImplementedError("no training form for {}".format(type(model).__name__))
+    yt = y if isinstance(y, torch.Tensor) else torch.as_tensor(y)
+    yt = yt.to(device=p.x.device, dtype=torch.float32).reshape(-1)
+    loss, dp, correct = ops.bce(p.x, yt)
+    p.grad = dp.reshape(-1, 1)
+    tape.backward()
+    return tape, loss, correct, p.x
+
+
+def l2_coefficients(model):
+    """id(weight) -> l2 coefficient, from the regularisers attached at add_weight time."""
+    out = {}
+
+    def walk(layer):
+        for name, w in layer._weights.items():
+            reg = layer._regularizers.get(name)
+            if reg is not None:
+                out[id(w)] = reg.l2
+        for _, sub in layer._sublayers():
+            walk(sub)
+
+    walk(model)
+    return out
+
+
+def train_step(model, optimizer, inputs, y):
+    """One optimiser step on one batch.  Returns device scalars (loss incl. the l2 penalty, #correct)."""
+    tape, loss, correct, _ = forward_backward(model, inputs, y)
+    l2 = l2_coefficients(model)
+    ws = [w for w in model.trainable_weights if id(w) in tape.wgrads]
+    for w in ws:
+        c = l2.get(id(w), 0.0)
+        if c:
+            ops.sum_squares(w, c, loss, accumulate=True)
+    optimizer.apply(ws, [tape.wgrads[id(w)] for w in ws], [l2.get(id(w), 0.0) for w in ws])
+    if hasattr(model, "invalidate"):
+        model.invalidate()
+    return loss, correct

@@ -250,6 +250,49 @@ int cbrs_dense_bcast(const float *x1, int64_t ld1, const int64_t *idx1, int32_t 
                      float *q_out, float *out, int64_t ldo, void *const *out_peers_host,
                      void *const *q_peers_host, int n_peers, void *stream);
 
+/* ---- training step (scope row (f)-1) ------------------------------------------------------
+ * The reference differentiates with TensorFlow autograd inside Keras `fit`
+ * (src/experiment.py:155-188): loss = binary cross-entropy (config.yaml:50) + l2 * sum w^2 over
+ * the embeddings and GNN kernels/biases (src/models/gnn.py:239-246), optimiser Adam(1e-3, 0.9)
+ * (config.yaml:52-56).  Here each derivative is an explicit kernel; the sparse backward is
+ * cbrs_spmm_csr itself (A_hat is symmetric) and dX = dPre W^T is cbrs_dense on W^T.
+ * All reductions use a fixed order: gradients are reproducible run to run.                  */
+/* dPre = dOut * act'(out) for CBRS_ACT_*; 2-D strided views */
+int cbrs_act_grad(const float *dout, int64_t ldd, const float *out, int64_t ldo, int64_t rows, int32_t d,
+                  int act, float *dpre, int64_t ldp, void *stream);
+/* dW[f1+f2, n] = [X1[idx1] || X2[idx2]]^T dPre[m, n];  db[n] = column sums of dPre (db may be NULL) */
+size_t cbrs_dense_grad_w_workspace_bytes(int64_t m, int32_t k, int32_t n);
+int cbrs_dense_grad_w(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2,
+                      int64_t ld2, const int64_t *idx2, int32_t f2, const float *dpre, int64_t ldd, int64_t m,
+                      int32_t n, float *dw, float *db, void *workspace, size_t workspace_bytes, void *stream);
+int cbrs_transpose_f32(const float *src, int32_t rows, int32_t cols, float *dst, void *stream);
+/* dst[idx[m], 0:d] += src[m, 0:d]  (backward of tf.nn.embedding_lookup, src/models/basic.py:72-75);
+ * duplicates are added in ascending m */
+size_t cbrs_scatter_add_rows_workspace_bytes(int64_t m);
+int cbrs_scatter_add_rows(const float *src, int64_t lds, const int64_t *idx, int64_t m, int32_t d,
+                          int64_t n_rows, float *dst, int64_t ldd, void *workspace, size_t workspace_bytes,
+                          void *stream);
+/* GraphSageConv epilogue as its own kernel (training keeps the pre-normalisation v) and its backward */
+int cbrs_l2norm_act(const float *v, int64_t ldv, int64_t rows, int32_t d, int relu, float *out, int64_t ldo,
+                    void *stream);
+int cbrs_l2norm_relu_grad(const float *v, int64_t ldv, const float *dout, int64_t ldd, int64_t rows, int32_t d,
+                          int relu, float *dv, int64_t ldo, void *stream);
+/* out[r,:] = x[r,:] / (rowptr[r+1]-rowptr[r])  (0 for empty rows): mean-aggregator backward = A^T (dAgg / deg) */
+int cbrs_scale_rows_inv_degree(const float *x, int64_t ldx, const int64_t *rowptr, int64_t rows, int32_t d,
+                               float *out, int64_t ldo, void *stream);
+/* out = ca*a + cb*b (b may be NULL) on strided 2-D views */
+int cbrs_axpby2d(const float *a, int64_t lda, float ca, const float *b, int64_t ldb, float cb, int64_t rows,
+                 int32_t d, float *out, int64_t ldo, void *stream);
+/* Keras binary_crossentropy on probabilities (clipped to [1e-7, 1-1e-7]): *loss_out = mean; dp_out[i] =
+ * dLoss/dp_i (0 where the clip is active); *correct_out = #((p > .5) == (y > .5)).  dp/correct may be NULL */
+int cbrs_bce(const float *p, const float *y, int64_t n, float *loss_out, float *dp_out, float *correct_out,
+             void *stream);
+/* *out = (accumulate ? *out : 0) + scale * sum w^2 */
+int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int accumulate, void *stream);
+/* Keras Adam: g' = g + 2*l2*w; m,v updated in place; w -= lr_t * m / (sqrt(v) + eps), lr_t precomputed on the host */
+int cbrs_adam_step(float *w, const float *g, float *m, float *v, int64_t n, float lr_t, float beta1,
+                   float beta2, float eps, float l2, void *stream);
+
 /* ---- primitives exported for tests -------------------------------------------- */
 size_t cbrs_sort_workspace_bytes(int64_t n);
 /* stable ascending sort of 64-bit keys (bits [0,key_bits)) with a 32-bit payload */

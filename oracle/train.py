@@ -1,0 +1,133 @@
+"""Oracle (TEST INFRASTRUCTURE): one training step of the hot path, differentiated by
+torch-CPU autograd in float64/float32, with the Keras Adam update written out.
+
+Restates what Keras `fit` does per batch for the reference's models
+(/root/reference/src/experiment.py:155-188): forward (SequentialGNN + scorer), loss =
+binary cross-entropy on probabilities clipped to [1e-7, 1-1e-7] (Keras backend) + l2 * sum(w^2)
+over the embeddings and GNN kernels/biases (src/models/gnn.py:239-246,293-294), Adam with
+lr_t = lr*sqrt(1-b2^t)/(1-b1^t) and w -= lr_t*m/(sqrt(v)+eps) (Keras optimizer_v2; epsilon 1e-7).
+PARITY UNPINNED for the same reason as oracle/layers.py: TensorFlow/Keras cannot run here.
+The forward reuses the layer definitions of oracle/layers.py, re-expressed on torch tensors so
+autograd can differentiate them; tests/test_gpu_training.py checks the product's explicit
+backward kernels against these gradients.
+"""
+import numpy as np
+import torch
+
+
+def _t(a, dtype):
+    return torch.tensor(np.asarray(a), dtype=dtype, requires_grad=True)
+
+
+def _csr_torch(indptr, indices, data, n, dtype):
+    rows = np.repeat(np.arange(n), np.diff(indptr))
+    idx = torch.tensor(np.stack([rows, np.asarray(indices)]), dtype=torch.int64)
+    return torch.sparse_coo_tensor(idx, torch.tensor(np.asarray(data), dtype=dtype), (n, n)).coalesce()
+
+
+def _dense_stack(x, layers, last_sigmoid=False):
+    for k, (w, b) in enumerate(layers):
+        x = x @ w + b
+        x = torch.sigmoid(x) if (last_sigmoid and k == len(layers) - 1) else torch.relu(x)
+    return x
+
+
+def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregate="mean", l2=0.0, hybrid=False,
+                 feature_based=False, dtype=torch.float64):
+    """w: the export_weights() structure (numpy); graph: scipy CSR A_hat (gcn/lightgcn) or
+    (indptr, indices) of the raw adjacency (sage).  Returns (loss, bce, probs, leaves) where
+    leaves maps names to the torch leaf tensors whose .grad the caller reads after backward()."""
+    leaves = {}
+    emb = leaves["embeddings"] = _t(w["embeddings"], dtype)
+    n = emb.shape[0]
+    if kind in ("gcn", "lightgcn"):
+        a = _csr_torch(graph.indptr, graph.indices, graph.data, n, dtype)
+    else:
+        a = _csr_torch(graph[0], graph[1], np.ones(len(graph[1]), np.float32), n, dtype)
+        deg = torch.tensor(np.diff(graph[0]).astype(np.float64), dtype=dtype).clamp(min=1.0).reshape(-1, 1)
+    x, hs, reg = emb, [emb], []
+    reg.append(emb)
+    for li, lw in enumerate(w["layers"]):
+        if kind == "gcn":
+            k = leaves["layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
+            b = leaves["layers.%d.bias" % li] = _t(lw["bias"], dtype)
+            reg += [k, b]
+            x = torch.relu(torch.sparse.mm(a, x @ k) + b)
+        elif kind == "lightgcn":
+            x = torch.sparse.mm(a, x)
+        elif kind == "sage":
+            k = leaves["layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
+            b = leaves["layers.%d.bias" % li] = _t(lw["bias"], dtype)
+            reg += [k, b]
+            s = torch.sparse.mm(a, x)
+            agg = s / deg if aggregate == "mean" else s
+            o = torch.cat([x, agg], dim=1) @ k + b
+            o = o / torch.sqrt(torch.clamp((o * o).sum(dim=1, keepdim=True), min=1e-12))
+            x = torch.relu(o)
+        else:
+            raise ValueError(kind)
+        hs.append(x)
+    if kind == "lightgcn":
+        final_node = "mean"
+    if final_node == "concatenation":
+        red = torch.cat(hs, dim=1)
+    elif final_node == "mean":
+        red = sum(hs) / len(hs)
+    elif final_node == "sum":
+        red = sum(hs)
+    else:
+        red = hs[-1]
+
+    def stack(name):
+        out = []
+        for k, (kern, bias) in enumerate(w[name]):
+            kk = leaves["%s.%d.kernel" % (name, k)] = _t(kern, dtype)
+            bb = leaves["%s.%d.bias" % (name, k)] = _t(bias, dtype)
+            out.append((kk, bb))
+        return out
+
+    u = torch.as_tensor(np.asarray(inputs[0]), dtype=torch.int64)
+    i = torch.as_tensor(np.asarray(inputs[1]), dtype=torch.int64)
+    if not hybrid:
+        uu = _dense_stack(red[u], stack("unet"))
+        ii = _dense_stack(red[i], stack("inet"))
+        p = _dense_stack(torch.cat([uu, ii], dim=1), stack("clf"), last_sigmoid=True)
+    else:
+        ub = torch.tensor(np.asarray(inputs[2]), dtype=dtype)
+        ib = torch.tensor(np.asarray(inputs[3]), dtype=dtype)
+        ug = _dense_stack(red[u], stack("dense1a"))
+        ig = _dense_stack(red[i], stack("dense1b"))
+        ub = _dense_stack(ub, stack("dense2a"))
+        ib = _dense_stack(ib, stack("dense2b"))
+        if feature_based:
+            x1 = _dense_stack(torch.cat([ug, ig], dim=1), stack("dense3a"))
+            x2 = _dense_stack(torch.cat([ub, ib], dim=1), stack("dense3b"))
+        else:
+            x1 = _dense_stack(torch.cat([ug, ub], dim=1), stack("dense3a"))
+            x2 = _dense_stack(torch.cat([ig, ib], dim=1), stack("dense3b"))
+        p = _dense_stack(torch.cat([x1, x2], dim=1), stack("clf"), last_sigmoid=True)
+    p = p.reshape(-1)
+    yt = torch.tensor(np.asarray(y, dtype=np.float64), dtype=dtype)
+    pc = torch.clamp(p, 1e-7, 1 - 1e-7)
+    bce = -(yt * torch.log(pc) + (1 - yt) * torch.log(1 - pc)).mean()
+    loss = bce
+    if l2:
+        loss = loss + l2 * sum((t * t).sum() for t in reg)
+    return loss, bce, p, leaves
+
+
+def gradients(kind, w, graph, inputs, y, **kw):
+    """{leaf name: dLoss/dleaf (numpy float64)} plus the loss value and the probabilities."""
+    loss, bce, p, leaves = forward_loss(kind, w, graph, inputs, y, **kw)
+    loss.backward()
+    grads = {k: (v.grad.detach().numpy().astype(np.float64) if v.grad is not None else np.zeros(tuple(v.shape)))
+             for k, v in leaves.items()}
+    return grads, float(loss.detach()), p.detach().numpy()
+
+
+def adam_update(w, g, m, v, t, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
+    """One Keras Adam step on numpy arrays (float64 math); returns (w, m, v)."""
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+    return w - lr_t * m / (np.sqrt(v) + eps), m, v

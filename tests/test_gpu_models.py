@@ -288,8 +288,10 @@ def test_predict_evaluate_and_pair_top_k(tmp_path):
                                           ratings_pred[:, 2].astype(np.float32), k)
         assert df['users'].tolist() == train.users[uu].tolist()
         assert df['items'].tolist() == train.items[ii.astype(np.int64) - len(train.users)].tolist()
-    with pytest.raises(NotImplementedError):
-        model.fit(train, epochs=1)
+    # the reference's Experimenter.train call (experiment.py:183-188) on the golden fixture's Sequence
+    model.compile(loss="binary_crossentropy", optimizer={"learning_rate": 1e-3, "beta_1": 0.9}, metrics=["accuracy"])
+    hist = model.fit(train, epochs=2, workers=1, callbacks=[])
+    assert len(hist.history["loss"]) == 2 and np.isfinite(hist.history["loss"]).all()
 
 
 def test_large_graph_properties():
