@@ -21,6 +21,8 @@
 // cbrs_spmm_csr on the same CSR.
 #include "common.cuh"
 
+#include <string.h>
+
 namespace cbrs {
 
 // ------------------------------------------------------------------ activation backward
@@ -276,9 +278,11 @@ __global__ void __launch_bounds__(1024) sum_squares_kernel(const float *__restri
 // Keras Adam (optimizer_v2): lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m, v moving averages;
 // w -= lr_t * m / (sqrt(v) + eps).  The l2 regulariser's gradient 2*l2*w joins g here.
 __global__ void adam_kernel(float *__restrict__ w, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-                            int64_t n, float lr_t, float b1, float b2, float eps, float l2) {
+                            int64_t n, float lr_t, const float *__restrict__ lr_t_dev, float b1, float b2, float eps,
+                            float l2) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (lr_t_dev) lr_t = *lr_t_dev;  // CUDA-graph replay: the step-dependent rate lives in device memory
     const float wi = w[i];
     const float gi = fmaf(2.f * l2, wi, g[i]);
     const float mi = fmaf(1.f - b1, gi - m[i], m[i]);
@@ -288,9 +292,68 @@ __global__ void adam_kernel(float *__restrict__ w, const float *__restrict__ g, 
     w[i] = wi - lr_t * mi / (sqrtf(vi) + eps);
 }
 
+constexpr int kAdamMaxTensors = 48;
+struct AdamMultiParams {
+    float *w[kAdamMaxTensors];
+    const float *g[kAdamMaxTensors];
+    float *m[kAdamMaxTensors];
+    float *v[kAdamMaxTensors];
+    int64_t n[kAdamMaxTensors];
+    float l2[kAdamMaxTensors];
+    int32_t block_end[kAdamMaxTensors];  // exclusive prefix of 256-thread blocks
+    int n_tensors;
+    float lr_t;
+    const float *lr_t_dev;
+    float b1, b2, eps;
+};
+
+// one launch for all weight tensors of the model (a step updates ~40 small tensors)
+__global__ void __launch_bounds__(256) adam_multi_kernel(const AdamMultiParams p) {
+    int t = 0;
+    while (t < p.n_tensors - 1 && (int)blockIdx.x >= p.block_end[t]) ++t;
+    const int first = t == 0 ? 0 : p.block_end[t - 1];
+    const int64_t i = (int64_t)(blockIdx.x - first) * 256 + threadIdx.x;
+    if (i >= p.n[t]) return;
+    const float lr_t = p.lr_t_dev ? *p.lr_t_dev : p.lr_t;
+    const float wi = p.w[t][i];
+    const float gi = fmaf(2.f * p.l2[t], wi, p.g[t][i]);
+    const float mi = fmaf(1.f - p.b1, gi - p.m[t][i], p.m[t][i]);
+    const float vi = fmaf(1.f - p.b2, gi * gi - p.v[t][i], p.v[t][i]);
+    p.m[t][i] = mi;
+    p.v[t][i] = vi;
+    p.w[t][i] = wi - lr_t * mi / (sqrtf(vi) + p.eps);
+}
+
 }  // namespace cbrs
 
 using namespace cbrs;
+
+extern "C" int cbrs_adam_step_multi(int32_t n_tensors, void *const *w_host, const void *const *g_host, void *const *m_host,
+                                    void *const *v_host, const int64_t *n_host, const float *l2_host, float lr_t,
+                                    const float *lr_t_dev, float beta1, float beta2, float eps, void *stream) {
+    CBRS_REQUIRE(n_tensors >= 0 && w_host && g_host && m_host && v_host && n_host, CBRS_E_INVALID,
+                 "adam_step_multi: bad argument");
+    for (int base = 0; base < n_tensors; base += kAdamMaxTensors) {
+        AdamMultiParams p;
+        memset(&p, 0, sizeof(p));
+        const int cnt = n_tensors - base < kAdamMaxTensors ? n_tensors - base : kAdamMaxTensors;
+        int64_t blocks = 0;
+        for (int t = 0; t < cnt; ++t) {
+            CBRS_REQUIRE(w_host[base + t] && g_host[base + t] && m_host[base + t] && v_host[base + t] && n_host[base + t] > 0,
+                         CBRS_E_INVALID, "adam_step_multi: tensor %d", base + t);
+            p.w[t] = (float *)w_host[base + t]; p.g[t] = (const float *)g_host[base + t];
+            p.m[t] = (float *)m_host[base + t]; p.v[t] = (float *)v_host[base + t];
+            p.n[t] = n_host[base + t]; p.l2[t] = l2_host ? l2_host[base + t] : 0.f;
+            blocks += cdiv(p.n[t], 256);
+            CBRS_REQUIRE(blocks < ((int64_t)1 << 31), CBRS_E_INVALID, "adam_step_multi: too many elements");
+            p.block_end[t] = (int32_t)blocks;
+        }
+        p.n_tensors = cnt; p.lr_t = lr_t; p.lr_t_dev = lr_t_dev; p.b1 = beta1; p.b2 = beta2; p.eps = eps;
+        adam_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+        CBRS_CHECK_LAUNCH("adam_step_multi");
+    }
+    return CBRS_OK;
+}
 
 extern "C" int cbrs_act_grad(const float *dout, int64_t ldd, const float *out, int64_t ldo, int64_t rows, int32_t d,
                              int act, float *dpre, int64_t ldp, void *stream) {
@@ -304,13 +367,20 @@ extern "C" int cbrs_act_grad(const float *dout, int64_t ldd, const float *out, i
     return CBRS_OK;
 }
 
-static int grad_w_slabs(int64_t m) {
-    const int64_t want = cdiv(m, 2048);
-    return (int)(want < 1 ? 1 : (want > 256 ? 256 : want));
+// Row slabs: enough of them that tiles x slabs fills the chip twice (a batch-sized GEMM has only a few
+// 32x32 output tiles), never fewer than 32 rows per slab, at most 256.  A pure function of the shape,
+// so the reduction tree - and the bits of dW - are the same on every run.
+static int grad_w_slabs(int64_t m, int32_t k, int32_t n) {
+    const int64_t tiles = cdiv(k, kGwTile) * cdiv(n, kGwTile);
+    int64_t want = cdiv(2 * kSMs, tiles);
+    const int64_t most = cdiv(m, kGwRows);
+    if (want > most) want = most;
+    if (want > 256) want = 256;
+    return (int)(want < 1 ? 1 : want);
 }
 
 extern "C" size_t cbrs_dense_grad_w_workspace_bytes(int64_t m, int32_t k, int32_t n) {
-    const size_t slabs = (size_t)grad_w_slabs(m);
+    const size_t slabs = (size_t)grad_w_slabs(m, k, n);
     return align_up(slabs * (size_t)k * (size_t)n * sizeof(float)) + align_up(slabs * (size_t)n * sizeof(float)) + 256;
 }
 
@@ -326,7 +396,7 @@ extern "C" int cbrs_dense_grad_w(const float *x1, int64_t ld1, const int64_t *id
     GradWParams p;
     p.x1 = x1; p.ld1 = ld1; p.idx1 = idx1; p.f1 = f1; p.x2 = x2; p.ld2 = ld2; p.idx2 = idx2; p.f2 = f2;
     p.dpre = dpre; p.ldd = ldd; p.m = m; p.n = n;
-    p.slabs = grad_w_slabs(m);
+    p.slabs = grad_w_slabs(m, K, n);
     p.rows_per_slab = cdiv(cdiv(m, p.slabs), kGwRows) * kGwRows;
     Arena a(workspace, workspace_bytes);
     p.partial = a.take<float>((size_t)p.slabs * K * n);
@@ -439,10 +509,11 @@ extern "C" int cbrs_sum_squares(const float *w, int64_t n, float scale, float *o
     return CBRS_OK;
 }
 
-extern "C" int cbrs_adam_step(float *w, const float *g, float *m, float *v, int64_t n, float lr_t, float beta1,
-                              float beta2, float eps, float l2, void *stream) {
+extern "C" int cbrs_adam_step(float *w, const float *g, float *m, float *v, int64_t n, float lr_t,
+                              const float *lr_t_dev, float beta1, float beta2, float eps, float l2, void *stream) {
     CBRS_REQUIRE(w && g && m && v && n > 0, CBRS_E_INVALID, "adam_step: bad argument");
-    adam_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, v, n, lr_t, beta1, beta2, eps, l2);
+    adam_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(w, g, m, v, n, lr_t, lr_t_dev, beta1, beta2, eps,
+                                                                          l2);
     CBRS_CHECK_LAUNCH("adam_step");
     return CBRS_OK;
 }

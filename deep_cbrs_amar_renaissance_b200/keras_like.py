@@ -174,6 +174,13 @@ class Model(Layer):
             self._adam = training.Adam.from_config(self.optimizer)
         return training.train_step(self, self._adam, x, y)
 
+    def make_graphed_train_step(self, batch_size, content_dim=None):
+        """CUDA-graph replay of the whole optimiser step for a fixed batch size (training.GraphedTrainStep)."""
+        from . import training
+        if getattr(self, "_adam", None) is None:
+            self._adam = training.Adam.from_config(self.optimizer)
+        return training.GraphedTrainStep(self, self._adam, batch_size, content_dim)
+
     def predict(self, sequence):
         outs = []
         for i in range(len(sequence)):
@@ -194,12 +201,14 @@ class Model(Layer):
             n += len(y)
         return [loss / max(n, 1), acc / max(n, 1)]
 
-    def fit(self, sequence, epochs=1, workers=1, callbacks=None, shuffle=True, verbose=0):
+    def fit(self, sequence, epochs=1, workers=1, callbacks=None, shuffle=True, verbose=0, cuda_graph=False):
         """Keras `fit` over a `Sequence` (/root/reference/src/experiment.py:183-188): per epoch every batch
         once, in shuffled batch order, `sequence.on_epoch_end()` after the last one (the reference's
         datasets reshuffle their rows there, src/data/datasets.py:205-213); callbacks receive the Keras
         hooks the reference's own callbacks implement (src/utilities/keras.py:43-90).  `workers` is accepted
-        and ignored (batches are index slices of an in-memory array)."""
+        and ignored (batches are index slices of an in-memory array).  cuda_graph=True replays full-size
+        batches through one captured CUDA graph of the whole step (same kernels, same results); a short last
+        batch runs eagerly."""
         callbacks = list(callbacks or [])
         hist = History()
 
@@ -215,6 +224,7 @@ class Model(Layer):
             else:
                 cb.model = self
         rng = np.random.RandomState(self.shuffle_seed)
+        graphed = None
         fire("on_train_begin", {})
         logs = {}
         for epoch in range(int(epochs)):
@@ -224,7 +234,15 @@ class Model(Layer):
             for step, b in enumerate(order):
                 x, y = sequence[int(b)]
                 fire("on_train_batch_begin", step, {})
-                loss, correct = self.train_on_batch(x, y)
+                if cuda_graph and len(x) == 2:
+                    if graphed is None and len(sequence) > 1:
+                        graphed = self.make_graphed_train_step(len(sequence[0][1]))
+                    if graphed is not None and len(y) == graphed.batch_size:
+                        loss, correct = graphed(x, y)
+                    else:
+                        loss, correct = self.train_on_batch(x, y)
+                else:
+                    loss, correct = self.train_on_batch(x, y)
                 losses.append(loss)
                 corrects.append(correct)
                 sizes.append(len(y))

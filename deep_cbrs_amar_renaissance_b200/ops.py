@@ -471,11 +471,26 @@ def sum_squares(w, scale, out, accumulate=True):
     return out
 
 
-def adam_step(w, g, m, v, lr_t, beta1, beta2, eps, l2=0.0):
+def adam_step(w, g, m, v, lr_t, beta1, beta2, eps, l2=0.0, lr_t_dev=None):
     lib = L.load()
     if not (w.is_contiguous() and g.is_contiguous()):
         raise L.CbrsError("adam_step: weight and gradient must be contiguous")
     L.check(lib.cbrs_adam_step(_ptr(w, torch.float32), _ptr(g, torch.float32), _ptr(m, torch.float32),
-                               _ptr(v, torch.float32), w.numel(), float(lr_t), float(beta1), float(beta2), float(eps),
-                               float(l2), _stream()), "cbrs_adam_step")
+                               _ptr(v, torch.float32), w.numel(), float(lr_t), _ptr(lr_t_dev, torch.float32), float(beta1),
+                               float(beta2), float(eps), float(l2), _stream()), "cbrs_adam_step")
     _count(1)
+
+
+def adam_step_multi(ws, gs, ms, vs, l2s, lr_t, beta1, beta2, eps, lr_t_dev=None):
+    """cbrs_adam_step for every weight tensor of a model in one launch"""
+    lib = L.load()
+    k = len(ws)
+    for w, g in zip(ws, gs):
+        if not (w.is_contiguous() and g.is_contiguous()) or w.dtype != torch.float32 or g.dtype != torch.float32:
+            raise L.CbrsError("adam_step_multi: weights and gradients must be contiguous float32")
+    arr = lambda ts: (ctypes.c_void_p * k)(*[t.data_ptr() for t in ts])
+    L.check(lib.cbrs_adam_step_multi(k, arr(ws), arr(gs), arr(ms), arr(vs), (ctypes.c_int64 * k)(*[w.numel() for w in ws]),
+                                     (ctypes.c_float * k)(*[float(c) for c in l2s]), float(lr_t),
+                                     _ptr(lr_t_dev, torch.float32), float(beta1), float(beta2), float(eps), _stream()),
+            "cbrs_adam_step_multi")
+    _count((k + 47) // 48)

@@ -306,6 +306,7 @@ class Adam:
                                                                       float(beta_2), float(epsilon))
         self.iterations = 0
         self._state = {}
+        self.lr_t_dev = None  # set by GraphedTrainStep: the captured Adam kernels read the rate from here
 
     @classmethod
     def from_config(cls, cfg):
@@ -322,16 +323,23 @@ class Adam:
         get = lambda k, d: float(getattr(cfg, k, d))  # a keras-like optimizer object
         return cls(get("learning_rate", 1e-3), get("beta_1", 0.9), get("beta_2", 0.999), get("epsilon", 1e-7))
 
-    def apply(self, weights, grads, l2s):
-        self.iterations += 1
-        t = self.iterations
-        lr_t = self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
-        for w, g, l2 in zip(weights, grads, l2s):
+    def rate(self, t):
+        return self.learning_rate * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+
+    def apply(self, weights, grads, l2s, capturing=False):
+        if not capturing:
+            self.iterations += 1
+        lr_t = self.rate(max(self.iterations, 1))
+        ms, vs = [], []
+        for w in weights:
             st = self._state.get(id(w))
             if st is None:
                 st = self._state[id(w)] = (torch.zeros_like(w), torch.zeros_like(w))
-            ops.adam_step(w, g if g.is_contiguous() else g.contiguous(), st[0], st[1], lr_t, self.beta_1, self.beta_2,
-                          self.epsilon, l2)
+            ms.append(st[0])
+            vs.append(st[1])
+        grads = [g if g.is_contiguous() else g.contiguous() for g in grads]
+        ops.adam_step_multi(weights, grads, ms, vs, l2s, lr_t, self.beta_1, self.beta_2, self.epsilon,
+                            lr_t_dev=self.lr_t_dev if capturing else None)
 
 
 # ------------------------------------------------------------------ one step
@@ -384,7 +392,7 @@ def l2_coefficients(model):
     return out
 
 
-def train_step(model, optimizer, inputs, y):
+def train_step(model, optimizer, inputs, y, capturing=False):
     """One optimiser step on one batch.  Returns device scalars (loss incl. the l2 penalty, #correct)."""
     tape, loss, correct, _ = forward_backward(model, inputs, y)
     l2 = l2_coefficients(model)
@@ -393,7 +401,71 @@ def train_step(model, optimizer, inputs, y):
         c = l2.get(id(w), 0.0)
         if c:
             ops.sum_squares(w, c, loss, accumulate=True)
-    optimizer.apply(ws, [tape.wgrads[id(w)] for w in ws], [l2.get(id(w), 0.0) for w in ws])
+    optimizer.apply(ws, [tape.wgrads[id(w)] for w in ws], [l2.get(id(w), 0.0) for w in ws], capturing=capturing)
     if hasattr(model, "invalidate"):
         model.invalidate()
     return loss, correct
+
+
+class GraphedTrainStep:
+    """The whole optimiser step (forward, backward, loss, Adam: ~100 kernels) captured once into a CUDA
+    graph over static batch buffers and replayed per batch.  At MovieLens-1M shape the step is bound by
+    launch latency and host dispatch, not by the kernels; replay leaves three small H2D copies, one
+    fill of the step's Adam rate and one graph launch on the host side.  Results are the eager step's:
+    same kernels, same order."""
+
+    def __init__(self, model, optimizer, batch_size, content_dim=None):
+        import numpy as np
+        self.model, self.optimizer, self.batch_size = model, optimizer, int(batch_size)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.u = torch.zeros(self.batch_size, dtype=torch.int64, device=dev)
+        self.i = torch.zeros(self.batch_size, dtype=torch.int64, device=dev)
+        self.y = torch.zeros(self.batch_size, dtype=torch.float32, device=dev)
+        self.inputs = (self.u, self.i)
+        if content_dim:
+            self.ub = torch.zeros(self.batch_size, content_dim, dtype=torch.float32, device=dev)
+            self.ib = torch.zeros(self.batch_size, content_dim, dtype=torch.float32, device=dev)
+            self.inputs = (self.u, self.i, self.ub, self.ib)
+        optimizer.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        # warm-up off the capture (sizes workspaces, creates the Adam slots), then put everything back
+        if content_dim:
+            model.build_weights(content_dim)
+        else:
+            model.build_weights()
+        saved_w = [w.clone() for w in model.weights]
+        saved_it = optimizer.iterations
+        saved_s = {k: (m.clone(), v.clone()) for k, (m, v) in optimizer._state.items()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                train_step(model, optimizer, self.inputs, self.y)
+            for w, s0 in zip(model.weights, saved_w):
+                w.copy_(s0)
+            for k, (m, v) in optimizer._state.items():
+                if k in saved_s:
+                    m.copy_(saved_s[k][0])
+                    v.copy_(saved_s[k][1])
+                else:
+                    m.zero_()
+                    v.zero_()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        optimizer.iterations = saved_it
+        self._np = np
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.correct = train_step(model, optimizer, self.inputs, self.y, capturing=True)
+
+    def __call__(self, inputs, y):
+        np = self._np
+        n = len(y)
+        if n != self.batch_size:
+            raise ValueError("captured for batches of {}, got {}".format(self.batch_size, n))
+        for dst, src in zip(self.inputs + (self.y,), tuple(inputs) + (y,)):
+            t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src))
+            dst.copy_(t.to(dst.dtype), non_blocking=True)
+        self.optimizer.iterations += 1
+        self.optimizer.lr_t_dev.fill_(self.optimizer.rate(self.optimizer.iterations))
+        self.graph.replay()
+        return self.loss.clone(), self.correct.clone()

@@ -289,9 +289,16 @@ int cbrs_bce(const float *p, const float *y, int64_t n, float *loss_out, float *
              void *stream);
 /* *out = (accumulate ? *out : 0) + scale * sum w^2 */
 int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int accumulate, void *stream);
-/* Keras Adam: g' = g + 2*l2*w; m,v updated in place; w -= lr_t * m / (sqrt(v) + eps), lr_t precomputed on the host */
-int cbrs_adam_step(float *w, const float *g, float *m, float *v, int64_t n, float lr_t, float beta1,
-                   float beta2, float eps, float l2, void *stream);
+/* Keras Adam: g' = g + 2*l2*w; m,v updated in place; w -= lr_t * m / (sqrt(v) + eps).  lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
+ * is computed by the host; lr_t_dev (device float, may be NULL) overrides the immediate so that a captured
+ * CUDA graph of the whole step can be replayed with the rate of step t                                        */
+int cbrs_adam_step(float *w, const float *g, float *m, float *v, int64_t n, float lr_t, const float *lr_t_dev,
+                   float beta1, float beta2, float eps, float l2, void *stream);
+
+/* the same update for all n_tensors weight tensors of a model in one launch (host arrays of device pointers) */
+int cbrs_adam_step_multi(int32_t n_tensors, void *const *w_host, const void *const *g_host, void *const *m_host,
+                         void *const *v_host, const int64_t *n_host, const float *l2_host, float lr_t,
+                         const float *lr_t_dev, float beta1, float beta2, float eps, void *stream);
 
 /* ---- primitives exported for tests -------------------------------------------- */
 size_t cbrs_sort_workspace_bytes(int64_t n);

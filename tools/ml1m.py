@@ -10,7 +10,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deep_cbrs_amar_renaissance_b200.graphed import GraphedForward  # noqa: E402
 from deep_cbrs_amar_renaissance_b200.keras_like import set_seed  # noqa: E402
 from deep_cbrs_amar_renaissance_b200.models import basic, hybrid  # noqa: E402
@@ -28,6 +28,28 @@ def timeit(fn, n=50, warm=5):
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
+
+
+def cpu_train_step_ms(name, model, adj, inputs, y):
+    """the oracle's autograd twin (float32, all host threads): forward + backward of one batch"""
+    from oracle import graph as og
+    from oracle import train as ot
+    from tests.helpers import export_weights
+    kind = {"BasicGCN": "gcn", "BasicGraphSage": "sage", "BasicLightGCN": "lightgcn"}[name]
+    w = export_weights(model)
+    if kind == "sage":
+        ptr, idx, _ = og.reorder_raw(adj)
+        graph = (ptr, idx)
+    else:
+        graph = og.gcn_filter(adj)
+    fn = "mean" if kind == "lightgcn" else "concatenation"
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        loss, _, _, leaves = ot.forward_loss(kind, w, graph, inputs, y, final_node=fn, l2=1e-4, dtype=torch.float32)
+        loss.backward()
+        ts.append(time.perf_counter() - t0)
+    return min(ts) * 1e3
 
 
 def main():
@@ -60,7 +82,28 @@ def main():
         model.cache_propagation = True
         model.propagate()
         cat = timeit(lambda: model.recommend_top_k(n_users, n_items, 10), n=5, warm=1) if not is_h else None
+        model.cache_propagation = False
+        model.invalidate()
+        # one optimiser step (forward with saved activations, explicit backward, BCE + l2, Adam), batch 1024 as in
+        # config.yaml:46; next to the same step on the host cores (torch-CPU autograd twin, fp32, all threads)
+        train_ms = cpu_train_ms = train_graph_ms = None
+        if "GAT" not in name or os.environ.get("CBRS_TRAIN_GAT"):
+            yb = rng.randint(0, 2, size=1024)
+            ub, ib = u[:1024], i[:1024]
+            model.compile(loss="binary_crossentropy", optimizer={"learning_rate": 1e-3})
+            train_graph_ms = None
+            try:
+                train_ms = timeit(lambda: model.train_on_batch((ub, ib), yb), n=20, warm=3)
+                if True:
+                    gstep = model.make_graphed_train_step(1024)
+                    train_graph_ms = timeit(lambda: gstep((ub, ib), yb), n=50, warm=3)
+            except NotImplementedError:
+                train_ms = None
+            if train_ms is not None and not is_h and "uip" not in name:
+                cpu_train_ms = cpu_train_step_ms(name, model, a, (ub, ib), yb)
         print(json.dumps({"model": name, "nnz": nnz, "layers": 2, "batch": batch, "eager_ms": eager, "graph_ms": graphed,
+                          "train_step_ms_batch1024": train_ms, "train_step_graph_ms_batch1024": train_graph_ms, "cpu_train_step_ms_batch1024": cpu_train_ms,
+                          "cpu_threads": torch.get_num_threads(),
                           "edges_per_s_graph": 2 * nnz / (graphed * 1e-3),
                           "catalog_top10_ms": cat, "catalog_pairs_per_s": (n_users * n_items / (cat * 1e-3)) if cat else None}),
               flush=True)
