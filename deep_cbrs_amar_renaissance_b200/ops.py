@@ -494,3 +494,22 @@ def adam_step_multi(ws, gs, ms, vs, l2s, lr_t, beta1, beta2, eps, lr_t_dev=None)
                                      _ptr(lr_t_dev, torch.float32), float(beta1), float(beta2), float(eps), _stream()),
             "cbrs_adam_step_multi")
     _count((k + 47) // 48)
+
+
+def gat_backward(csr, z, p, q, y, bias, d_o, a_self, a_neigh):
+    """(dz [N,h] incl. the dp/dq rank-1 terms, dp [N], dq [N]) of the fused GAT layer"""
+    lib = L.load()
+    z, ldz = _rowmajor(z)
+    y, ldy = _rowmajor(y)
+    d_o, ldo = _rowmajor(d_o)
+    n, h = z.shape
+    dz = torch.empty(n, h, dtype=torch.float32, device=z.device)
+    dp = torch.empty(n, dtype=torch.float32, device=z.device)
+    dq = torch.empty(n, dtype=torch.float32, device=z.device)
+    ws = _ws(lib.cbrs_gat_backward_workspace_bytes(n), z.device)
+    L.check(lib.cbrs_gat_backward(ctypes.byref(csr.desc), _ptr(z), ldz, _ptr(p, torch.float32), _ptr(q, torch.float32),
+                                  _ptr(y), ldy, _ptr(bias, torch.float32), _ptr(d_o), ldo, h,
+                                  _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32), _ptr(dz), h, _ptr(dp),
+                                  _ptr(dq), _ptr(ws), ws.numel(), _stream()), "cbrs_gat_backward")
+    _count(3)
+    return dz, dp, dq

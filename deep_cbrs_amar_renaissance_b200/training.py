@@ -203,6 +203,37 @@ def _sage_train(tape, layer, x_node, graph, out):
     return node
 
 
+def _gat_train(tape, layer, x_node, graph, out):
+    """GATConv: z = x W, p = z.a_self, q = z.a_neigh, fused edge softmax + aggregate (csrc/gat.cu);
+    backward = csrc/gat_bwd.cu, then the dense pieces."""
+    x = x_node.x
+    csr = graph.raw
+    f = x.shape[1]
+    w2 = layer.kernel.reshape(f, layer.channels)
+    a_s, a_n = layer.attn_kernel_self.reshape(-1), layer.attn_kernel_neighs.reshape(-1)
+    z, p, q = ops.dense(x, w2, rowop=L.ROWOP_ATTN, a_self=a_s, a_neigh=a_n)
+    y = ops.gat(csr, z, p, q, out, bias=layer.bias, relu=layer.activation == "relu")
+    node = Node(y)
+
+    def bwd():
+        if node.grad is None:
+            return
+        d_o = ops.act_grad(node.grad, y, layer.activation)
+        if layer.bias is not None:
+            tape.wgrad(layer.bias, ops.colsum(d_o))
+        dz, dp, dq = ops.gat_backward(csr, z, p, q, y, layer.bias, d_o, a_s, a_n)
+        da_s, _ = ops.dense_grad_w(z, dp.reshape(-1, 1), want_bias=False)
+        da_n, _ = ops.dense_grad_w(z, dq.reshape(-1, 1), want_bias=False)
+        tape.wgrad(layer.attn_kernel_self, da_s)
+        tape.wgrad(layer.attn_kernel_neighs, da_n)
+        dw, _ = ops.dense_grad_w(x, dz, want_bias=False)
+        tape.wgrad(layer.kernel, dw)
+        x_node.add_grad(ops.dense(dz, ops.transpose(w2)))
+
+    tape.ops.append(bwd)
+    return node
+
+
 def gnn_train(tape, seq):
     """SequentialGNN.call (/root/reference/src/models/gnn.py:74-84) on the tape -> Node of [N, D_out]."""
     emb = seq.embeddings
@@ -234,8 +265,7 @@ def gnn_train(tape, seq):
         elif isinstance(layer, GraphSageConv):
             x_node = _sage_train(tape, layer, x_node, graph, out)
         elif isinstance(layer, GATConv):
-            raise NotImplementedError("GATConv backward (edge-softmax gradient) is not built yet; GCN, GraphSage "
-                                      "and LightGCN train")
+            x_node = _gat_train(tape, layer, x_node, graph, out)
         else:
             raise NotImplementedError("no training form for {}".format(type(layer).__name__))
         nodes.append(x_node)

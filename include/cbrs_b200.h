@@ -295,6 +295,16 @@ int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int acc
 int cbrs_adam_step(float *w, const float *g, float *m, float *v, int64_t n, float lr_t, const float *lr_t_dev,
                    float beta1, float beta2, float eps, float l2, void *stream);
 
+/* Backward of cbrs_gat_csr (fused edge-softmax gradient).  d_o = dY * act'(y).  Outputs: dz [N,h] =
+ * sum_i alpha_ij dO_i + dp (x) a_self + dq (x) a_neigh (the full gradient w.r.t. z = X W), dp, dq [N] (for
+ * d a_self = z^T dp, d a_neigh = z^T dq).  The graph must be structurally symmetric (every adjacency of the
+ * reference is, config.yaml:36): the edges ending in a node are read from that node's own row.  Full graph
+ * only (g->n_rows == N); rows are not chunked (training runs at MovieLens scale).                        */
+size_t cbrs_gat_backward_workspace_bytes(int64_t n_rows);
+int cbrs_gat_backward(const cbrs_csr_t *g, const float *z, int64_t ldz, const float *p, const float *q,
+                      const float *y, int64_t ldy, const float *bias, const float *d_o, int64_t ldo, int32_t h,
+                      const float *a_self, const float *a_neigh, float *dz, int64_t lddz, float *dp, float *dq,
+                      void *workspace, size_t workspace_bytes, void *stream);
 /* the same update for all n_tensors weight tensors of a model in one launch (host arrays of device pointers) */
 int cbrs_adam_step_multi(int32_t n_tensors, void *const *w_host, const void *const *g_host, void *const *m_host,
                          void *const *v_host, const int64_t *n_host, const float *l2_host, float lr_t,

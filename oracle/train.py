@@ -42,6 +42,11 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
     n = emb.shape[0]
     if kind in ("gcn", "lightgcn"):
         a = _csr_torch(graph.indptr, graph.indices, graph.data, n, dtype)
+    elif kind == "gat":
+        from .graph import gat_edges
+        gptr, gcols = gat_edges(np.asarray(graph[0]), np.asarray(graph[1]))
+        g_rows = torch.tensor(np.repeat(np.arange(n), np.diff(gptr)), dtype=torch.int64)
+        g_cols = torch.tensor(np.asarray(gcols), dtype=torch.int64)
     else:
         a = _csr_torch(graph[0], graph[1], np.ones(len(graph[1]), np.float32), n, dtype)
         deg = torch.tensor(np.diff(graph[0]).astype(np.float64), dtype=dtype).clamp(min=1.0).reshape(-1, 1)
@@ -64,6 +69,22 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
             o = torch.cat([x, agg], dim=1) @ k + b
             o = o / torch.sqrt(torch.clamp((o * o).sum(dim=1, keepdim=True), min=1e-12))
             x = torch.relu(o)
+        elif kind == "gat":
+            # spektral GATConv, single head, dropout 0; autograd also differentiates the max shift
+            k = leaves["layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
+            a_s = leaves["layers.%d.attn_kernel_self" % li] = _t(lw["attn_self"], dtype)
+            a_n = leaves["layers.%d.attn_kernel_neigh" % li] = _t(lw["attn_neigh"], dtype)
+            b = leaves["layers.%d.bias" % li] = _t(lw["bias"], dtype)
+            reg += [k, b]  # attention kernels carry no regulariser in the reference (gnn.py:321-328)
+            z = x @ k
+            p_, q_ = z @ a_s, z @ a_n
+            e = torch.nn.functional.leaky_relu(p_[g_rows] + q_[g_cols], 0.2)
+            mx = torch.full((n,), -float("inf"), dtype=dtype).scatter_reduce(0, g_rows, e, reduce="amax")
+            wgt = torch.exp(e - mx[g_rows])
+            ssum = torch.zeros(n, dtype=dtype).index_add(0, g_rows, wgt)
+            alpha = wgt / (ssum[g_rows] + 1e-9)
+            o = torch.zeros(n, z.shape[1], dtype=dtype).index_add(0, g_rows, alpha[:, None] * z[g_cols])
+            x = torch.relu(o + b)
         else:
             raise ValueError(kind)
         hs.append(x)
