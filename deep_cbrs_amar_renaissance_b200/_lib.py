@@ -68,6 +68,9 @@ _SIGS = {
                                    POINTER(c_void_p), c_int, P, c_size_t, P]),
     "cbrs_dense_bcast": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int, c_int,
                                  P, P, P, P, P, c_int64, POINTER(c_void_p), POINTER(c_void_p), c_int, P]),
+    "cbrs_compact_ids_workspace_bytes": (c_size_t, [c_int64]),
+    "cbrs_compact_ids": (c_int, [P, c_int64, P, P, P, P, c_size_t, P]),
+    "cbrs_lookup_ids": (c_int, [P, c_int64, P, c_int64, P, P]),
     "cbrs_act_grad": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int, P, c_int64, P]),
     "cbrs_dense_grad_w_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "cbrs_dense_grad_w": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, c_int64, c_int64, c_int32, P, P,

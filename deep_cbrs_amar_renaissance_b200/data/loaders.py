@@ -15,13 +15,45 @@ def _read(path, sep):
     return pd.read_csv(path, sep=sep, header=None).to_numpy()
 
 
-def _lookup(vocab, raw, what):
+DEVICE_IDS_MIN_ROWS = 1 << 16  # below this the host numpy path is faster than two H2D/D2H copies
+
+
+def _on_device(n, device_ids):
+    if device_ids is None:
+        import torch
+        return torch.cuda.is_available() and n >= DEVICE_IDS_MIN_ROWS
+    return bool(device_ids)
+
+
+def _unique_inverse(raw, device_ids=None):
+    """np.unique(raw, return_inverse=True) (loaders.py:47-49); on device for large integer columns
+    (cbrs_compact_ids: radix sort + scan, bit-identical result)."""
+    raw = np.asarray(raw)
+    if _on_device(len(raw), device_ids) and np.issubdtype(raw.dtype, np.integer):
+        import torch
+        from .. import ops
+        ids = torch.from_numpy(np.ascontiguousarray(raw, dtype=np.int64)).cuda()
+        uniq, inv = ops.compact_ids(ids)
+        return uniq.cpu().numpy().astype(raw.dtype), inv.cpu().numpy()
+    return np.unique(raw, return_inverse=True)
+
+
+def _lookup(vocab, raw, what, device_ids=None):
     """Index of each raw id in a sorted-unique vocabulary.
 
     The reference compares an [n,1] column against the whole vocabulary
     (loaders.py:53-54,64: an n x U boolean, 1.1 GB at MovieLens-1M) and keeps the
     matching column index; a binary search returns the same index in O(n log U).
     """
+    raw = np.asarray(raw)
+    if _on_device(len(raw), device_ids) and np.issubdtype(raw.dtype, np.integer) and np.issubdtype(np.asarray(vocab).dtype, np.integer):
+        import torch
+        from .. import ops
+        pos = ops.lookup_ids(torch.from_numpy(np.ascontiguousarray(vocab, dtype=np.int64)).cuda(),
+                             torch.from_numpy(np.ascontiguousarray(raw, dtype=np.int64)).cuda()).cpu().numpy()
+        if (pos < 0).any():
+            raise KeyError("{} ids absent from the training vocabulary: {}".format(what, np.unique(raw[pos < 0])[:5]))
+        return pos
     pos = np.searchsorted(vocab, raw)
     ok = pos < len(vocab)
     ok[ok] = vocab[pos[ok]] == raw[ok]
@@ -32,24 +64,26 @@ def _lookup(vocab, raw, what):
 
 def load_train_test_ratings(train_filepath, test_filepath, props_filepath=None, sep='\t',
                             return_adjacency=False, type_adjacency='unary', sparse_adjacency=True,
-                            symmetric_adjacency=True):
-    """Ratings with sequential ids (items offset by the user count) [+ adjacency]."""
+                            symmetric_adjacency=True, device_ids=None):
+    """Ratings with sequential ids (items offset by the user count) [+ adjacency].
+    device_ids: None = compaction on the GPU for columns of >= 65,536 rows when one is present,
+    True / False to force; the result is the same array either way."""
     raw_train, raw_test = _read(train_filepath, sep), _read(test_filepath, sep)
-    users, u_of = np.unique(raw_train[:, 0], return_inverse=True)
-    items, i_of = np.unique(raw_train[:, 1], return_inverse=True)
+    users, u_of = _unique_inverse(raw_train[:, 0], device_ids)
+    items, i_of = _unique_inverse(raw_train[:, 1], device_ids)
     n_users = len(users)
     train = np.stack([u_of, i_of + n_users, raw_train[:, 2]], axis=1)
-    test = np.stack([_lookup(users, raw_test[:, 0], 'test user'),
-                     _lookup(items, raw_test[:, 1], 'test item') + n_users, raw_test[:, 2]], axis=1)
+    test = np.stack([_lookup(users, raw_test[:, 0], 'test user', device_ids),
+                     _lookup(items, raw_test[:, 1], 'test item', device_ids) + n_users, raw_test[:, 2]], axis=1)
     if not return_adjacency:
         return (train, test), (users, items)
 
     props = triples = None
     if type_adjacency in ('unary-kg', 'unary-uip') and props_filepath is not None:
         raw = _read(props_filepath, sep)
-        props, p_of = np.unique(raw[:, 1], return_inverse=True)
+        props, p_of = _unique_inverse(raw[:, 1], device_ids)
         # the relation column is dropped, every link weighs one (loaders.py:67-68)
-        triples = np.stack([_lookup(items, raw[:, 0], 'property item'), p_of + len(items),
+        triples = np.stack([_lookup(items, raw[:, 0], 'property item', device_ids), p_of + len(items),
                             np.ones(len(raw), dtype=raw.dtype)], axis=1)
     adj = build_adjacency_matrix(train, users, items, props_triples=triples, props=props,
                                  type_adjacency=type_adjacency, sparse_adjacency=sparse_adjacency,

@@ -513,3 +513,26 @@ def gat_backward(csr, z, p, q, y, bias, d_o, a_self, a_neigh):
                                   _ptr(dq), _ptr(ws), ws.numel(), _stream()), "cbrs_gat_backward")
     _count(3)
     return dz, dp, dq
+
+
+# ------------------------------------------------------------------ id compaction (rows G0 / (f)-2)
+def compact_ids(ids):
+    """np.unique(ids, return_inverse=True) on device: (sorted uniques int64 [k], inverse int64 [n])"""
+    lib = L.load()
+    n = ids.numel()
+    uniques = torch.empty(n, dtype=torch.int64, device=ids.device)
+    inverse = torch.empty(n, dtype=torch.int64, device=ids.device)
+    count = torch.zeros(1, dtype=torch.int64, device=ids.device)
+    ws = _ws(lib.cbrs_compact_ids_workspace_bytes(n), ids.device)
+    L.check(lib.cbrs_compact_ids(_ptr(ids, torch.int64), n, _ptr(uniques), _ptr(inverse), _ptr(count), _ptr(ws),
+                                 ws.numel(), _stream()), "cbrs_compact_ids")
+    return uniques[:int(count.item())], inverse
+
+
+def lookup_ids(vocab_sorted, ids):
+    """index of each id in the sorted vocabulary (int64), -1 where absent"""
+    lib = L.load()
+    out = torch.empty(ids.numel(), dtype=torch.int64, device=ids.device)
+    L.check(lib.cbrs_lookup_ids(_ptr(vocab_sorted, torch.int64), vocab_sorted.numel(), _ptr(ids, torch.int64),
+                                ids.numel(), _ptr(out), _stream()), "cbrs_lookup_ids")
+    return out

@@ -250,6 +250,18 @@ int cbrs_dense_bcast(const float *x1, int64_t ld1, const int64_t *idx1, int32_t 
                      float *q_out, float *out, int64_t ldo, void *const *out_peers_host,
                      void *const *q_peers_host, int n_peers, void *stream);
 
+/* ---- id compaction (rows G0 / (f)-2) ------------------------------------------------------------
+ * cbrs_compact_ids == np.unique(ids, return_inverse=True) (src/data/loaders.py:47-49,65): uniques_out
+ * (capacity n) receives the sorted distinct values, inverse_out[i] the index of ids[i] among them,
+ * *n_unique_out (device) their count.  cbrs_lookup_ids replaces the `col[:,None] == vocab` broadcast +
+ * argwhere of loaders.py:53-54,64 with a binary search; ids absent from the vocabulary give -1 (the
+ * reference silently drops such rows; the host wrapper raises).  Bit-exact integer work.             */
+size_t cbrs_compact_ids_workspace_bytes(int64_t n);
+int cbrs_compact_ids(const int64_t *ids, int64_t n, int64_t *uniques_out, int64_t *inverse_out,
+                     int64_t *n_unique_out, void *workspace, size_t workspace_bytes, void *stream);
+int cbrs_lookup_ids(const int64_t *vocab_sorted, int64_t n_vocab, const int64_t *ids, int64_t n,
+                    int64_t *index_out, void *stream);
+
 /* ---- training step (scope row (f)-1) ------------------------------------------------------
  * The reference differentiates with TensorFlow autograd inside Keras `fit`
  * (src/experiment.py:155-188): loss = binary cross-entropy (config.yaml:50) + l2 * sum w^2 over

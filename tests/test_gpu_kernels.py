@@ -431,3 +431,43 @@ def test_synthetic_generator_is_the_documented_hash(dev):
     assert np.array_equal(row.cpu().numpy()[:n_edges], u.astype(np.int32))
     assert np.array_equal(col.cpu().numpy()[:n_edges], (n_users + it).astype(np.int32))
     assert torch.equal(row[n_edges:], col[:n_edges]) and torch.equal(col[n_edges:], row[:n_edges])
+
+
+# ------------------------------------------------------------------ id compaction (rows G0 / (f)-2)
+@pytest.mark.parametrize("n,span", [(1, 5), (1000, 50), (200_000, 6040), (300_000, 2 ** 40)])
+def test_compact_ids_equals_numpy_unique(n, span):
+    from deep_cbrs_amar_renaissance_b200 import ops
+    rng = np.random.RandomState(n % 97)
+    raw = rng.randint(-span, span, size=n).astype(np.int64) * 3 + 7  # negative and non-contiguous ids
+    uniq, inv = ops.compact_ids(torch.from_numpy(raw).cuda())
+    want_u, want_inv = np.unique(raw, return_inverse=True)
+    assert np.array_equal(uniq.cpu().numpy(), want_u)
+    assert np.array_equal(inv.cpu().numpy(), want_inv)
+
+
+def test_lookup_ids_equals_broadcast_argwhere():
+    from deep_cbrs_amar_renaissance_b200 import ops
+    rng = np.random.RandomState(3)
+    vocab = np.unique(rng.randint(0, 10 ** 6, size=5000).astype(np.int64))
+    ids = np.concatenate([vocab[rng.randint(0, len(vocab), size=3000)], np.array([-5, 10 ** 7], np.int64)])
+    got = ops.lookup_ids(torch.from_numpy(vocab).cuda(), torch.from_numpy(ids).cuda()).cpu().numpy()
+    want = np.argwhere(ids[:3000, None] == vocab)[:, 1]  # the reference's formulation (loaders.py:53-54)
+    assert np.array_equal(got[:3000], want)
+    assert (got[3000:] == -1).all()
+
+
+def test_loader_device_ids_give_the_same_arrays(tmp_path):
+    from deep_cbrs_amar_renaissance_b200.data import loaders
+    rng = np.random.RandomState(5)
+    n = 5000
+    tr = np.stack([rng.randint(0, 300, n) * 11 + 1000, rng.randint(0, 200, n) * 7 + 50000, rng.randint(0, 2, n)], 1)
+    te = tr[rng.randint(0, n, 800)]
+    pr = np.stack([tr[rng.randint(0, n, 600), 1], rng.randint(0, 90, 600) + 90000, rng.randint(0, 5, 600)], 1)
+    for name, arr in (("train", tr), ("test", te), ("props", pr)):
+        np.savetxt(tmp_path / (name + ".tsv"), arr, fmt="%d", delimiter="\t")
+    args = (str(tmp_path / "train.tsv"), str(tmp_path / "test.tsv"), str(tmp_path / "props.tsv"))
+    host = loaders.load_train_test_ratings(*args, return_adjacency=True, type_adjacency='unary-uip', device_ids=False)
+    dev = loaders.load_train_test_ratings(*args, return_adjacency=True, type_adjacency='unary-uip', device_ids=True)
+    for a, b in zip(host[0] + host[1], dev[0] + dev[1]):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    assert (host[2] != dev[2]).nnz == 0 and np.array_equal(host[2].row, dev[2].row)
