@@ -71,6 +71,14 @@ _SIGS = {
     "cbrs_compact_ids_workspace_bytes": (c_size_t, [c_int64]),
     "cbrs_compact_ids": (c_int, [P, c_int64, P, P, P, P, c_size_t, P]),
     "cbrs_lookup_ids": (c_int, [P, c_int64, P, c_int64, P, P]),
+    "cbrs_spgemm_workspace_bytes": (c_size_t, [c_int64]),
+    "cbrs_spgemm_count": (c_int, [POINTER(CsrDesc), POINTER(CsrDesc), P, P, P, c_size_t, P]),
+    "cbrs_spgemm_expand": (c_int, [POINTER(CsrDesc), POINTER(CsrDesc), P, P, P, P, P]),
+    "cbrs_count_above": (c_int, [P, c_int64, POINTER(c_float), c_int32, P, P]),
+    "cbrs_csr_filter_above_workspace_bytes": (c_size_t, [c_int64]),
+    "cbrs_csr_filter_above": (c_int, [POINTER(CsrDesc), c_float, P, P, P, P, c_size_t, P]),
+    "cbrs_row_gate": (c_int, [P, c_int64, P, c_int64, c_int32, P, c_int64, P]),
+    "cbrs_row_gate_grad": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int32, P, c_int64, P, P]),
     "cbrs_act_grad": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int, P, c_int64, P]),
     "cbrs_dense_grad_w_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "cbrs_dense_grad_w": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, c_int64, c_int64, c_int32, P, P,

@@ -96,3 +96,37 @@ class DeviceGraph:
     @property
     def raw(self):
         return self._view("raw", 0, False)
+
+    @property
+    def plain(self):
+        """duplicates summed, values kept, nothing else: scipy's A.tocsr()"""
+        return self._view("plain", L.GRAPH_DEDUP_SUM, True)
+
+    DGCF_EPSILONS = (1e-1, 1e-2, 1e-3, 5e-4)  # dgcf_conv.py:60
+
+    @property
+    def dgcf(self):
+        """DGCFConv.preprocess on device (/root/reference/src/layers/dgcf_conv.py:38-80):
+        gcn_filter(A) + high_pass(gcn_filter(A.A)) + I as one CSR."""
+        if "dgcf" not in self._views:
+            n = self.n_nodes
+            a = self.plain
+            r, c, v = ops.spgemm_products(a, a)                                   # crosshop = a.dot(a)
+            flags = L.GRAPH_DEDUP_SUM | L.GRAPH_ADD_SELF_LOOPS | L.GRAPH_SYM_NORM
+            cross = CsrSlice(*[t.contiguous() for t in ops.graph_build_csr(r, c, v, n, flags)], n, self.chunk_edges)
+            del r, c, v
+            a_hat = self.norm                                                      # gcn_filter(a)
+            counts = ops.count_above(cross.vals, self.DGCF_EPSILONS)
+            edges = a_hat.nnz
+            ratios = [float("inf") if k == 0 else (edges / k if edges > k else k / edges) for k in counts]
+            best = min(range(len(ratios)), key=lambda j: (ratios[j], j))           # argmin, first on ties
+            self.dgcf_info = dict(edges=edges, cross_edges=counts, ratios=ratios, epsilon=self.DGCF_EPSILONS[best])
+            fr, fc, fv = ops.csr_filter_above(cross, self.DGCF_EPSILONS[best], counts[best])
+            ar, ac, av = ops.csr_filter_above(a_hat, float("-inf"), a_hat.nnz)     # A_hat as COO
+            eye = torch.arange(n, dtype=torch.int32, device=fr.device)
+            row = torch.cat([ar, fr, eye])
+            col = torch.cat([ac, fc, eye])
+            val = torch.cat([av, fv, torch.ones(n, dtype=torch.float32, device=fr.device)])
+            rowptr, colidx, vals = ops.graph_build_csr(row, col, val, n, L.GRAPH_DEDUP_SUM)  # (a + crosshop) + I
+            self._views["dgcf"] = CsrSlice(rowptr, colidx.contiguous(), vals.contiguous(), n, self.chunk_edges)
+        return self._views["dgcf"]

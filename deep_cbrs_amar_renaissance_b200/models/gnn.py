@@ -12,7 +12,7 @@ import torch
 
 from ..graph import DeviceGraph
 from ..keras_like import L2, Model, default_device
-from ..layers import GATConv, GCNConv, GraphSageConv, LightGCNConv, ReductionLayer, RGCNConv
+from ..layers import DGCFConv, GATConv, GCNConv, GraphSageConv, LightGCNConv, ReductionLayer, RGCNConv
 from ..utilities.math import convert_to_tensor
 
 
@@ -151,12 +151,15 @@ class LightGCN(GNN):
 
 
 class DGCF(GNN):
-    def __init__(self, adj_matrix, n_layers=3, **kwargs):
-        raise NotImplementedError("DGCF needs an SpGEMM A.A + threshold search at build time: scope row (f)-3, "
-                                  "not named in the north star (DESIGN.md)")
+    """gnn.py:391-415: final_node forced to 'mean', adjacency replaced by the crosshop operator."""
 
-    def build_gnn_layer(self, i, **kwargs):
-        raise NotImplementedError
+    def __init__(self, adj_matrix, n_layers=3, **kwargs):
+        kwargs['final_node'] = 'mean'
+        adj_matrix = DGCFConv.preprocess(adj_matrix)
+        super().__init__(adj_matrix, n_layers, **kwargs)
+
+    def build_gnn_layer(self, i, regularizer=None, **kwargs):
+        return DGCFConv(regularizer)
 
 
 class RGCN(GNN):

@@ -536,3 +536,74 @@ def lookup_ids(vocab_sorted, ids):
     L.check(lib.cbrs_lookup_ids(_ptr(vocab_sorted, torch.int64), vocab_sorted.numel(), _ptr(ids, torch.int64),
                                 ids.numel(), _ptr(out), _stream()), "cbrs_lookup_ids")
     return out
+
+
+# ------------------------------------------------------------------ DGCF operator build (scope row (f)-3)
+def spgemm_products(left, right):
+    """COO (row int32, col int32, val float32) of the elementary products of left @ right (both graph.CsrSlice);
+    duplicates are NOT summed here - cbrs_graph_build_csr does that."""
+    lib = L.load()
+    dev = left.rowptr.device
+    offsets = torch.empty(left.n_rows, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws = _ws(lib.cbrs_spgemm_workspace_bytes(left.n_rows), dev)
+    L.check(lib.cbrs_spgemm_count(ctypes.byref(left.desc), ctypes.byref(right.desc), _ptr(offsets), _ptr(total), _ptr(ws),
+                                  ws.numel(), _stream()), "cbrs_spgemm_count")
+    n = int(total.item())
+    row = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    col = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    val = torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+    L.check(lib.cbrs_spgemm_expand(ctypes.byref(left.desc), ctypes.byref(right.desc), _ptr(offsets), _ptr(row), _ptr(col),
+                                   _ptr(val), _stream()), "cbrs_spgemm_expand")
+    return row[:n], col[:n], val[:n]
+
+
+def count_above(vals, eps_list):
+    """[#(vals > eps) for eps in eps_list] (python ints)"""
+    lib = L.load()
+    k = len(eps_list)
+    counts = torch.zeros(k, dtype=torch.int64, device=vals.device)
+    L.check(lib.cbrs_count_above(_ptr(vals, torch.float32), vals.numel(), (ctypes.c_float * k)(*[float(e) for e in eps_list]),
+                                 k, _ptr(counts), _stream()), "cbrs_count_above")
+    return [int(c) for c in counts.tolist()]
+
+
+def csr_filter_above(csr, eps, count):
+    """COO of the entries of `csr` (with values) greater than eps; `count` from count_above"""
+    lib = L.load()
+    dev = csr.rowptr.device
+    row = torch.empty(max(count, 1), dtype=torch.int32, device=dev)
+    col = torch.empty(max(count, 1), dtype=torch.int32, device=dev)
+    val = torch.empty(max(count, 1), dtype=torch.float32, device=dev)
+    ws = _ws(lib.cbrs_csr_filter_above_workspace_bytes(csr.nnz), dev)
+    L.check(lib.cbrs_csr_filter_above(ctypes.byref(csr.desc), float(eps), _ptr(row), _ptr(col), _ptr(val), _ptr(ws),
+                                      ws.numel(), _stream()), "cbrs_csr_filter_above")
+    return row[:count], col[:count], val[:count]
+
+
+def row_gate(x, w, out=None):
+    """x * sigmoid(w) with w [N] or [N,1] (LocalityAdaptive, dgcf_conv.py:101-102)"""
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    rows, d = x.shape
+    if out is None:
+        out = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+    out, ldo = _rowmajor(out)
+    L.check(lib.cbrs_row_gate(_ptr(x), ldx, _ptr(w.reshape(-1), torch.float32), rows, d, _ptr(out), ldo, _stream()),
+            "cbrs_row_gate")
+    _count(1)
+    return out
+
+
+def row_gate_grad(g, x, w):
+    """(dx [N,d], dw [N]) of out = x * sigmoid(w)"""
+    lib = L.load()
+    g, ldg = _rowmajor(g)
+    x, ldx = _rowmajor(x)
+    rows, d = x.shape
+    dx = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+    dw = torch.empty(rows, dtype=torch.float32, device=x.device)
+    L.check(lib.cbrs_row_gate_grad(_ptr(g), ldg, _ptr(x), ldx, _ptr(w.reshape(-1), torch.float32), rows, d, _ptr(dx), d,
+                                   _ptr(dw), _stream()), "cbrs_row_gate_grad")
+    _count(1)
+    return dx, dw

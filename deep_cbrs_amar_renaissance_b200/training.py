@@ -18,7 +18,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .layers import GATConv, GCNConv, GraphSageConv, LightGCNConv, RGCNConv
+from .layers import DGCFConv, GATConv, GCNConv, GraphSageConv, LightGCNConv, RGCNConv
 
 
 class Node:
@@ -171,6 +171,28 @@ def _lightgcn_train(tape, layer, x_node, graph, out):
     return node
 
 
+def _dgcf_train(tape, layer, x_node, graph, out):
+    """DGCFConv: y = M (x * sigmoid(w)); M is symmetric (sum of symmetric pieces), so dGated = M dY."""
+    csr = graph.dgcf
+    x = x_node.x
+    w = layer.locality_adaptive.w
+    gated = ops.row_gate(x, w)
+    y = ops.spmm(csr, gated, out)
+    node = Node(y)
+
+    def bwd():
+        if node.grad is None:
+            return
+        dg = torch.empty(csr.n_rows, x.shape[1], dtype=torch.float32, device=x.device)
+        ops.spmm(csr, node.grad, dg)
+        dx, dw = ops.row_gate_grad(dg, x, w)
+        tape.wgrad(w, dw)
+        x_node.add_grad(dx)
+
+    tape.ops.append(bwd)
+    return node
+
+
 def _sage_train(tape, layer, x_node, graph, out):
     """GraphSageConv: agg = mean/sum over the raw edge list; v = [x || agg] W + b; out = relu(v / |v|).
     Training keeps v (the fused inference epilogue does not), so the epilogue is its own kernel."""
@@ -266,6 +288,8 @@ def gnn_train(tape, seq):
             x_node = _sage_train(tape, layer, x_node, graph, out)
         elif isinstance(layer, GATConv):
             x_node = _gat_train(tape, layer, x_node, graph, out)
+        elif isinstance(layer, DGCFConv):
+            x_node = _dgcf_train(tape, layer, x_node, graph, out)
         else:
             raise NotImplementedError("no training form for {}".format(type(layer).__name__))
         nodes.append(x_node)

@@ -262,6 +262,31 @@ int cbrs_compact_ids(const int64_t *ids, int64_t n, int64_t *uniques_out, int64_
 int cbrs_lookup_ids(const int64_t *vocab_sorted, int64_t n_vocab, const int64_t *ids, int64_t n,
                     int64_t *index_out, void *stream);
 
+/* ---- DGCF operator build and layer pieces (scope row (f)-3) -------------------------------------
+ * Replaces, on device, DGCFConv.preprocess / high_pass_filter (src/layers/dgcf_conv.py:38-80; scipy on
+ * the host in the reference) and LocalityAdaptive.call (:101-102).
+ * A.dot(A) -> cbrs_spgemm_count (row_offsets [n_rows] = exclusive scan of the products per row,
+ * *total_out device int64) + cbrs_spgemm_expand (COO of the elementary products a_ik*a_kj, row-major,
+ * k ascending) -> cbrs_graph_build_csr sums the duplicates (and applies gcn_filter).                 */
+size_t cbrs_spgemm_workspace_bytes(int64_t n_rows);
+int cbrs_spgemm_count(const cbrs_csr_t *left, const cbrs_csr_t *right, int64_t *row_offsets, int64_t *total_out,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int cbrs_spgemm_expand(const cbrs_csr_t *left, const cbrs_csr_t *right, const int64_t *row_offsets,
+                       int32_t *coo_row, int32_t *coo_col, float *coo_val, void *stream);
+/* counts[j] (device uint64) = #{i : vals[i] > eps_host[j]}, j < n_eps <= 8: the threshold search of
+ * high_pass_filter (dgcf_conv.py:60-80) */
+int cbrs_count_above(const float *vals, int64_t n, const float *eps_host, int32_t n_eps, uint64_t *counts,
+                     void *stream);
+/* COO (row-major order kept) of the CSR entries with value > eps; capacity = the count from cbrs_count_above */
+size_t cbrs_csr_filter_above_workspace_bytes(int64_t nnz);
+int cbrs_csr_filter_above(const cbrs_csr_t *g, float eps, int32_t *coo_row, int32_t *coo_col, float *coo_val,
+                          void *workspace, size_t workspace_bytes, void *stream);
+/* LocalityAdaptive: out[r,:] = x[r,:] * sigmoid(w[r]); backward: dx = g*sigmoid(w), dw[r] = sigmoid'(w[r]) * g[r,:].x[r,:] */
+int cbrs_row_gate(const float *x, int64_t ldx, const float *w, int64_t rows, int32_t d, float *out, int64_t ldo,
+                  void *stream);
+int cbrs_row_gate_grad(const float *g, int64_t ldg, const float *x, int64_t ldx, const float *w, int64_t rows,
+                       int32_t d, float *dx, int64_t lddx, float *dw, void *stream);
+
 /* ---- training step (scope row (f)-1) ------------------------------------------------------
  * The reference differentiates with TensorFlow autograd inside Keras `fit`
  * (src/experiment.py:155-188): loss = binary cross-entropy (config.yaml:50) + l2 * sum w^2 over

@@ -77,6 +77,39 @@ def lightgcn_conv(x, a_hat):
     return (a_hat @ np.asarray(x, F32)).astype(F32)
 
 
+# ------------------------------------------------------------------------- (f)-3 DGCF
+DGCF_EPSILONS = [1e-1, 1e-2, 1e-3, 5e-4]
+
+
+def dgcf_preprocess(adj_coo):
+    """layers/dgcf_conv.py:38-80 (the reference's own scipy code, restated): crosshop = a.dot(a);
+    a, crosshop = gcn_filter(a), gcn_filter(crosshop); crosshop = high_pass_filter(a, crosshop)
+    (keep entries > eps for the eps in [1e-1, 1e-2, 1e-3, 5e-4] whose surviving count is closest in ratio to
+    a's edge count, first on ties); return a + crosshop + eye.  float32 CSR, sorted indices.
+    Returns (matrix, info dict)."""
+    from .graph import gcn_filter
+    a = sparse.csr_matrix(adj_coo, dtype=F32)
+    a.sum_duplicates()
+    crosshop = a.dot(a)
+    a_hat, cross_hat = gcn_filter(adj_coo), gcn_filter(crosshop.tocoo())
+    edges = len(a_hat.data)
+    filtered = [cross_hat.multiply(cross_hat > F32(eps)).tocsr() for eps in DGCF_EPSILONS]
+    for f in filtered:
+        f.eliminate_zeros()
+    cross_edges = [len(f.data) for f in filtered]
+    ratios = [float("inf") if c == 0 else (edges / c if edges > c else c / edges) for c in cross_edges]
+    best = int(np.argmin(ratios))
+    out = (a_hat + filtered[best] + sparse.eye(a_hat.shape[0], dtype=F32, format="csr")).tocsr().astype(F32)
+    out.sort_indices()
+    return out, dict(edges=edges, cross_edges=cross_edges, ratios=ratios, epsilon=DGCF_EPSILONS[best])
+
+
+def dgcf_conv(x, m, w):
+    """DGCFConv.call (dgcf_conv.py:32-36) with LocalityAdaptive (:101-102): M (x * sigmoid(w)), w [N,1]."""
+    gate = sigmoid(np.asarray(w, F32).reshape(-1, 1))
+    return (m @ (np.asarray(x, F32) * gate).astype(F32)).astype(F32)
+
+
 # ------------------------------------------------------------------------- P2
 def sage_aggregate(x, indptr, indices, aggregate="mean"):
     """Neighbourhood aggregate over the RAW edge list (values ignored, dups kept)."""
@@ -194,10 +227,12 @@ def propagate(kind, emb, graph, layer_weights, final_node="concatenation", aggre
             x = sage_conv(x, graph[0], graph[1], w["kernel"], w["bias"], aggregate)
         elif kind == "gat":
             x = gat_conv(x, graph[0], graph[1], w["kernel"], w["attn_self"], w["attn_neigh"], w["bias"])
+        elif kind == "dgcf":
+            x = dgcf_conv(x, graph, w["locality_adaptive/locality-adaptive-weights"])
         else:
             raise ValueError(kind)
         hs.append(x)
-    if kind == "lightgcn":
+    if kind in ("lightgcn", "dgcf"):
         final_node = "mean"  # gnn.py:378
     return reduce_layers(hs, final_node)
 

@@ -40,7 +40,7 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
     leaves = {}
     emb = leaves["embeddings"] = _t(w["embeddings"], dtype)
     n = emb.shape[0]
-    if kind in ("gcn", "lightgcn"):
+    if kind in ("gcn", "lightgcn", "dgcf"):
         a = _csr_torch(graph.indptr, graph.indices, graph.data, n, dtype)
     elif kind == "gat":
         from .graph import gat_edges
@@ -60,6 +60,11 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
             x = torch.relu(torch.sparse.mm(a, x @ k) + b)
         elif kind == "lightgcn":
             x = torch.sparse.mm(a, x)
+        elif kind == "dgcf":
+            gw = leaves["layers.%d.locality_adaptive/locality-adaptive-weights" % li] = _t(
+                lw["locality_adaptive/locality-adaptive-weights"], dtype)
+            reg.append(gw)
+            x = torch.sparse.mm(a, x * torch.sigmoid(gw))
         elif kind == "sage":
             k = leaves["layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
             b = leaves["layers.%d.bias" % li] = _t(lw["bias"], dtype)
@@ -88,7 +93,7 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
         else:
             raise ValueError(kind)
         hs.append(x)
-    if kind == "lightgcn":
+    if kind in ("lightgcn", "dgcf"):
         final_node = "mean"
     if final_node == "concatenation":
         red = torch.cat(hs, dim=1)

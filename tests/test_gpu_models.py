@@ -12,7 +12,7 @@ from tests.helpers import assert_close, assert_topk_equivalent, export_weights, 
 
 pytestmark = pytest.mark.gpu
 
-KINDS = {"BasicGCN": "gcn", "BasicGraphSage": "sage", "BasicGAT": "gat", "BasicLightGCN": "lightgcn"}
+KINDS = {"BasicGCN": "gcn", "BasicGraphSage": "sage", "BasicGAT": "gat", "BasicLightGCN": "lightgcn", "BasicDGCF": "dgcf"}
 # the six grids of econfigs/basic-gnn.yaml: (embedding_dim, n_hiddens, dense_units, clf_units)
 GRIDS = [(8, [8, 8], [24, 24], [48, 48]), (16, [16, 16], [48, 48], [64, 64]), (32, [32, 32], [96, 48], [64, 64]),
          (8, [8, 8, 8], [32, 32], [64, 64]), (16, [16, 16, 16], [64, 64], [64, 64]), (32, [32, 32, 32], [128, 64], [64, 64])]
@@ -28,6 +28,8 @@ def _device():
 def _oracle_graph(kind, adj):
     if kind in ("gcn", "lightgcn"):
         return og.gcn_filter(adj)
+    if kind == "dgcf":
+        return ol.dgcf_preprocess(adj)[0]
     ptr, idx, _ = og.reorder_raw(adj)
     return (ptr, idx)
 
@@ -133,8 +135,8 @@ def test_constructor_contract():
         basic.BasicGCN(adj, cache_neighbours=True)
     with pytest.raises(ValueError):
         basic.BasicGCN(adj, final_node="nope")
-    with pytest.raises(NotImplementedError):
-        basic.BasicDGCF(adj)
+    d = basic.BasicDGCF(adj, final_node="concatenation", embedding_dim=8, n_layers=2)
+    assert d.gnn.gnn_layers.final_node == "mean"  # gnn.py:405 overrides it
     m = basic.BasicLightGCN(adj, final_node="concatenation", embedding_dim=8, n_layers=2)
     assert m.gnn.gnn_layers.final_node == "mean"  # gnn.py:378 overrides it
     assert len(gnn.GCN(adj, n_hiddens=(8, 8, 8)).gnn_layers) == 3
@@ -333,3 +335,23 @@ def test_large_graph_properties():
     lhs = (x.double() * ay.double()).sum().item()
     rhs = (ax.double() * y.double()).sum().item()
     assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), 1.0)  # fp32 outputs, float64 reduction
+
+
+@pytest.mark.parametrize("case", ["ui", "uip-dups"])
+def test_dgcf_operator_matches_the_reference_recipe(case):
+    """DGCFConv.preprocess on device (SpGEMM products + the graph-build pipeline + threshold search) against the
+    scipy recipe of dgcf_conv.py:38-80: same epsilon chosen, same structure, values within 1e-5."""
+    from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
+    if case == "ui":
+        adj = random_bipartite(150, 100, 1800, seed=5)
+    else:
+        adj = random_bipartite(120, 90, 1500, seed=6, n_props=40, n_links=300, dup_links=60)
+    want, info = ol.dgcf_preprocess(adj)
+    g = DeviceGraph.from_scipy(adj)
+    got = g.dgcf.to_scipy()
+    assert g.dgcf_info["epsilon"] == info["epsilon"] and g.dgcf_info["edges"] == info["edges"]
+    assert g.dgcf_info["cross_edges"] == info["cross_edges"], (g.dgcf_info, info)
+    got.sort_indices()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert_close(got.data, want.data, what="dgcf operator values")
+    assert abs(got - got.T).max() < 1e-6  # symmetric: the training backward relies on it

@@ -15,7 +15,7 @@ from tests.test_gpu_models import KINDS, _build, _oracle_graph, _randomise
 
 pytestmark = pytest.mark.gpu
 
-TRAINABLE = ["BasicGCN", "BasicGraphSage", "BasicLightGCN", "BasicGAT"]
+TRAINABLE = ["BasicGCN", "BasicGraphSage", "BasicLightGCN", "BasicGAT", "BasicDGCF"]
 GRAD_RTOL = 2e-4
 GRAD_FLOOR = 1e-10  # a gradient that is analytically ~0 (e.g. GAT's attn_kernel_self when all scores share a sign)
 
@@ -44,7 +44,7 @@ def _named_grads(model, tape):
         if name == "gnn/gnn_layers/embeddings":
             out["embeddings"] = g
         elif name.startswith("gnn/gnn_layers/seq_layers."):
-            k, leaf = name[len("gnn/gnn_layers/seq_layers."):].split("/")
+            k, leaf = name[len("gnn/gnn_layers/seq_layers."):].split("/", 1)
             out["layers.%s.%s" % (k, leaf)] = g.reshape(g.shape[0], -1) if leaf == "kernel" else g.reshape(-1) if leaf.startswith("attn") else g
         elif name.startswith("rs/"):
             stack, layer, leaf = name[3:].split("/")
@@ -68,9 +68,9 @@ def test_gradients_match_autograd_oracle(name, final_node):
     n_users, n_items = 300, 200
     adj = random_bipartite(n_users, n_items, 6000, seed=7)
     model = _build(name, adj, (16, [16, 16], [48, 48], [64, 64]))
-    if KINDS[name] == "lightgcn":
+    if KINDS[name] in ("lightgcn", "dgcf"):
         if final_node != "mean":
-            pytest.skip("LightGCN forces final_node='mean' (gnn.py:378)")
+            pytest.skip("LightGCN and DGCF force final_node='mean' (gnn.py:378,405)")
     else:
         from deep_cbrs_amar_renaissance_b200.layers import ReductionLayer
         model.gnn.gnn_layers.final_node = final_node
@@ -82,7 +82,7 @@ def test_gradients_match_autograd_oracle(name, final_node):
     kind = KINDS[name]
     tape, loss, correct, probs = training.forward_backward(model, (u, i), y)
     torch.cuda.synchronize()
-    fn = "mean" if kind == "lightgcn" else final_node
+    fn = "mean" if kind in ("lightgcn", "dgcf") else final_node
     want, want_loss, want_p = ot.gradients(kind, w, _oracle_graph(kind, adj), (u, i), y, final_node=fn)
     assert_close(probs.cpu().numpy().reshape(-1), want_p, rtol=2e-5, what=name + " probabilities")
     assert abs(float(loss.item()) - want_loss) <= 1e-5 * max(1.0, abs(want_loss))
@@ -131,10 +131,11 @@ def test_three_adam_steps_match_oracle(name):
     _randomise(model, seed=8)
     kind = KINDS[name]
     graph = _oracle_graph(kind, adj)
-    fn = "mean" if kind == "lightgcn" else "concatenation"
+    fn = "mean" if kind in ("lightgcn", "dgcf") else "concatenation"
     adam = training.Adam(learning_rate=1e-2)
     l2 = training.l2_coefficients(model)
-    assert len(l2) == (1 if kind == "lightgcn" else 5) and set(l2.values()) == {1e-4}  # embeddings + 2 x (kernel, bias)
+    # embeddings + per layer: (kernel, bias) for GCN/GAT/GraphSage, the gate for DGCF, nothing for LightGCN
+    assert len(l2) == {"lightgcn": 1, "dgcf": 3}.get(kind, 5) and set(l2.values()) == {1e-4}
     state = {}
     for t, (u, i, y) in enumerate(batches, start=1):
         w = export_weights(model)
@@ -171,7 +172,7 @@ def _oracle_names(model):
         if name == "gnn/gnn_layers/embeddings":
             out.append("embeddings")
         elif name.startswith("gnn/gnn_layers/seq_layers."):
-            k, leaf = name[len("gnn/gnn_layers/seq_layers."):].split("/")
+            k, leaf = name[len("gnn/gnn_layers/seq_layers."):].split("/", 1)
             out.append("layers.%s.%s" % (k, leaf))
         else:
             stack, layer, leaf = name[3:].split("/")
