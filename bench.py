@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--scale", default=os.environ.get("CBRS_BENCH_SCALE", "c5"), choices=sorted(SCALES))
     ap.add_argument("--cpu-scale", default="c5-hundredth", choices=sorted(SCALES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the bf16-operand variant of the step")
     ap.add_argument("--catalog-users", type=int, default=2048)
     return ap.parse_args()
 
@@ -287,6 +288,33 @@ def run_b200(args):
                 "note": "achieved = algorithmic bytes (no-reuse gather model) / measured launch time; it can exceed the "
                         "DRAM peak because hot item rows hit in L2 - `traffic` is what ncu saw cross the HBM pins"}
 
+    # ---- the same step with bf16 STORAGE of the gathered operand (config 5's "bf16 feature variant") -------
+    # Z = X W is written as bf16 by the dense kernel (and travels as bf16 between GPUs); products and sums stay
+    # fp32.  Not the headline: the reference computes in fp32.  Tolerance vs the fp32 result: tests/test_gpu_bf16.py.
+    bf16_block = None
+    if not args.no_bf16:
+        seq.set_feature_dtype("bf16")
+        ops.PROFILE.clear()
+        for _ in range(2):
+            model((u_dev, i_dev))
+        barrier()
+        ops.PROFILE_ON = True
+        ms16, _, _ = timed(lambda: model((u_dev, i_dev)), args.steps, 0)
+        ops.PROFILE_ON = False
+        s_ms = [a.elapsed_time(b) for (name, a, b, _) in ops.PROFILE if name == "spmm"]
+        s_meta = [meta for (name, _, _, meta) in ops.PROFILE if name == "spmm"]
+        ach16 = (sum(m["bytes"] for m in s_meta) / (sum(s_ms) * 1e-3) / 1e9) if s_ms else float("nan")
+        bd16 = {}
+        for (name, a, b, _) in ops.PROFILE:
+            bd16[name] = bd16.get(name, 0.0) + a.elapsed_time(b) / args.steps
+        bf16_block = {"value": LAYERS * nnz_total / (ms16 / args.steps * 1e-3), "unit": "edges/s",
+                      "ms_per_step": ms16 / args.steps, "what": "same step, Z = X W stored as bf16 (264 B/edge), fp32 accumulate",
+                      "spmm_launch_ms": float(np.mean(s_ms)) if s_ms else None, "bytes_per_edge": 8 + DIM * 2,
+                      "roofline": {"bound": "hbm", "achieved": ach16, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": ach16 / hbm_peak}, "step_breakdown_ms": bd16}
+        seq.set_feature_dtype("fp32")
+        ops.PROFILE.clear()
+
     # ---- full-catalog scoring + top-10 for a block of this rank's users --------------------
     model.cache_propagation = True
     model.propagate()
@@ -312,7 +340,7 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.scale, world),
         "edges_per_s_per_gpu": value / world, "nnz_a_hat": nnz_total, "heavy_rows": heavy,
         "graph_build_s": build_s, "gpu_launches": launches, "clocks": clocks,
-        "step_breakdown_ms": breakdown,
+        "step_breakdown_ms": breakdown, "bf16_operands": bf16_block,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": 2 * PAIR_BATCH * 8,
                 "d2h_bytes_per_step": PAIR_BATCH * 4, "ms_per_step": ms_e2e / args.steps},
         "roofline": roofline,

@@ -12,6 +12,8 @@
 // index vectors, so a gathered, concatenated batch is never materialised in HBM.
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace cbrs {
 
 struct DenseParams {
@@ -26,7 +28,24 @@ struct DenseParams {
     float *out_peer[CBRS_MAX_PEERS - 1];
     float *q_peer[CBRS_MAX_PEERS - 1];
     int n_peer;
+    int out_bf16;  // out / out_peer hold bf16 (round to nearest even), ldo in elements
 };
+
+__device__ __forceinline__ void store_out1(float *base, int64_t idx, float v, int bf16) {
+    if (bf16) reinterpret_cast<__nv_bfloat16 *>(base)[idx] = __float2bfloat16_rn(v);
+    else base[idx] = v;
+}
+__device__ __forceinline__ void store_out4(float *base, int64_t idx, float a, float b, float c, float d, int bf16) {
+    if (bf16) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+        uint2 r;
+        r.x = *reinterpret_cast<const unsigned int *>(&lo);
+        r.y = *reinterpret_cast<const unsigned int *>(&hi);
+        *reinterpret_cast<uint2 *>(reinterpret_cast<__nv_bfloat16 *>(base) + idx) = r;
+    } else {
+        *reinterpret_cast<float4 *>(base + idx) = make_float4(a, b, c, d);
+    }
+}
 
 constexpr int kBM = 128, kBK = 32, kTM = 8;
 constexpr int kDenseThreads = 256;
@@ -158,8 +177,8 @@ __global__ void __launch_bounds__(kDenseThreads) dense_kernel(const DenseParams 
             const int ng = n0 + tx * TN + j;
             if (ng < p.n) {
                 const float v = apply_act(acc[i][j] * scale, p.act);
-                p.out[m * p.ldo + ng] = v;
-                for (int q = 0; q < p.n_peer; ++q) p.out_peer[q][m * p.ldo + ng] = v;
+                store_out1(p.out, m * p.ldo + ng, v, p.out_bf16);
+                for (int q = 0; q < p.n_peer; ++q) store_out1(p.out_peer[q], m * p.ldo + ng, v, p.out_bf16);
             }
         }
     }
@@ -306,7 +325,7 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_fast_kernel(const Dens
         if (TN == 8) return n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
         return n0 + tx * TN + j;
     };
-    const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out) % 16 == 0) && TN >= 4;
+    const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out) % (p.out_bf16 ? 8 : 16) == 0) && TN >= 4;
 #pragma unroll
     for (int i = 0; i < kTM; ++i) {
         const int64_t m = m0 + ty + 16 * i;
@@ -347,20 +366,20 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_fast_kernel(const Dens
         for (int j = 0; j < TN; ++j) acc[i][j] = apply_act(acc[i][j] * scale, p.act);
         // copy -1 is the local output; 0 .. n_peer-1 are the peers' (same layout, NVLink stores)
         for (int q = -1; q < p.n_peer; ++q) {
-            float *orow = (q < 0 ? p.out : p.out_peer[q]) + m * p.ldo;
+            float *obase = q < 0 ? p.out : p.out_peer[q];
             if (vec_out) {
 #pragma unroll
                 for (int j0 = 0; j0 < TN; j0 += 4) {
                     const int ng = col_of(j0);
                     if (ng < p.n)  // n % 4 == 0: a 4-wide group is entirely in or out
-                        *reinterpret_cast<float4 *>(orow + ng) =
-                            make_float4(acc[i][j0], acc[i][(j0 + 1) % TN], acc[i][(j0 + 2) % TN], acc[i][(j0 + 3) % TN]);
+                        store_out4(obase, m * p.ldo + ng, acc[i][j0], acc[i][(j0 + 1) % TN], acc[i][(j0 + 2) % TN],
+                                   acc[i][(j0 + 3) % TN], p.out_bf16);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
                     const int ng = col_of(j);
-                    if (ng < p.n) orow[ng] = acc[i][j];
+                    if (ng < p.n) store_out1(obase, m * p.ldo + ng, acc[i][j], p.out_bf16);
                 }
             }
         }
@@ -407,8 +426,12 @@ using namespace cbrs;
 static int dense_impl(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2, int64_t ld2,
                       const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m, int32_t n, int act,
                       int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out, float *out,
-                      int64_t ldo, void *const *out_peers_host, void *const *q_peers_host, int n_peers, void *stream) {
+                      int64_t ldo, void *const *out_peers_host, void *const *q_peers_host, int n_peers, int out_dtype,
+                      void *stream) {
     CBRS_REQUIRE(x1 && w && out, CBRS_E_INVALID, "dense: null argument");
+    CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || out_dtype == CBRS_DTYPE_BF16, CBRS_E_INVALID, "dense: out_dtype=%d", out_dtype);
+    CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || !(rowop == CBRS_ROWOP_L2NORM && n > 128), CBRS_E_UNSUPPORTED,
+                 "dense: the two-pass l2-normalise (n > 128) writes float32 only");
     CBRS_REQUIRE(n_peers >= 0 && n_peers < CBRS_MAX_PEERS && (n_peers == 0 || out_peers_host), CBRS_E_INVALID,
                  "dense: n_peers=%d (at most %d peer copies)", n_peers, CBRS_MAX_PEERS - 1);
     CBRS_REQUIRE(n_peers == 0 || rowop != CBRS_ROWOP_ATTN || q_peers_host, CBRS_E_INVALID,
@@ -427,6 +450,7 @@ static int dense_impl(const float *x1, int64_t ld1, const int64_t *idx1, int32_t
     cudaStream_t s = (cudaStream_t)stream;
     DenseParams p{x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out, out, ldo};
     p.n_peer = n_peers;
+    p.out_bf16 = out_dtype == CBRS_DTYPE_BF16;
     for (int q = 0; q < CBRS_MAX_PEERS - 1; ++q) {
         p.out_peer[q] = q < n_peers ? (float *)out_peers_host[q] : nullptr;
         p.q_peer[q] = (q < n_peers && q_peers_host) ? (float *)q_peers_host[q] : nullptr;
@@ -459,7 +483,7 @@ extern "C" int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int
                           int act, int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out,
                           float *out, int64_t ldo, void *stream) {
     return dense_impl(x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out, out,
-                      ldo, nullptr, nullptr, 0, stream);
+                      ldo, nullptr, nullptr, 0, CBRS_DTYPE_F32, stream);
 }
 
 extern "C" int cbrs_dense_bcast(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2,
@@ -468,5 +492,14 @@ extern "C" int cbrs_dense_bcast(const float *x1, int64_t ld1, const int64_t *idx
                                 float *q_out, float *out, int64_t ldo, void *const *out_peers_host,
                                 void *const *q_peers_host, int n_peers, void *stream) {
     return dense_impl(x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out, out,
-                      ldo, out_peers_host, q_peers_host, n_peers, stream);
+                      ldo, out_peers_host, q_peers_host, n_peers, CBRS_DTYPE_F32, stream);
+}
+
+extern "C" int cbrs_dense_ex(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2, int64_t ld2,
+                             const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m, int32_t n, int act,
+                             int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out, void *out,
+                             int64_t ldo, int out_dtype, void *const *out_peers_host, void *const *q_peers_host, int n_peers,
+                             void *stream) {
+    return dense_impl(x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out,
+                      (float *)out, ldo, out_peers_host, q_peers_host, n_peers, out_dtype, stream);
 }

@@ -15,7 +15,10 @@
 //    second kernel adds the partials in ascending chunk order (fixed tree).
 #include "common.cuh"
 
+#include <cuda_bf16.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 namespace cbrs {
 
@@ -28,7 +31,7 @@ struct SpmmParams {
     const int32_t *chunk_slot;
     int64_t n_chunks;
     int32_t chunk_edges;
-    const float *x;
+    const void *x;  // float32, or bf16 when the kernel is instantiated with XT = __nv_bfloat16
     int64_t ldx;
     float *y;
     int64_t ldy;
@@ -53,6 +56,12 @@ struct Vec<4> {
     __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void load(const float *p) { v = ldg4(p); }
     __device__ __forceinline__ void load_plain(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
+    // 4 bf16 (8 bytes) -> 4 floats; the conversion is exact (bf16 is the top half of a float)
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+        v = make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                        __uint_as_float(r.y & 0xffff0000u));
+    }
     __device__ __forceinline__ void fma(float a, const Vec &x) {
         v.x = fmaf(a, x.v.x, v.x); v.y = fmaf(a, x.v.y, v.y); v.z = fmaf(a, x.v.z, v.z); v.w = fmaf(a, x.v.w, v.w);
     }
@@ -70,6 +79,9 @@ struct Vec<1> {
     __device__ __forceinline__ void zero() { v = 0.f; }
     __device__ __forceinline__ void load(const float *p) { v = __ldg(p); }
     __device__ __forceinline__ void load_plain(const float *p) { v = *p; }
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) {
+        v = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short *>(p)) << 16);
+    }
     __device__ __forceinline__ void fma(float a, const Vec &x) { v = fmaf(a, x.v, v); }
     __device__ __forceinline__ void add(const Vec &x) { v += x.v; }
     __device__ __forceinline__ void div(float c) { v /= c; }
@@ -82,7 +94,7 @@ struct Vec<1> {
 
 constexpr int kSpmmThreads = 256;
 
-template <int G, int VEC, int UMAX = 4, int MINB = 4>
+template <int G, int VEC, int UMAX = 4, int MINB = 4, typename XT = float>
 __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const SpmmParams p) {
     constexpr int U = G < UMAX ? G : UMAX;  // independent row loads in flight per group
     const int64_t gid = ((int64_t)blockIdx.x * kSpmmThreads + threadIdx.x) / G;
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const Sp
     for (int c0 = 0; c0 < p.d; c0 += G * VEC) {
         const int col = c0 + lg * VEC;
         const bool col_ok = col < p.d;
-        const float *xcol = p.x + (col_ok ? col : 0);
+        const XT *xcol = reinterpret_cast<const XT *>(p.x) + (col_ok ? col : 0);
         Vec<VEC> acc;
         acc.zero();
         // (col,val) of the next G edges are fetched while the current G rows are in flight
@@ -195,12 +207,14 @@ static int spmm_variant() {
     return v;
 }
 
-template <int G, int VEC>
+template <int G, int VEC, typename XT = float>
 static int launch(const SpmmParams &p, cudaStream_t s) {
     const int64_t threads = p.n_chunks * G;
     if (threads > 0) {
         const unsigned grid = (unsigned)cdiv(threads, kSpmmThreads);
-        if (G == 32 && VEC == 4) {
+        if (!std::is_same<XT, float>::value) {
+            spmm_chunk_kernel<G, VEC, 4, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p);
+        } else if (G == 32 && VEC == 4) {
             // measured on config 5 (profiles/r01_tune_spmm.log): 4 loads in flight x 32 warps/SM beats
             // 8 x 16 by 1.45x - occupancy, not per-warp MLP, is what saturates HBM here
             switch (spmm_variant()) {
@@ -223,14 +237,14 @@ static int launch(const SpmmParams &p, cudaStream_t s) {
     return CBRS_OK;
 }
 
-template <int VEC>
+template <int VEC, typename XT = float>
 static int dispatch_g(int lanes_needed, const SpmmParams &p, cudaStream_t s) {
-    if (lanes_needed <= 1) return launch<1, VEC>(p, s);
-    if (lanes_needed <= 2) return launch<2, VEC>(p, s);
-    if (lanes_needed <= 4) return launch<4, VEC>(p, s);
-    if (lanes_needed <= 8) return launch<8, VEC>(p, s);
-    if (lanes_needed <= 16) return launch<16, VEC>(p, s);
-    return launch<32, VEC>(p, s);
+    if (lanes_needed <= 1) return launch<1, VEC, XT>(p, s);
+    if (lanes_needed <= 2) return launch<2, VEC, XT>(p, s);
+    if (lanes_needed <= 4) return launch<4, VEC, XT>(p, s);
+    if (lanes_needed <= 8) return launch<8, VEC, XT>(p, s);
+    if (lanes_needed <= 16) return launch<16, VEC, XT>(p, s);
+    return launch<32, VEC, XT>(p, s);
 }
 
 }  // namespace cbrs
@@ -248,7 +262,7 @@ static int spmm_impl(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, i
     CBRS_REQUIRE(g && x && y, CBRS_E_INVALID, "spmm: null argument");
     CBRS_REQUIRE(n_peers >= 0 && n_peers < CBRS_MAX_PEERS && (n_peers == 0 || y_peers_host), CBRS_E_INVALID,
                  "spmm: n_peers=%d (at most %d peer copies)", n_peers, CBRS_MAX_PEERS - 1);
-    CBRS_REQUIRE(dtype == CBRS_DTYPE_F32, CBRS_E_UNSUPPORTED, "spmm: only float32 features are built in this round");
+    CBRS_REQUIRE(dtype == CBRS_DTYPE_F32 || dtype == CBRS_DTYPE_BF16, CBRS_E_INVALID, "spmm: dtype=%d", dtype);
     CBRS_REQUIRE(d > 0 && ldx >= d && ldy >= d, CBRS_E_INVALID, "spmm: d=%d ldx=%lld ldy=%lld", d, (long long)ldx,
                  (long long)ldy);
     CBRS_REQUIRE(agg >= CBRS_AGG_WEIGHTED && agg <= CBRS_AGG_MEAN, CBRS_E_INVALID, "spmm: agg=%d", agg);
@@ -264,20 +278,28 @@ static int spmm_impl(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, i
     p.rowptr = g->rowptr; p.colidx = g->colidx; p.vals = g->vals;
     p.chunk_row = g->chunk_row; p.chunk_begin = g->chunk_begin; p.chunk_slot = g->chunk_slot;
     p.n_chunks = g->n_chunks; p.chunk_edges = g->chunk_edges;
-    p.x = (const float *)x; p.ldx = ldx; p.y = (float *)y; p.ldy = ldy; p.d = d; p.agg = agg;
+    p.x = x; p.ldx = ldx; p.y = (float *)y; p.ldy = ldy; p.d = d; p.agg = agg;
     p.bias = bias; p.relu = relu; p.partial = (float *)workspace;
     p.heavy_row = g->heavy_row; p.heavy_slot_ptr = g->heavy_slot_ptr; p.n_heavy = g->n_heavy;
     bool vec4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 16 == 0) &&
                 ((uintptr_t)y % 16 == 0) && ((uintptr_t)workspace % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0);
     p.n_peer = n_peers;
+    bool vec4_peers = true;
     for (int q = 0; q < CBRS_MAX_PEERS - 1; ++q) {
         p.y_peer[q] = q < n_peers ? (float *)y_peers_host[q] : nullptr;
         if (q < n_peers) {
             CBRS_REQUIRE(p.y_peer[q], CBRS_E_INVALID, "spmm: peer copy %d is null", q);
-            vec4 = vec4 && ((uintptr_t)p.y_peer[q] % 16 == 0);
+            vec4_peers = vec4_peers && ((uintptr_t)p.y_peer[q] % 16 == 0);
         }
     }
+    vec4 = vec4 && vec4_peers;
     cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == CBRS_DTYPE_BF16) {
+        // a 4-wide bf16 group is an 8-byte load: same lane layout as fp32, half the bytes per edge
+        const bool v4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 8 == 0) && ((uintptr_t)y % 16 == 0) &&
+                        ((uintptr_t)workspace % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0) && vec4_peers;
+        return v4 ? dispatch_g<4, __nv_bfloat16>(d / 4, p, s) : dispatch_g<1, __nv_bfloat16>(d, p, s);
+    }
     return vec4 ? dispatch_g<4>(d / 4, p, s) : dispatch_g<1>(d, p, s);
 }
 

@@ -79,8 +79,10 @@ class SymmetricBuffer:
         if self.flat.data_ptr() != self.local:
             raise RuntimeError("torch copied the symmetric buffer instead of viewing it")
 
-    def matrix(self, n, w):
-        """float32 [n, w] view of the local copy"""
+    def matrix(self, n, w, dtype=torch.float32):
+        """[n, w] view of the local copy (float32 or bfloat16)"""
+        if dtype == torch.bfloat16:
+            return self.flat.view(torch.bfloat16)[:n * w].view(n, w)
         return self.flat[:n * w].view(n, w)
 
     def peer_addrs(self, view):
@@ -250,9 +252,10 @@ class RowPartition:
     def local_edges(self, view_name):
         return sum(s.nnz for s in self._slices.get(view_name, []))
 
-    def _buf(self, key, n, w, device):
+    def _buf(self, key, n, w, device, dtype=torch.float32):
+        key = key + (str(dtype),)
         if key not in self._bufs:
-            self._bufs[key] = torch.empty(n, w, dtype=torch.float32, device=device)
+            self._bufs[key] = torch.empty(n, w, dtype=dtype, device=device)
         return self._bufs[key]
 
     def _exchange(self, x, types=None):
@@ -302,11 +305,12 @@ class RowPartition:
                 ops.spmm(sl, zs[s], out[sl.row_offset:sl.row_offset + sl.n_rows, s * hs:(s + 1) * hs], bias=bias, relu=relu)
 
     # ------------------------------------------------------------------ peer exchange
-    def _symbuf(self, key, n, w):
-        """symmetric [n, w] float32 buffer -> (SymmetricBuffer, local matrix view)"""
+    def _symbuf(self, key, n, w, dtype=torch.float32):
+        """symmetric [n, w] buffer -> (SymmetricBuffer, local matrix view)"""
+        key = key + (str(dtype),)
         if key not in self._sym:
-            sb = self.heap.alloc(n * w * 4)
-            self._sym[key] = (sb, sb.matrix(n, w))
+            sb = self.heap.alloc(n * w * (2 if dtype == torch.bfloat16 else 4))
+            self._sym[key] = (sb, sb.matrix(n, w, dtype))
         return self._sym[key]
 
     def _type_of(self, a):
@@ -376,7 +380,8 @@ class RowPartition:
 
             if isinstance(layer, (GCNConv, RGCNConv)):
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
-                zsb, z = self._symbuf(("z", l), len(kernels) * n, layer.channels)
+                zdt = torch.bfloat16 if getattr(layer, "feature_dtype", "fp32") == "bf16" else torch.float32
+                zsb, z = self._symbuf(("z", l), len(kernels) * n, layer.channels, zdt)
                 if not z_ahead:
                     for r, w in enumerate(kernels):
                         for a, b in self.mine:
@@ -390,7 +395,8 @@ class RowPartition:
                     if not nxt.built:
                         nxt.build([(n, widths[l + 1]), None])
                         nxt.built = True
-                    nsb, nz = self._symbuf(("z", l + 1), n, nxt.channels)
+                    ndt = torch.bfloat16 if getattr(nxt, "feature_dtype", "fp32") == "bf16" else torch.float32
+                    nsb, nz = self._symbuf(("z", l + 1), n, nxt.channels, ndt)
                     if self._side is None:
                         self._side = torch.cuda.Stream(device=emb.device, priority=-1)
                     main = torch.cuda.current_stream(emb.device)
@@ -491,7 +497,8 @@ class RowPartition:
                 self._gcn_pipelined(layer, l, x_full, out, graph, relu)
             elif isinstance(layer, (GCNConv, RGCNConv)):
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
-                z = self._buf(("z", l), len(kernels) * n, layer.channels, dev)
+                zdt = torch.bfloat16 if getattr(layer, "feature_dtype", "fp32") == "bf16" else torch.float32
+                z = self._buf(("z", l), len(kernels) * n, layer.channels, dev, zdt)
                 for r, w in enumerate(kernels):
                     for a, b in self.mine:
                         ops.dense(x_full[a:b], w, out=z[r * n + a:r * n + b])

@@ -21,6 +21,9 @@ class _Conv(Layer):
         self.kernel_regularizer, self.bias_regularizer = kernel_regularizer, bias_regularizer
         if activation not in (None, "linear", "relu"):
             raise NotImplementedError("fused epilogues cover relu / linear (all the reference's grids use relu)")
+        # storage type of the operand the sparse kernel gathers ("fp32" = the reference's arithmetic; "bf16" halves the
+        # bytes per edge: products and sums stay fp32, only the stored transform is rounded; SequentialGNN.set_feature_dtype)
+        self.feature_dtype = "fp32"
 
     def _out(self, out, n_rows, device):
         if out is None:
@@ -46,7 +49,7 @@ class GCNConv(_Conv):
     def call(self, inputs, out=None, csr=None, **kwargs):
         x, a = inputs
         csr = csr or a.norm
-        z = ops.dense(x, self.kernel)
+        z = ops.dense(x, self.kernel, out_dtype=torch.bfloat16 if self.feature_dtype == "bf16" else None)
         return ops.spmm(csr, z, self._out(out, csr.n_rows, x.device), bias=self.bias,
                         relu=self.activation == "relu")
 

@@ -37,6 +37,16 @@ class SequentialGNN(Model):
         self.partition = None  # set by distributed.RowPartition.attach
         self.built = True
 
+    def set_feature_dtype(self, dtype):
+        """'fp32' (the reference's arithmetic, default) or 'bf16': GCN layers store the transform Z = X W that the
+        sparse kernel gathers as bf16 (fp32 products and sums; stated tolerance in tests/test_gpu_bf16.py)."""
+        if dtype not in ("fp32", "bf16"):
+            raise ValueError("feature dtype must be 'fp32' or 'bf16'")
+        for layer in self.seq_layers:
+            if dtype == "bf16" and not isinstance(layer, GCNConv):
+                raise NotImplementedError("bf16 operand storage is built for GCNConv stacks")
+            layer.feature_dtype = dtype
+
     @property
     def n_hops(self):
         return len(self.seq_layers)

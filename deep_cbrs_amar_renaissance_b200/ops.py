@@ -36,10 +36,10 @@ def _ptr(t, dtype=None):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _rowmajor(t):
-    """(tensor, leading dimension) of a 2-D float32 view whose rows are contiguous."""
-    if t.dim() != 2 or t.dtype != torch.float32 or (t.shape[1] > 1 and t.stride(1) != 1):
-        raise L.CbrsError("expected a 2-D float32 tensor with unit column stride")
+def _rowmajor(t, dtypes=(torch.float32,)):
+    """(tensor, leading dimension in elements) of a 2-D view whose rows are contiguous."""
+    if t.dim() != 2 or t.dtype not in dtypes or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise L.CbrsError("expected a 2-D {} tensor with unit column stride".format("/".join(str(d) for d in dtypes)))
     return t, (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
 
 
@@ -111,7 +111,8 @@ def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None,
     peers: device addresses of the same `out` view in the other ranks' symmetric buffers; every
     finished row is stored there too (cbrs_spmm_csr_bcast)."""
     lib = L.load()
-    x, ldx = _rowmajor(x)
+    x, ldx = _rowmajor(x, (torch.float32, torch.bfloat16))
+    xdt = L.DTYPE_BF16 if x.dtype == torch.bfloat16 else L.DTYPE_F32
     out, ldy = _rowmajor(out)
     d = x.shape[1]
     if out.shape[1] != d or out.shape[0] != csr.n_rows:
@@ -123,17 +124,18 @@ def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None,
         e0.record()
     if peers:
         L.check(lib.cbrs_spmm_csr_bcast(ctypes.byref(csr.desc), _ptr(x), ldx, _ptr(out), ldy, d, agg,
-                                        _ptr(bias, torch.float32), 1 if relu else 0, L.DTYPE_F32, _ptr_array(peers),
+                                        _ptr(bias, torch.float32), 1 if relu else 0, xdt, _ptr_array(peers),
                                         len(peers), _ptr(ws), ws.numel(), _stream()), "cbrs_spmm_csr_bcast")
     else:
         L.check(lib.cbrs_spmm_csr(ctypes.byref(csr.desc), _ptr(x), ldx, _ptr(out), ldy, d, agg,
-                                  _ptr(bias, torch.float32), 1 if relu else 0, L.DTYPE_F32, _ptr(ws), ws.numel(),
+                                  _ptr(bias, torch.float32), 1 if relu else 0, xdt, _ptr(ws), ws.numel(),
                                   _stream()), "cbrs_spmm_csr")
     if PROFILE_ON:
         e1.record()
         # algorithmic bytes of this launch: nnz*(4 col + 4 val + d*4 row) + rows*(d*4 out + 8 rowptr)
+        xb = x.element_size()
         PROFILE.append(("spmm", e0, e1, {"nnz": csr.nnz, "rows": csr.n_rows, "d": d,
-                                         "bytes": csr.nnz * (8 + 4 * d) + csr.n_rows * (4 * d + 8)}))
+                                         "bytes": csr.nnz * (8 + xb * d) + csr.n_rows * (4 * d + 8)}))
     _count(1 + (1 if csr.chunks["n_heavy"] else 0))
     return out
 
@@ -159,7 +161,7 @@ def gat(csr, z, p, q, out, bias=None, relu=True, row_offset=0, workspace=None, p
 
 
 def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_NONE, a_self=None, a_neigh=None,
-          out=None, m=None, peers=None, q_out=None, q_peers=None):
+          out=None, m=None, peers=None, q_out=None, q_peers=None, out_dtype=None):
     """act(rowop([x1[idx1] || x2[idx2]] @ w + b)); returns out (and (p, q) for the attention row-op).
     peers / q_peers: device addresses of the same `out` (and q) views in the other ranks' symmetric
     buffers; finished rows are stored there too (cbrs_dense_bcast)."""
@@ -177,8 +179,8 @@ def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_
         raise L.CbrsError("dense: kernel must be contiguous [{}, n], got {}".format(f1 + f2, tuple(w.shape)))
     n = w.shape[1]
     if out is None:
-        out = torch.empty(m, n, dtype=torch.float32, device=x1.device)
-    out, ldo = _rowmajor(out)
+        out = torch.empty(m, n, dtype=out_dtype or torch.float32, device=x1.device)
+    out, ldo = _rowmajor(out, (torch.float32, torch.bfloat16))
     p_out = None
     if rowop != L.ROWOP_ATTN:
         q_out = None
@@ -190,7 +192,14 @@ def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_
     if PROFILE_ON:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    if peers:
+    if out.dtype == torch.bfloat16:
+        L.check(lib.cbrs_dense_ex(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2, _ptr(idx2, torch.int64), f2,
+                                  _ptr(w, torch.float32), _ptr(b, torch.float32), m, n, code, rowop,
+                                  _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32), _ptr(p_out), _ptr(q_out),
+                                  _ptr(out), ldo, L.DTYPE_BF16, _ptr_array(peers) if peers else None,
+                                  _ptr_array(q_peers) if q_peers else None, len(peers) if peers else 0, _stream()),
+                "cbrs_dense_ex")
+    elif peers:
         L.check(lib.cbrs_dense_bcast(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2,
                                      _ptr(idx2, torch.int64), f2, _ptr(w, torch.float32), _ptr(b, torch.float32), m, n,
                                      code, rowop, _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32),

@@ -116,7 +116,8 @@ int cbrs_chunks_fill(const int64_t *rowptr, int64_t n_rows, int32_t chunk_edges,
 #define CBRS_AGG_SUM 1      /* edge values ignored                      */
 #define CBRS_AGG_MEAN 2     /* sum / edge count; empty row -> 0         */
 #define CBRS_DTYPE_F32 0
-#define CBRS_DTYPE_BF16 1   /* X stored bf16, accumulate fp32, Y fp32 or bf16 (same as X) */
+#define CBRS_DTYPE_BF16 1   /* X stored bf16 (ldx in elements), products and accumulation fp32, Y fp32: the gathered
+                               operand costs 2 B per element instead of 4 (264 instead of 520 B per edge at D=128) */
 
 size_t cbrs_spmm_workspace_bytes(const cbrs_csr_t *g, int32_t d);
 int cbrs_spmm_csr(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d,
@@ -152,6 +153,15 @@ int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, co
                int64_t m, int32_t n, int act, int rowop, const float *a_self,
                const float *a_neigh, float *p_out, float *q_out, float *out, int64_t ldo,
                void *stream);
+
+/* General form of cbrs_dense: the output (and its peer copies) can be written as bf16 (out_dtype =
+ * CBRS_DTYPE_BF16, round to nearest even, ldo in elements) so that the GCN transform Z = X W feeds the bf16
+ * sparse kernel without a conversion pass; out_peers_host / q_peers_host / n_peers as in cbrs_dense_bcast.  */
+int cbrs_dense_ex(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2, int64_t ld2,
+                  const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m, int32_t n, int act,
+                  int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out, void *out,
+                  int64_t ldo, int out_dtype, void *const *out_peers_host, void *const *q_peers_host, int n_peers,
+                  void *stream);
 
 /* ---- reduction of layer outputs (row P5) ------------------------------------
  * out = sum_l coef[l] * h_l  ('sum': 1, 'mean': add then divide by L, 'w-sum': w^2).

@@ -61,10 +61,20 @@ def dense_classifier(x, layers, act="relu"):
     return dense(x, k, b, "sigmoid")
 
 
+def bf16_round(x):
+    """float32 -> nearest bfloat16 (ties to even) -> float32: what storing a tensor as bf16 does to it"""
+    u = np.ascontiguousarray(x, dtype=F32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) & np.uint32(0xFFFF0000)).view(F32)
+
+
 # ------------------------------------------------------------------------- P1
-def gcn_conv(x, a_hat, kernel, bias, act="relu"):
-    """[3P] spektral GCNConv.call: act(A_hat @ (x @ kernel) + bias). Transform first."""
+def gcn_conv(x, a_hat, kernel, bias, act="relu", operand_dtype="fp32"):
+    """[3P] spektral GCNConv.call: act(A_hat @ (x @ kernel) + bias). Transform first.
+    operand_dtype='bf16' restates the product's optional bf16 STORAGE of the transform (products and sums fp32)."""
     z = (np.asarray(x, F32) @ np.asarray(kernel, F32)).astype(F32)
+    if operand_dtype == "bf16":
+        z = bf16_round(z)
     y = (a_hat @ z).astype(F32)
     if bias is not None:
         y = y + np.asarray(bias, F32)
@@ -210,7 +220,7 @@ def reduce_layers(hs, method="concatenation", w=None):
 
 
 # ------------------------------------------------------------------------- P0
-def propagate(kind, emb, graph, layer_weights, final_node="concatenation", aggregate="mean"):
+def propagate(kind, emb, graph, layer_weights, final_node="concatenation", aggregate="mean", operand_dtype="fp32"):
     """SequentialGNN.call, models/gnn.py:74-84: x=E; hs=[x]; for l: x=layer([x,A]); reduce(hs).
 
     kind in {'gcn','lightgcn','sage','gat'}; graph = scipy CSR A_hat for
@@ -220,7 +230,7 @@ def propagate(kind, emb, graph, layer_weights, final_node="concatenation", aggre
     hs = [x]
     for w in layer_weights:
         if kind == "gcn":
-            x = gcn_conv(x, graph, w["kernel"], w["bias"])
+            x = gcn_conv(x, graph, w["kernel"], w["bias"], operand_dtype=operand_dtype)
         elif kind == "lightgcn":
             x = lightgcn_conv(x, graph)
         elif kind == "sage":
