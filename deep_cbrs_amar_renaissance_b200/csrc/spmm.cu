@@ -145,12 +145,29 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const Sp
                     cc[u] = __shfl_sync(gmask, c, k0 + u, G);
                     vv[u] = __shfl_sync(gmask, v, k0 + u, G);
                 }
+                if constexpr (!std::is_same<XT, float>::value && VEC == 4) {
+                    // bf16 rows: keep the raw 8-byte loads in flight (2 registers each) and widen at the FMA, so twice
+                    // as many row loads fit in the register budget - the same BYTES in flight per warp as the fp32 kernel
+                    uint2 raw[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (col_ok && k0 + u < cnt) xr[u].load(xcol + (int64_t)cc[u] * p.ldx);
+                    for (int u = 0; u < U; ++u)
+                        if (col_ok && k0 + u < cnt)
+                            raw[u] = __ldg(reinterpret_cast<const uint2 *>(xcol + (int64_t)cc[u] * p.ldx));
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    if (col_ok && k0 + u < cnt) acc.fma(vv[u], xr[u]);
+                    for (int u = 0; u < U; ++u)
+                        if (col_ok && k0 + u < cnt) {
+                            xr[0].v = make_float4(__uint_as_float(raw[u].x << 16), __uint_as_float(raw[u].x & 0xffff0000u),
+                                                  __uint_as_float(raw[u].y << 16), __uint_as_float(raw[u].y & 0xffff0000u));
+                            acc.fma(vv[u], xr[0]);
+                        }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (col_ok && k0 + u < cnt) xr[u].load(xcol + (int64_t)cc[u] * p.ldx);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (col_ok && k0 + u < cnt) acc.fma(vv[u], xr[u]);
+                }
             }
         }
         if (!col_ok) continue;
@@ -213,7 +230,13 @@ static int launch(const SpmmParams &p, cudaStream_t s) {
     if (threads > 0) {
         const unsigned grid = (unsigned)cdiv(threads, kSpmmThreads);
         if (!std::is_same<XT, float>::value) {
-            spmm_chunk_kernel<G, VEC, 4, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p);
+            switch (spmm_variant()) {  // CBRS_SPMM_VARIANT: loads in flight for the bf16 kernel (tuning knob)
+                case 1: spmm_chunk_kernel<G, VEC, 4, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 2: spmm_chunk_kernel<G, VEC, 16, 3, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 3: spmm_chunk_kernel<G, VEC, 8, 3, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 4: spmm_chunk_kernel<G, VEC, 6, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                default: spmm_chunk_kernel<G, VEC, 8, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
+            }
         } else if (G == 32 && VEC == 4) {
             // measured on config 5 (profiles/r01_tune_spmm.log): 4 loads in flight x 32 warps/SM beats
             // 8 x 16 by 1.45x - occupancy, not per-warp MLP, is what saturates HBM here
