@@ -278,6 +278,256 @@ __global__ void __launch_bounds__(kTcThreads, QREG ? 4 : 3) score_tc_kernel(cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v2 (first classifier width <= 64, the reference's grids): packed bf16 producer + software pipeline.
+//  * P[u] and Q[i] are rounded to bf16 once (Q by the prep kernel into the workspace, P while it is staged in
+//    shared memory); a thread keeps its item's Q row as 8 x uint4 (32 registers instead of 64) and builds its A
+//    row with add.rn.bf16x2 + max.bf16x2: 8 packed instructions per 16-byte chunk instead of 20 scalar ones.
+//    h1 = bf16(bf16(P) + bf16(Q)), relu - the bf16 oracle in the tests does the same roundings;
+//  * A tiles and TMEM accumulators are double buffered: the A tile of step s+1 is produced and its MMA issued
+//    BEFORE the epilogue of step s, so the tensor core's issue->commit latency hides behind CUDA-core work;
+//  * the epilogue uses the packed fp32 pipe (add.rn.f32x2 / fma.rn.f32x2) for bias and the output layer.
+struct ScoreTc2Params {
+    const float *P; int64_t ldp;
+    const uint4 *Qb;            // [n_items_pad][8] : 64 bf16 per item, zero padded
+    int64_t n_users; int32_t n_items;
+    int32_t c1, c2;
+    const uint8_t *w2_image;
+    const float *b2, *w3, *b3;
+    int32_t k;
+    int32_t *ids_out; float *scores_out;
+};
+
+__global__ void score_tc_qprep_kernel(const float *__restrict__ Q, int64_t ldq, int32_t n_items, int32_t n_items_pad,
+                                      int32_t c1, uint4 *__restrict__ Qb) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk (8 bf16) per thread
+    if (e >= (int64_t)n_items_pad * 8) return;
+    const int64_t it = e >> 3;
+    const int cg = (int)(e & 7);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int kk = cg * 8 + j;
+        v[j] = (it < n_items && kk < c1) ? Q[it * ldq + kk] : 0.f;
+    }
+    Qb[e] = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                       tc::pack_bf16x2(v[6], v[7]));
+}
+
+__device__ __forceinline__ uint32_t bf16x2_add_relu(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162 *>(&a), y = *reinterpret_cast<const __nv_bfloat162 *>(&b);
+    const __nv_bfloat162 r = __hmax2(__hadd2(x, y), __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<const uint32_t *>(&r);
+}
+__device__ __forceinline__ unsigned long long f32x2_pack(float lo, float hi) {
+    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 4) score_tc2_kernel(const ScoreTc2Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int c1 = p.c1;
+    const int n_pad = (p.c2 + 15) / 16 * 16;
+    const int cap = 2 * p.k + kTcTI;
+    unsigned char *As = smem_raw;                                    // [2][128][128 B]
+    unsigned char *Bs = As + 2 * 16384;                              // [n_pad][128 B]
+    uint4 *Pb = reinterpret_cast<uint4 *>(Bs + n_pad * 128);         // [TU][8] bf16 rows of P
+    float4 *bw = reinterpret_cast<float4 *>(Pb + kTcTU * 8);         // [n_pad/2] (b2[2j], b2[2j+1], w3[2j], w3[2j+1])
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(bw + n_pad / 2);  // [TU][cap]
+    unsigned long long *thr = cand + kTcTU * cap;                    // [TU]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + kTcTU);      // [2]
+    int *cnt = reinterpret_cast<int *>(mbar + 2);                    // [TU]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(cnt + kTcTU);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t u0 = (int64_t)blockIdx.x * kTcTU;
+    const float b3 = __ldg(p.b3);
+    uint32_t tmem_cols = 64;
+    while ((int)tmem_cols < 2 * n_pad) tmem_cols <<= 1;
+    const uint32_t buf_cols = tmem_cols / 2;
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (tid == 0) {
+        tc::mbar_init(mbar, 1);
+        tc::mbar_init(mbar + 1, 1);
+        tc::fence_mbar_init();
+    }
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(p.w2_image);
+        int4 *dst = reinterpret_cast<int4 *>(Bs);
+        for (int e = tid; e < n_pad * 8; e += kTcThreads) dst[e] = __ldg(src + e);
+        for (int e = tid; e < n_pad / 2; e += kTcThreads) {
+            const int j0 = 2 * e, j1 = 2 * e + 1;
+            bw[e] = make_float4(j0 < p.c2 ? __ldg(p.b2 + j0) : 0.f, j1 < p.c2 ? __ldg(p.b2 + j1) : 0.f,
+                                j0 < p.c2 ? __ldg(p.w3 + j0) : 0.f, j1 < p.c2 ? __ldg(p.w3 + j1) : 0.f);
+        }
+        for (int e = tid; e < kTcTU * 8; e += kTcThreads) {
+            const int ul = e >> 3, cg = e & 7;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kk = cg * 8 + j;
+                v[j] = (kk < c1 && u0 + ul < p.n_users) ? __ldg(p.P + (u0 + ul) * p.ldp + kk) : 0.f;
+            }
+            Pb[e] = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                               tc::pack_bf16x2(v[6], v[7]));
+        }
+        if (tid < kTcTU) { cnt[tid] = 0; thr[tid] = 0ull; }
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs);
+    if ((a_addr & 1023u) != 0u) __trap();
+    const uint32_t idesc = tc::idesc_bf16_f32(128, n_pad);
+    const int k_steps = (c1 + 15) / 16;
+    const int chunks = k_steps * 2;
+    constexpr int kPasses = kTcTU / 4;
+    const int n_tiles = (p.n_items + kTcTI - 1) / kTcTI;
+    const int n_steps = n_tiles * kPasses;
+
+    uint4 qreg[8];
+    auto load_q = [&](int tile) {  // rows are padded to a multiple of 32 items: no bounds check
+        const uint4 *qr = p.Qb + ((int64_t)tile * kTcTI + lane) * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) qreg[j] = __ldg(qr + j);
+    };
+    auto produce = [&](int step) {   // A row `tid` of step `step` into buffer step & 1
+        const int pass = step % kPasses;
+        const uint4 *prow = Pb + (pass * 4 + warp) * 8;
+        unsigned char *a = As + (step & 1) * 16384;
+#pragma unroll
+        for (int cg = 0; cg < 8; ++cg) {
+            if (cg < chunks) {
+                const uint4 pv = prow[cg];
+                const uint4 qv = qreg[cg];
+                uint4 h;
+                h.x = bf16x2_add_relu(pv.x, qv.x); h.y = bf16x2_add_relu(pv.y, qv.y);
+                h.z = bf16x2_add_relu(pv.z, qv.z); h.w = bf16x2_add_relu(pv.w, qv.w);
+                *reinterpret_cast<uint4 *>(a + tc::sw128_offset(tid, cg)) = h;
+            }
+        }
+    };
+    auto issue = [&](int step) {     // one thread: the MMAs of step `step` into TMEM buffer step & 1
+        const uint32_t d = tmem_base + (uint32_t)(step & 1) * buf_cols;
+        const uint32_t a = a_addr + (uint32_t)(step & 1) * 16384;
+        for (int s = 0; s < k_steps; ++s) {
+            const uint32_t koff = (uint32_t)s * 32;
+            tc::mma_bf16_ss(d, tc::smem_desc_sw128(a + koff), tc::smem_desc_sw128(b_addr + koff), idesc, s > 0 ? 1u : 0u);
+        }
+        tc::mma_commit(mbar + (step & 1));
+    };
+
+    load_q(0);
+    produce(0);
+    load_q(kPasses == 1 ? 1 : 0);  // (kPasses > 1: step 1 still belongs to tile 0)
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        tc::tc_fence_after_sync();
+        issue(0);
+    }
+    for (int step = 0; step < n_steps; ++step) {
+        const int tile = step / kPasses, pass = step % kPasses;
+        const int nxt = step + 1;
+        if (pass == 0)
+            for (int ul = warp; ul < kTcTU; ul += kTcThreads / 32)
+                if (cnt[ul] > cap - kTcTI) tcs_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
+        if (nxt < n_steps) {
+            produce(nxt);                                   // qreg holds the tile of step nxt
+            if (nxt % kPasses == kPasses - 1 && nxt + 1 < n_steps) load_q(nxt / kPasses + 1);  // refill for the tile after
+        }
+        tc::fence_proxy_async_smem();
+        tc::tc_fence_before_sync();   // my tcgen05.ld of step-1 precede the MMA that will overwrite that TMEM buffer
+        __syncthreads();
+        if (tid == 0 && nxt < n_steps) {
+            tc::tc_fence_after_sync();
+            issue(nxt);
+        }
+        tc::mbar_wait(mbar + (step & 1), (uint32_t)(step >> 1) & 1u);
+        tc::tc_fence_after_sync();
+        // ---- epilogue of `step`: accumulator row `tid` ------------------------------------------------------
+        const uint32_t trow = tmem_row + (uint32_t)(step & 1) * buf_cols;
+        unsigned long long logit2 = 0ull;
+        for (int cb = 0; cb < n_pad; cb += 32) {
+            uint32_t v0[16], v1[16];
+            tc::tmem_ld16(trow + (uint32_t)cb, v0);
+            if (cb + 16 < n_pad) tc::tmem_ld16(trow + (uint32_t)cb + 16, v1);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const float4 t = bw[(cb + j) >> 1];
+                const unsigned long long x = f32x2_add(((unsigned long long)v0[j + 1] << 32) | v0[j], f32x2_pack(t.x, t.y));
+                const float lo = fmaxf(__uint_as_float((uint32_t)x), 0.f), hi = fmaxf(__uint_as_float((uint32_t)(x >> 32)), 0.f);
+                logit2 = f32x2_fma(f32x2_pack(lo, hi), f32x2_pack(t.z, t.w), logit2);
+            }
+            if (cb + 16 < n_pad) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    const float4 t = bw[(cb + 16 + j) >> 1];
+                    const unsigned long long x = f32x2_add(((unsigned long long)v1[j + 1] << 32) | v1[j], f32x2_pack(t.x, t.y));
+                    const float lo = fmaxf(__uint_as_float((uint32_t)x), 0.f), hi = fmaxf(__uint_as_float((uint32_t)(x >> 32)), 0.f);
+                    logit2 = f32x2_fma(f32x2_pack(lo, hi), f32x2_pack(t.z, t.w), logit2);
+                }
+            }
+        }
+        const float logit = __uint_as_float((uint32_t)logit2) + __uint_as_float((uint32_t)(logit2 >> 32));
+        const int ul = pass * 4 + warp;
+        const int item = tile * kTcTI + lane;
+        const int64_t user = u0 + ul;
+        if (item < p.n_items && user < p.n_users) {
+            const unsigned long long key =
+                ((unsigned long long)tcs_orderable(logit + b3) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)item);
+            if (key > thr[ul]) {
+                const int pos = atomicAdd(cnt + ul, 1);
+                cand[ul * cap + pos] = key;
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc::tc_fence_after_sync();
+        tc::tmem_dealloc(tmem_base, tmem_cols);
+    }
+    for (int ul = warp; ul < kTcTU; ul += kTcThreads / 32) {
+        tcs_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
+        const int64_t user = u0 + ul;
+        if (user >= p.n_users) continue;
+        const int n = cnt[ul];
+        for (int r = lane; r < p.k; r += 32) {
+            const int64_t o = user * p.k + r;
+            if (r < n) {
+                const unsigned long long key = cand[ul * cap + r];
+                p.ids_out[o] = (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+                p.scores_out[o] = 1.f / (1.f + expf(-tcs_from_orderable((uint32_t)(key >> 32))));
+            } else {
+                p.ids_out[o] = -1;
+                p.scores_out[o] = -INFINITY;
+            }
+        }
+    }
+}
+
+static size_t score_tc2_smem(int c2, int k) {
+    const int n_pad = (c2 + 15) / 16 * 16, cap = 2 * k + kTcTI;
+    return 1024 + 2 * 16384 + (size_t)n_pad * 128 + (size_t)kTcTU * 8 * 16 + (size_t)(n_pad / 2) * 16 +
+           (size_t)kTcTU * cap * 8 + kTcTU * 8 + 16 + kTcTU * 4 + 16;
+}
+
 static size_t score_tc_smem(int c1, int c2, int k) {
     const int kb = (c1 + 63) / 64, n_pad = (c2 + 15) / 16 * 16, cap = 2 * k + kTcTI;
     return 1024 + (size_t)kb * 16384 + (size_t)kb * n_pad * 128 + (size_t)kTcTU * kb * 64 * 4 + (size_t)n_pad * 8 +
@@ -288,9 +538,13 @@ static size_t score_tc_smem(int c1, int c2, int k) {
 
 using namespace cbrs;
 
-extern "C" size_t cbrs_score_catalog_topk_bf16_workspace_bytes(int32_t c1, int32_t c2) {
+static bool score_tc_use_v2(int c1, int c2) { return c1 <= 64 && c2 <= 128; }
+
+extern "C" size_t cbrs_score_catalog_topk_bf16_workspace_bytes(int32_t n_items, int32_t c1, int32_t c2) {
     const int kb = (c1 + 63) / 64, n_pad = (c2 + 15) / 16 * 16;
-    return align_up((size_t)kb * n_pad * 128);
+    size_t bytes = align_up((size_t)kb * n_pad * 128);
+    if (score_tc_use_v2(c1, c2)) bytes += align_up((size_t)((n_items + kTcTI - 1) / kTcTI) * kTcTI * 128);  // Q as bf16, 128 B per item
+    return bytes;
 }
 
 extern "C" int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const float *Q, int64_t ldq, int64_t n_users,
@@ -304,7 +558,7 @@ extern "C" int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const f
                  "score_catalog_bf16: classifier widths c1=%d (multiple of 8, <= 256), c2=%d (<= 256)", c1, c2);
     CBRS_REQUIRE(ldp >= c1 && ldq >= c1 && ldq % 4 == 0 && ((uintptr_t)Q % 16) == 0, CBRS_E_INVALID,
                  "score_catalog_bf16: Q must be 16-byte aligned with ldq %% 4 == 0");
-    const size_t need = cbrs_score_catalog_topk_bf16_workspace_bytes(c1, c2);
+    const size_t need = cbrs_score_catalog_topk_bf16_workspace_bytes(n_items, c1, c2);
     CBRS_REQUIRE(workspace && workspace_bytes >= need && ((uintptr_t)workspace % 16) == 0, CBRS_E_WORKSPACE,
                  "score_catalog_bf16: workspace %zu < %zu bytes", workspace_bytes, need);
     if (n_users == 0) return CBRS_OK;
@@ -312,6 +566,20 @@ extern "C" int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const f
     const int kb = (c1 + 63) / 64, n_pad = (c2 + 15) / 16 * 16;
     score_tc_prep_kernel<<<32, 256, 0, s>>>(w2, c1, c2, n_pad, kb, (uint8_t *)workspace);
     CBRS_CHECK_LAUNCH("score_tc_prep");
+    if (score_tc_use_v2(c1, c2)) {
+        const int n_items_pad = (n_items + kTcTI - 1) / kTcTI * kTcTI;
+        uint4 *Qb = reinterpret_cast<uint4 *>((uint8_t *)workspace + align_up((size_t)kb * n_pad * 128));
+        score_tc_qprep_kernel<<<(unsigned)cdiv((int64_t)n_items_pad * 8, 256), 256, 0, s>>>(Q, ldq, n_items, n_items_pad, c1, Qb);
+        CBRS_CHECK_LAUNCH("score_tc_qprep");
+        const size_t smem2 = score_tc2_smem(c2, k);
+        CBRS_REQUIRE(smem2 <= 220 * 1024, CBRS_E_UNSUPPORTED, "score_catalog_bf16: needs %zu bytes of shared memory", smem2);
+        cudaError_t e2 = cudaFuncSetAttribute(score_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        CBRS_REQUIRE(e2 == cudaSuccess, CBRS_E_CUDA, "score_catalog_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e2));
+        ScoreTc2Params p2{P, ldp, Qb, n_users, n_items, c1, c2, (const uint8_t *)workspace, b2, w3, b3, k, ids_out, scores_out};
+        score_tc2_kernel<<<(unsigned)cdiv(n_users, kTcTU), kTcThreads, smem2, s>>>(p2);
+        CBRS_CHECK_LAUNCH("score_tc2");
+        return CBRS_OK;
+    }
     const size_t smem = score_tc_smem(c1, c2, k);
     CBRS_REQUIRE(smem <= 220 * 1024, CBRS_E_UNSUPPORTED, "score_catalog_bf16: needs %zu bytes of shared memory", smem);
     ScoreTcParams p{P, ldp, Q, ldq, n_users, n_items, c1, c2, (const uint8_t *)workspace, b2, w3, b3, k, ids_out, scores_out};

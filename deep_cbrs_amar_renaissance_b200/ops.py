@@ -299,13 +299,13 @@ def score_catalog_topk(P, Q, w2, b2, w3, b3, k, precision="fp32"):
         c2 = w2.shape[1]
         ids = torch.empty(n_users, k, dtype=torch.int32, device=P.device)
         vals = torch.empty(n_users, k, dtype=torch.float32, device=P.device)
-        ws = _ws(lib.cbrs_score_catalog_topk_bf16_workspace_bytes(c1, c2), P.device)
+        ws = _ws(lib.cbrs_score_catalog_topk_bf16_workspace_bytes(Q.shape[0], c1, c2), P.device)
         L.check(lib.cbrs_score_catalog_topk_bf16(_ptr(P), ldp, _ptr(Q), ldq, n_users, Q.shape[0], c1,
                                                  _ptr(w2, torch.float32), _ptr(b2, torch.float32), c2,
                                                  _ptr(w3, torch.float32), _ptr(b3, torch.float32), k, _ptr(ids),
                                                  _ptr(vals), _ptr(ws), ws.numel(), _stream()),
                 "cbrs_score_catalog_topk_bf16")
-        _count(2)
+        _count(3 if c1 <= 64 and c2 <= 128 else 2)
         return ids, vals
     P, ldp = _rowmajor(P)
     Q, ldq = _rowmajor(Q)

