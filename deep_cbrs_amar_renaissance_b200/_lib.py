@@ -95,6 +95,9 @@ _SIGS = {
     "cbrs_bce": (c_int, [P, P, c_int64, P, P, P, P]),
     "cbrs_sum_squares": (c_int, [P, c_int64, c_float, P, c_int, P]),
     "cbrs_adam_step": (c_int, [P, P, P, P, c_int64, c_float, P, c_float, c_float, c_float, c_float, P]),
+    "cbrs_attn_fuse": (c_int, [P, c_int64, P, c_int64, P, P, c_int64, c_int32, P, c_int64, P]),
+    "cbrs_attn_fuse_grad": (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int32, P, P, P, P, P]),
+    "cbrs_add3_act": (c_int, [P, c_int64, P, c_int64, P, c_int64, c_int64, c_int32, c_int, P, c_int64, P]),
     "cbrs_gat_backward_workspace_bytes": (c_size_t, [c_int64]),
     "cbrs_gat_backward": (c_int, [POINTER(CsrDesc), P, c_int64, P, P, P, c_int64, P, P, c_int64, c_int32, P, P, P, c_int64,
                                   P, P, P, c_size_t, P]),

@@ -517,3 +517,89 @@ extern "C" int cbrs_adam_step(float *w, const float *g, float *m, float *v, int6
     CBRS_CHECK_LAUNCH("adam_step");
     return CBRS_OK;
 }
+
+// ------------------------------------------------------------------ hybrid tweaks: attention fusion, residual add
+// FusionLayer('attention') (/root/reference/src/layers/fusion.py:56-68): x = stack([a, b]); att = softmax_over_the_two(
+// tanh(x @ W)); out = sum(att * x).  With ta = tanh(a W), tb = tanh(b W) (two cbrs_dense calls, shared W):
+// s = sigmoid(ta - tb); out = s*a + (1-s)*b.
+namespace cbrs {
+__global__ void attn_fuse_kernel(const float *__restrict__ a, int64_t lda, const float *__restrict__ b, int64_t ldb,
+                                 const float *__restrict__ ta, const float *__restrict__ tb, int64_t rows, int32_t d,
+                                 float *__restrict__ out, int64_t ldo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * d) return;
+    const int64_t r = i / d;
+    const int c = (int)(i % d);
+    const float ea = expf(ta[i]), eb = expf(tb[i]);  // tanh output: |t| <= 1, no overflow; same form as tf.math.softmax
+    const float inv = 1.f / (ea + eb);
+    out[r * ldo + c] = (ea * inv) * a[r * lda + c] + (eb * inv) * b[r * ldb + c];
+}
+// da = g*s, db = g*(1-s) (direct paths); dta = g*(a-b)*s*(1-s), dtb = -dta (through the softmax)
+__global__ void attn_fuse_grad_kernel(const float *__restrict__ g, int64_t ldg, const float *__restrict__ a, int64_t lda,
+                                      const float *__restrict__ b, int64_t ldb, const float *__restrict__ ta,
+                                      const float *__restrict__ tb, int64_t rows, int32_t d, float *__restrict__ da,
+                                      float *__restrict__ db, float *__restrict__ dta, float *__restrict__ dtb) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * d) return;
+    const int64_t r = i / d;
+    const int c = (int)(i % d);
+    const float ea = expf(ta[i]), eb = expf(tb[i]);
+    const float s = ea / (ea + eb);
+    const float gv = g[r * ldg + c];
+    da[i] = gv * s;
+    db[i] = gv * (1.f - s);
+    const float t = gv * (a[r * lda + c] - b[r * ldb + c]) * s * (1.f - s);
+    dta[i] = t;
+    dtb[i] = -t;
+}
+// out = act(a + b + c): the residual classifier's activation(residual(x) + x1 + x2) (src/models/hybrid.py:89)
+__global__ void add3_act_kernel(const float *__restrict__ a, int64_t lda, const float *__restrict__ b, int64_t ldb,
+                                const float *__restrict__ c3, int64_t ldc, int64_t rows, int32_t d, int act,
+                                float *__restrict__ out, int64_t ldo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * d) return;
+    const int64_t r = i / d;
+    const int c = (int)(i % d);
+    float v = (a[r * lda + c] + b[r * ldb + c]) + c3[r * ldc + c];
+    switch (act) {
+        case CBRS_ACT_RELU: v = fmaxf(v, 0.f); break;
+        case CBRS_ACT_SIGMOID: v = 1.f / (1.f + expf(-v)); break;
+        case CBRS_ACT_TANH: v = tanhf(v); break;
+        default: break;
+    }
+    out[r * ldo + c] = v;
+}
+}  // namespace cbrs
+
+extern "C" int cbrs_attn_fuse(const float *a, int64_t lda, const float *b, int64_t ldb, const float *ta, const float *tb,
+                              int64_t rows, int32_t d, float *out, int64_t ldo, void *stream) {
+    CBRS_REQUIRE(a && b && ta && tb && out && rows >= 0 && d > 0 && lda >= d && ldb >= d && ldo >= d, CBRS_E_INVALID,
+                 "attn_fuse: bad argument");
+    if (rows == 0) return CBRS_OK;
+    attn_fuse_kernel<<<(unsigned)cdiv(rows * d, 256), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, ta, tb, rows, d, out, ldo);
+    CBRS_CHECK_LAUNCH("attn_fuse");
+    return CBRS_OK;
+}
+
+extern "C" int cbrs_attn_fuse_grad(const float *g, int64_t ldg, const float *a, int64_t lda, const float *b, int64_t ldb,
+                                   const float *ta, const float *tb, int64_t rows, int32_t d, float *da, float *db,
+                                   float *dta, float *dtb, void *stream) {
+    CBRS_REQUIRE(g && a && b && ta && tb && da && db && dta && dtb && rows >= 0 && d > 0 && ldg >= d && lda >= d && ldb >= d,
+                 CBRS_E_INVALID, "attn_fuse_grad: bad argument");
+    if (rows == 0) return CBRS_OK;
+    attn_fuse_grad_kernel<<<(unsigned)cdiv(rows * d, 256), 256, 0, (cudaStream_t)stream>>>(g, ldg, a, lda, b, ldb, ta, tb, rows,
+                                                                                          d, da, db, dta, dtb);
+    CBRS_CHECK_LAUNCH("attn_fuse_grad");
+    return CBRS_OK;
+}
+
+extern "C" int cbrs_add3_act(const float *a, int64_t lda, const float *b, int64_t ldb, const float *c, int64_t ldc,
+                             int64_t rows, int32_t d, int act, float *out, int64_t ldo, void *stream) {
+    CBRS_REQUIRE(a && b && c && out && rows >= 0 && d > 0 && lda >= d && ldb >= d && ldc >= d && ldo >= d, CBRS_E_INVALID,
+                 "add3_act: bad argument");
+    CBRS_REQUIRE(act >= CBRS_ACT_NONE && act <= CBRS_ACT_TANH, CBRS_E_INVALID, "add3_act: act=%d", act);
+    if (rows == 0) return CBRS_OK;
+    add3_act_kernel<<<(unsigned)cdiv(rows * d, 256), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, c, ldc, rows, d, act, out, ldo);
+    CBRS_CHECK_LAUNCH("add3_act");
+    return CBRS_OK;
+}

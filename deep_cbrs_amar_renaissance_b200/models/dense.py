@@ -13,4 +13,6 @@ def build_dense_classifier(units, n_classes, **kwargs):
 
 
 def build_residual_dense_network(units, **kwargs):
-    raise NotImplementedError("residual classifier: tweaks grid only, outside the first hot-path bar (DESIGN.md)")
+    """dense.py:20-27: like build_dense_network but the last Dense is linear (the activation follows the residual add)."""
+    units = list(units)
+    return DenseStack(units, activation=kwargs.get('activation'), last_activation=None if units else "same")

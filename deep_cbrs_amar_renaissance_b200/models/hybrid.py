@@ -14,7 +14,9 @@ import torch
 from ..keras_like import Model, default_device
 from ..layers.fusion import FusionLayer
 from .basic import _ids
-from .dense import build_dense_classifier, build_dense_network
+from .. import ops
+from ..layers.dense import materialize
+from .dense import build_dense_classifier, build_dense_network, build_residual_dense_network
 from .gnn import GAT, GCN, DGCF, RGCN, GraphSage, LightGCN
 
 
@@ -40,9 +42,15 @@ class HybridCBRS(Model):
         self.dense3a = build_dense_network(dense_units[2], activation=activation)
         self.dense3b = build_dense_network(dense_units[2], activation=activation)
         if residual:
-            raise NotImplementedError("residual classifier: tweaks grid only, outside the first hot-path bar")
-        self.residual = self.activation = None
-        self.clf = build_dense_classifier(clf_units, n_classes=1, activation=activation)
+            if dense_units[2][-1] != clf_units[-1]:
+                raise ValueError("The last dense units before the last fusion layer "
+                                 "must be equal to the last classifier units for residual connections")
+            self.residual = build_residual_dense_network(clf_units, activation=activation)
+            self.activation = activation
+            self.clf = build_dense_classifier([], n_classes=1)
+        else:
+            self.residual = self.activation = None
+            self.clf = build_dense_classifier(clf_units, n_classes=1, activation=activation)
         self.built = True
 
     def build_for(self, d_graph, d_content):
@@ -50,9 +58,17 @@ class HybridCBRS(Model):
         self.dense1b.build_for(d_graph)
         c = self.dense2a.build_for(d_content)
         self.dense2b.build_for(d_content)
-        o1 = self.dense3a.build_for(2 * g if self.feature_based else g + c)
-        o2 = self.dense3b.build_for(2 * c if self.feature_based else g + c)
-        self.clf.build_for(o1 + o2)
+        if self.feature_based:
+            o1 = self.dense3a.build_for(self.fuse1a.build_for(g, g))
+            o2 = self.dense3b.build_for(self.fuse1b.build_for(c, c))
+        else:
+            o1 = self.dense3a.build_for(self.fuse1a.build_for(g, c))
+            o2 = self.dense3b.build_for(self.fuse1b.build_for(g, c))
+        x = self.fuse2.build_for(o1, o2)
+        if self.residual is not None:
+            self.clf.build_for(self.residual.build_for(x))
+        else:
+            self.clf.build_for(x)
 
     def call(self, inputs, **kwargs):
         ug, ig, ub, ib = inputs
@@ -63,13 +79,29 @@ class HybridCBRS(Model):
         ig = (self.dense1b.call_sources([ig_src]), None)
         ub = (self.dense2a.call_sources([ub_src]), None)
         ib = (self.dense2b.call_sources([ib_src]), None)
+        return self.tail(ug, ig, ub, ib)
+
+    @staticmethod
+    def _fuse(layer, a_src, b_src):
+        """FusionLayer on two (matrix, row index) sources -> the source list the next Dense consumes:
+        both sources for 'concatenate' (the kernel concatenates on the fly), the fused matrix for 'attention'."""
+        if layer.method == 'concatenate':
+            return [a_src, b_src]
+        return [(layer([materialize([a_src]), materialize([b_src])]), None)]
+
+    def tail(self, ug, ig, ub, ib):
+        """Everything after the four per-entity towers (hybrid.py:79-89); arguments are (matrix, row index) sources."""
         if self.feature_based:
-            x1 = self.dense3a.call_sources([ug, ig])
-            x2 = self.dense3b.call_sources([ub, ib])
+            x1 = self.dense3a.call_sources(self._fuse(self.fuse1a, ug, ig))
+            x2 = self.dense3b.call_sources(self._fuse(self.fuse1b, ub, ib))
         else:
-            x1 = self.dense3a.call_sources([ug, ub])
-            x2 = self.dense3b.call_sources([ig, ib])
-        return self.clf.call_sources([(x1, None), (x2, None)])
+            x1 = self.dense3a.call_sources(self._fuse(self.fuse1a, ug, ub))
+            x2 = self.dense3b.call_sources(self._fuse(self.fuse1b, ig, ib))
+        x = self._fuse(self.fuse2, (x1, None), (x2, None))
+        if self.residual is None:
+            return self.clf.call_sources(x)
+        r = self.residual.call_sources(x)
+        return self.clf.call_sources([(ops.add3_act(r, x1, x2, self.activation), None)])
 
 
 class HybridBertGNN(Model, abc.ABC):

@@ -616,3 +616,47 @@ def row_gate_grad(g, x, w):
                                    _ptr(dw), _stream()), "cbrs_row_gate_grad")
     _count(1)
     return dx, dw
+
+
+# ------------------------------------------------------------------ hybrid tweaks grid (scope row (f)-3)
+def attn_fuse(a, b, ta, tb):
+    """softmax over the two sources, per feature: (e^ta a + e^tb b) / (e^ta + e^tb)"""
+    lib = L.load()
+    a, lda = _rowmajor(a)
+    b, ldb = _rowmajor(b)
+    rows, d = a.shape
+    out = torch.empty(rows, d, dtype=torch.float32, device=a.device)
+    L.check(lib.cbrs_attn_fuse(_ptr(a), lda, _ptr(b), ldb, _ptr(ta.contiguous(), torch.float32),
+                               _ptr(tb.contiguous(), torch.float32), rows, d, _ptr(out), d, _stream()), "cbrs_attn_fuse")
+    _count(1)
+    return out
+
+
+def attn_fuse_grad(g, a, b, ta, tb):
+    """(da, db, dta, dtb) of attn_fuse"""
+    lib = L.load()
+    g, ldg = _rowmajor(g)
+    a, lda = _rowmajor(a)
+    b, ldb = _rowmajor(b)
+    rows, d = a.shape
+    outs = [torch.empty(rows, d, dtype=torch.float32, device=a.device) for _ in range(4)]
+    L.check(lib.cbrs_attn_fuse_grad(_ptr(g), ldg, _ptr(a), lda, _ptr(b), ldb, _ptr(ta.contiguous(), torch.float32),
+                                    _ptr(tb.contiguous(), torch.float32), rows, d, _ptr(outs[0]), _ptr(outs[1]),
+                                    _ptr(outs[2]), _ptr(outs[3]), _stream()), "cbrs_attn_fuse_grad")
+    _count(1)
+    return outs
+
+
+def add3_act(a, b, c, act=None):
+    """act(a + b + c)"""
+    lib = L.load()
+    a, lda = _rowmajor(a)
+    b, ldb = _rowmajor(b)
+    c, ldc = _rowmajor(c)
+    rows, d = a.shape
+    out = torch.empty(rows, d, dtype=torch.float32, device=a.device)
+    code = act if isinstance(act, int) else L.ACTS[act]
+    L.check(lib.cbrs_add3_act(_ptr(a), lda, _ptr(b), ldb, _ptr(c), ldc, rows, d, code, _ptr(out), d, _stream()),
+            "cbrs_add3_act")
+    _count(1)
+    return out

@@ -41,12 +41,10 @@ def _pair_scorer(model, emb, user_nodes, item_nodes):
     ig = rs.dense1b.call_sources([(emb, item_nodes)])
     ub = rs.dense2a.call_sources([(table, user_nodes)])
     ib = rs.dense2b.call_sources([(table, item_nodes)])
-    if rs.feature_based:
-        def score(pu, pi):
-            x1 = rs.dense3a.call_sources([(ug, pu), (ig, pi)])
-            x2 = rs.dense3b.call_sources([(ub, pu), (ib, pi)])
-            return rs.clf.call_sources([(x1, None), (x2, None)])
-        return score
+    plain = rs.residual is None and all(f.method == 'concatenate' for f in (rs.fuse1a, rs.fuse1b, rs.fuse2))
+    if rs.feature_based or not plain:
+        return lambda pu, pi: rs.tail((ug, pu), (ig, pi), (ub, pu), (ib, pi))
+    # entity-based, plain: dense3a / dense3b depend on one entity each and are hoisted too
     x1 = rs.dense3a.call_sources([(ug, None), (ub, None)])
     x2 = rs.dense3b.call_sources([(ig, None), (ib, None)])
     return lambda pu, pi: rs.clf.call_sources([(x1, pu), (x2, pi)])

@@ -102,8 +102,46 @@ def basic_rs_train(tape, rs, u_src, i_src):
     return stack_train(tape, rs.clf, u + i)[0]
 
 
+class _Linear:
+    """Dense-like view of a bare weight (FusionLayer's projection / attention matrices) for dense_train."""
+
+    def __init__(self, kernel, activation=None):
+        self.kernel, self.bias, self.activation = kernel, None, activation
+
+    def build_for(self, in_features):
+        return self.kernel.shape[1]
+
+
+def fuse_train(tape, layer, a, b):
+    """FusionLayer (/root/reference/src/layers/fusion.py:49-68) on the tape -> the node list the next Dense consumes."""
+    if layer.method == 'concatenate':
+        return [a, b]
+    layer.build_for(a.x.shape[1], b.x.shape[1])
+    if layer.proj_first is not None:
+        if layer.proj_first:
+            a = dense_train(tape, _Linear(layer.proj_weight), [a])
+        else:
+            b = dense_train(tape, _Linear(layer.proj_weight), [b])
+    ta = dense_train(tape, _Linear(layer.att_weight, "tanh"), [a])
+    tb = dense_train(tape, _Linear(layer.att_weight, "tanh"), [b])
+    node = Node(ops.attn_fuse(a.x, b.x, ta.x, tb.x))
+
+    def bwd():
+        if node.grad is None:
+            return
+        da, db, dta, dtb = ops.attn_fuse_grad(node.grad, a.x, b.x, ta.x, tb.x)
+        a.add_grad(da)
+        b.add_grad(db)
+        ta.add_grad(dta)
+        tb.add_grad(dtb)
+
+    tape.ops.append(bwd)
+    return [node]
+
+
 def hybrid_rs_train(tape, rs, ug, ig, ub, ib):
-    """HybridCBRS.call (/root/reference/src/models/hybrid.py:72-89), concatenate fusion"""
+    """HybridCBRS.call (/root/reference/src/models/hybrid.py:72-89): towers, fusion ('concatenate' or 'attention'),
+    classifier or residual classifier"""
     for name in ("dense1a", "dense1b", "dense2a", "dense2b", "dense3a", "dense3b"):
         if not getattr(rs, name).layers:
             raise NotImplementedError("training a HybridCBRS with an empty '%s' stack" % name)
@@ -112,12 +150,27 @@ def hybrid_rs_train(tape, rs, ug, ig, ub, ib):
     ub = stack_train(tape, rs.dense2a, [ub])[0]
     ib = stack_train(tape, rs.dense2b, [ib])[0]
     if rs.feature_based:
-        x1 = stack_train(tape, rs.dense3a, [ug, ig])[0]
-        x2 = stack_train(tape, rs.dense3b, [ub, ib])[0]
+        x1 = stack_train(tape, rs.dense3a, fuse_train(tape, rs.fuse1a, ug, ig))[0]
+        x2 = stack_train(tape, rs.dense3b, fuse_train(tape, rs.fuse1b, ub, ib))[0]
     else:
-        x1 = stack_train(tape, rs.dense3a, [ug, ub])[0]
-        x2 = stack_train(tape, rs.dense3b, [ig, ib])[0]
-    return stack_train(tape, rs.clf, [x1, x2])[0]
+        x1 = stack_train(tape, rs.dense3a, fuse_train(tape, rs.fuse1a, ug, ub))[0]
+        x2 = stack_train(tape, rs.dense3b, fuse_train(tape, rs.fuse1b, ig, ib))[0]
+    x = fuse_train(tape, rs.fuse2, x1, x2)
+    if rs.residual is None:
+        return stack_train(tape, rs.clf, x)[0]
+    r = stack_train(tape, rs.residual, x)[0]
+    h = Node(ops.add3_act(r.x, x1.x, x2.x, rs.activation))
+
+    def bwd():
+        if h.grad is None:
+            return
+        ds = ops.act_grad(h.grad, h.x, rs.activation)
+        r.add_grad(ds)
+        x1.add_grad(ds)
+        x2.add_grad(ds)
+
+    tape.ops.append(bwd)
+    return stack_train(tape, rs.clf, [h])[0]
 
 
 # ------------------------------------------------------------------ GNN layers

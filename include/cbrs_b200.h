@@ -347,6 +347,16 @@ int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int acc
 int cbrs_adam_step(float *w, const float *g, float *m, float *v, int64_t n, float lr_t, const float *lr_t_dev,
                    float beta1, float beta2, float eps, float l2, void *stream);
 
+/* Hybrid tweaks grid (scope row (f)-3).  FusionLayer('attention') (src/layers/fusion.py:56-68) with
+ * ta = tanh(a W), tb = tanh(b W) from two cbrs_dense calls: out = softmax2(ta, tb) . (a, b) per feature; ta/tb/da/
+ * db/dta/dtb are contiguous [rows, d].  cbrs_add3_act: activation(residual(x) + x1 + x2) (src/models/hybrid.py:89). */
+int cbrs_attn_fuse(const float *a, int64_t lda, const float *b, int64_t ldb, const float *ta, const float *tb,
+                   int64_t rows, int32_t d, float *out, int64_t ldo, void *stream);
+int cbrs_attn_fuse_grad(const float *g, int64_t ldg, const float *a, int64_t lda, const float *b, int64_t ldb,
+                        const float *ta, const float *tb, int64_t rows, int32_t d, float *da, float *db,
+                        float *dta, float *dtb, void *stream);
+int cbrs_add3_act(const float *a, int64_t lda, const float *b, int64_t ldb, const float *c, int64_t ldc,
+                  int64_t rows, int32_t d, int act, float *out, int64_t ldo, void *stream);
 /* Backward of cbrs_gat_csr (fused edge-softmax gradient).  d_o = dY * act'(y).  Outputs: dz [N,h] =
  * sum_i alpha_ij dO_i + dp (x) a_self + dq (x) a_neigh (the full gradient w.r.t. z = X W), dp, dq [N] (for
  * d a_self = z^T dp, d a_neigh = z^T dq).  The graph must be structurally symmetric (every adjacency of the

@@ -272,6 +272,22 @@ def basic_rs(emb, u_ids, i_ids, unet, inet, clf, act="relu"):
 
 
 # -------------------------------------------------------------------- S3 + S4
+def fusion(a, b, fw=None):
+    """layers/fusion.py:49-68.  fw None -> concatenate; else dict(att_weight [, proj_weight, proj_first])."""
+    if fw is None:
+        return np.concatenate([a, b], axis=1)
+    if fw.get("proj_weight") is not None:
+        if fw["proj_first"]:
+            a = (a @ np.asarray(fw["proj_weight"], F32)).astype(F32)
+        else:
+            b = (b @ np.asarray(fw["proj_weight"], F32)).astype(F32)
+    x = np.stack([a, b], axis=1).astype(F32)
+    att = np.tanh(x @ np.asarray(fw["att_weight"], F32), dtype=F32)
+    e = np.exp(att - att.max(axis=1, keepdims=True), dtype=F32)
+    att = e / e.sum(axis=1, keepdims=True)
+    return (att * x).sum(axis=1).astype(F32)
+
+
 def hybrid_cbrs(emb, u_ids, i_ids, u_bert, i_bert, w, act="relu", feature_based=True):
     """HybridBertGNN.embed_recommend + HybridCBRS.call, models/hybrid.py:72-89,130-140.
 
@@ -283,12 +299,19 @@ def hybrid_cbrs(emb, u_ids, i_ids, u_bert, i_bert, w, act="relu", feature_based=
     ub = dense_network(np.asarray(u_bert, F32), w["dense2a"], act)
     ib = dense_network(np.asarray(i_bert, F32), w["dense2b"], act)
     if feature_based:
-        x1 = dense_network(np.concatenate([ug, ig], axis=1), w["dense3a"], act)
-        x2 = dense_network(np.concatenate([ub, ib], axis=1), w["dense3b"], act)
+        x1 = dense_network(fusion(ug, ig, w.get("fuse1a")), w["dense3a"], act)
+        x2 = dense_network(fusion(ub, ib, w.get("fuse1b")), w["dense3b"], act)
     else:
-        x1 = dense_network(np.concatenate([ug, ub], axis=1), w["dense3a"], act)
-        x2 = dense_network(np.concatenate([ig, ib], axis=1), w["dense3b"], act)
-    return dense_classifier(np.concatenate([x1, x2], axis=1), w["clf"], act)
+        x1 = dense_network(fusion(ug, ub, w.get("fuse1a")), w["dense3a"], act)
+        x2 = dense_network(fusion(ig, ib, w.get("fuse1b")), w["dense3b"], act)
+    x = fusion(x1, x2, w.get("fuse2"))
+    if w.get("residual") is None:
+        return dense_classifier(x, w["clf"], act)
+    # models/hybrid.py:89 + models/dense.py:20-27: last residual Dense is linear, activation after the add
+    r = dense_network(x, w["residual"][:-1], act)
+    k, b = w["residual"][-1]
+    r = dense(r, k, b, None)
+    return dense_classifier(activation(act)(r + x1 + x2), w["clf"], act)
 
 
 # ------------------------------------------------------------------------- T

@@ -125,13 +125,35 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
         ig = _dense_stack(red[i], stack("dense1b"))
         ub = _dense_stack(ub, stack("dense2a"))
         ib = _dense_stack(ib, stack("dense2b"))
+        def fuse(name, a, b):
+            fw = w.get(name)
+            if fw is None:
+                return torch.cat([a, b], dim=1)
+            if fw.get("proj_weight") is not None:
+                pw = leaves["%s.proj_weight" % name] = _t(fw["proj_weight"], dtype)
+                if fw["proj_first"]:
+                    a = a @ pw
+                else:
+                    b = b @ pw
+            aw = leaves["%s.att_weight" % name] = _t(fw["att_weight"], dtype)
+            x = torch.stack([a, b], dim=1)
+            att = torch.softmax(torch.tanh(x @ aw), dim=1)
+            return (att * x).sum(dim=1)
+
         if feature_based:
-            x1 = _dense_stack(torch.cat([ug, ig], dim=1), stack("dense3a"))
-            x2 = _dense_stack(torch.cat([ub, ib], dim=1), stack("dense3b"))
+            x1 = _dense_stack(fuse("fuse1a", ug, ig), stack("dense3a"))
+            x2 = _dense_stack(fuse("fuse1b", ub, ib), stack("dense3b"))
         else:
-            x1 = _dense_stack(torch.cat([ug, ub], dim=1), stack("dense3a"))
-            x2 = _dense_stack(torch.cat([ig, ib], dim=1), stack("dense3b"))
-        p = _dense_stack(torch.cat([x1, x2], dim=1), stack("clf"), last_sigmoid=True)
+            x1 = _dense_stack(fuse("fuse1a", ug, ub), stack("dense3a"))
+            x2 = _dense_stack(fuse("fuse1b", ig, ib), stack("dense3b"))
+        x = fuse("fuse2", x1, x2)
+        if w.get("residual") is None:
+            p = _dense_stack(x, stack("clf"), last_sigmoid=True)
+        else:
+            rl = stack("residual")
+            r = _dense_stack(x, rl[:-1])
+            r = r @ rl[-1][0] + rl[-1][1]
+            p = _dense_stack(torch.relu(r + x1 + x2), stack("clf"), last_sigmoid=True)
     p = p.reshape(-1)
     yt = torch.tensor(np.asarray(y, dtype=np.float64), dtype=dtype)
     pc = torch.clamp(p, 1e-7, 1 - 1e-7)

@@ -88,4 +88,11 @@ def export_weights(model):
     else:
         for name in ("dense1a", "dense1b", "dense2a", "dense2b", "dense3a", "dense3b", "clf"):
             out[name] = stack("rs/%s/layers." % name)
+        if any(n.startswith("rs/residual/") for n in w):
+            out["residual"] = stack("rs/residual/layers.")
+        for name in ("fuse1a", "fuse1b", "fuse2"):
+            if "rs/%s/att_weight" % name in w:
+                layer = getattr(model.rs, name)
+                out[name] = dict(att_weight=w["rs/%s/att_weight" % name], proj_weight=w.get("rs/%s/proj_weight" % name),
+                                 proj_first=layer.proj_first)
     return out

@@ -46,6 +46,8 @@ def _named_grads(model, tape):
         elif name.startswith("gnn/gnn_layers/seq_layers."):
             k, leaf = name[len("gnn/gnn_layers/seq_layers."):].split("/", 1)
             out["layers.%s.%s" % (k, leaf)] = g.reshape(g.shape[0], -1) if leaf == "kernel" else g.reshape(-1) if leaf.startswith("attn") else g
+        elif name.startswith("rs/fuse"):
+            out[name[3:].replace("/", ".")] = g
         elif name.startswith("rs/"):
             stack, layer, leaf = name[3:].split("/")
             out["%s.%s.%s" % (stack, layer.split(".")[1], leaf)] = g
@@ -285,3 +287,41 @@ def test_cuda_graph_replay_equals_eager_steps(name):
     assert finals[0][0] == finals[1][0], (finals[0][0], finals[1][0])
     for a, b in zip(finals[0][1], finals[1][1]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("tweak", ["attention", "residual", "attention-projected"])
+def test_hybrid_tweaks_forward_and_gradients(tweak):
+    """econfigs/hybrid-gnn-tweaks*.yaml: attention fusion of the two branches, residual classifier; forward against
+    the numpy oracle, gradients against autograd"""
+    from deep_cbrs_amar_renaissance_b200 import training
+    from oracle import layers as ol
+    n_users, n_items = 200, 150
+    adj = random_bipartite(n_users, n_items, 4000, seed=9)
+    units = [[48, 48], [96, 32], [64, 64]] if tweak != "attention-projected" else [[48, 48], [96, 32], [64, 64]]
+    extra = dict(feature_based=True, fusion_method="attention" if tweak.startswith("attention") else "concatenate",
+                 residual=(tweak == "residual"))
+    if tweak == "attention-projected":  # entity-based: fuse1a/1b see widths 48 and 32 -> the narrower is projected
+        extra["feature_based"] = False
+    model = _build("HybridBertGCN", adj, (16, [16, 16], units, [64, 64]), module="hybrid", **extra)
+    rng = np.random.RandomState(2)
+    u, i, y = _batch(n_users, n_items, 256, 4)
+    ub = (rng.standard_normal((256, 96)) * 0.5).astype(np.float32)
+    ib = (rng.standard_normal((256, 96)) * 0.5).astype(np.float32)
+    model((u, i, ub, ib))
+    _randomise(model, seed=6)
+    w = export_weights(model)
+    emb = ol.propagate("gcn", w["embeddings"], og.gcn_filter(adj), w["layers"])
+    want_fwd = ol.hybrid_cbrs(emb, u, i, ub, ib, w, feature_based=extra["feature_based"])
+    assert_close(model((u, i, ub, ib)).cpu().numpy(), want_fwd, rtol=2e-5, what=tweak + " forward")
+    tape, loss, correct, probs = training.forward_backward(model, (u, i, ub, ib), y)
+    want, want_loss, want_p = ot.gradients("gcn", w, og.gcn_filter(adj), (u, i, ub, ib), y, hybrid=True,
+                                           feature_based=extra["feature_based"])
+    assert_close(probs.cpu().numpy().reshape(-1), want_p, rtol=2e-5, what=tweak + " probabilities")
+    got = _named_grads(model, tape)
+    assert set(got) == set(want), (sorted(set(got) ^ set(want)))
+    for k in sorted(want):
+        assert_grad_close(got[k], want[k], "%s grad %s" % (tweak, k))
+    # catalog scoring goes through the same tail
+    model.set_content_table((rng.standard_normal((n_users + n_items, 96)) * 0.5).astype(np.float32))
+    ids, vals = model.recommend_top_k(n_users, n_items, 5, users=torch.arange(8, device="cuda"))
+    assert ids.shape == (8, 5) and (vals[:, :-1] >= vals[:, 1:]).all()
