@@ -92,6 +92,48 @@ struct Vec<1> {
     __device__ __forceinline__ void store(float *p) const { *p = v; }
 };
 
+// 8-wide lane slice: used for bf16 rows, where 8 elements are one 16-byte load and a 128-wide row needs only 16
+// lanes - two chunks share a warp and every instruction of the edge loop serves two edges
+template <>
+struct Vec<8> {
+    float4 a, b;
+    __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
+    __device__ __forceinline__ void load(const float *p) { a = ldg4(p); b = ldg4(p + 4); }
+    __device__ __forceinline__ void load_plain(const float *p) {
+        a = *reinterpret_cast<const float4 *>(p); b = *reinterpret_cast<const float4 *>(p + 4);
+    }
+    __device__ __forceinline__ void from_raw(const uint4 r) {
+        a = make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                        __uint_as_float(r.y & 0xffff0000u));
+        b = make_float4(__uint_as_float(r.z << 16), __uint_as_float(r.z & 0xffff0000u), __uint_as_float(r.w << 16),
+                        __uint_as_float(r.w & 0xffff0000u));
+    }
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) { from_raw(__ldg(reinterpret_cast<const uint4 *>(p))); }
+    __device__ __forceinline__ void fma(float s, const Vec &x) {
+        a.x = fmaf(s, x.a.x, a.x); a.y = fmaf(s, x.a.y, a.y); a.z = fmaf(s, x.a.z, a.z); a.w = fmaf(s, x.a.w, a.w);
+        b.x = fmaf(s, x.b.x, b.x); b.y = fmaf(s, x.b.y, b.y); b.z = fmaf(s, x.b.z, b.z); b.w = fmaf(s, x.b.w, b.w);
+    }
+    __device__ __forceinline__ void add(const Vec &x) {
+        a.x += x.a.x; a.y += x.a.y; a.z += x.a.z; a.w += x.a.w; b.x += x.b.x; b.y += x.b.y; b.z += x.b.z; b.w += x.b.w;
+    }
+    __device__ __forceinline__ void div(float c) {
+        a.x /= c; a.y /= c; a.z /= c; a.w /= c; b.x /= c; b.y /= c; b.z /= c; b.w /= c;
+    }
+    __device__ __forceinline__ void epilogue(const float *bias, int relu) {
+        if (bias) {
+            const float4 u = ldg4(bias), v = ldg4(bias + 4);
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w; b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+        }
+        if (relu) {
+            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+        }
+    }
+    __device__ __forceinline__ void store(float *p) const {
+        *reinterpret_cast<float4 *>(p) = a; *reinterpret_cast<float4 *>(p + 4) = b;
+    }
+};
+
 constexpr int kSpmmThreads = 256;
 
 template <int G, int VEC, int UMAX = 4, int MINB = 4, typename XT = float>
@@ -158,6 +200,18 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const Sp
                         if (col_ok && k0 + u < cnt) {
                             xr[0].v = make_float4(__uint_as_float(raw[u].x << 16), __uint_as_float(raw[u].x & 0xffff0000u),
                                                   __uint_as_float(raw[u].y << 16), __uint_as_float(raw[u].y & 0xffff0000u));
+                            acc.fma(vv[u], xr[0]);
+                        }
+                } else if constexpr (!std::is_same<XT, float>::value && VEC == 8) {
+                    uint4 raw[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (col_ok && k0 + u < cnt)
+                            raw[u] = __ldg(reinterpret_cast<const uint4 *>(xcol + (int64_t)cc[u] * p.ldx));
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (col_ok && k0 + u < cnt) {
+                            xr[0].from_raw(raw[u]);
                             acc.fma(vv[u], xr[0]);
                         }
                 } else {
@@ -235,7 +289,10 @@ static int launch(const SpmmParams &p, cudaStream_t s) {
                 case 2: spmm_chunk_kernel<G, VEC, 16, 3, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
                 case 3: spmm_chunk_kernel<G, VEC, 8, 3, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
                 case 4: spmm_chunk_kernel<G, VEC, 6, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
-                default: spmm_chunk_kernel<G, VEC, 8, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                default:
+                    if (VEC == 8) spmm_chunk_kernel<G, VEC, 4, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p);
+                    else spmm_chunk_kernel<G, VEC, 8, 4, XT><<<grid, kSpmmThreads, 0, s>>>(p);
+                    break;
             }
         } else if (G == 32 && VEC == 4) {
             // measured on config 5 (profiles/r01_tune_spmm.log): 4 loads in flight x 32 warps/SM beats
@@ -321,6 +378,8 @@ static int spmm_impl(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, i
         // a 4-wide bf16 group is an 8-byte load: same lane layout as fp32, half the bytes per edge
         const bool v4 = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((uintptr_t)x % 8 == 0) && ((uintptr_t)y % 16 == 0) &&
                         ((uintptr_t)workspace % 16 == 0) && (!bias || (uintptr_t)bias % 16 == 0) && vec4_peers;
+        const bool v8 = v4 && (d % 8 == 0) && (ldx % 8 == 0) && ((uintptr_t)x % 16 == 0) && spmm_variant() != 9;
+        if (v8) return dispatch_g<8, __nv_bfloat16>(d / 8, p, s);  // 16-byte loads, half the lanes per row
         return v4 ? dispatch_g<4, __nv_bfloat16>(d / 4, p, s) : dispatch_g<1, __nv_bfloat16>(d, p, s);
     }
     return vec4 ? dispatch_g<4>(d / 4, p, s) : dispatch_g<1>(d, p, s);
