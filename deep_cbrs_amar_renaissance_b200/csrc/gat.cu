@@ -58,9 +58,11 @@ __device__ __forceinline__ float group_sum(float v, unsigned m) {
     return v;
 }
 
+// As for the SpMM kernel (profiles/r01_tune_spmm.log), occupancy beats per-warp memory-level parallelism for this
+// gather: 4 row loads in flight at 64 registers (32 warps per SM) instead of 8 at 104 registers (16 warps).
 template <int G, int VEC>
-__global__ void __launch_bounds__(kGatThreads) gat_chunk_kernel(const GatParams p) {
-    constexpr int U = G < 8 ? G : 8;
+__global__ void __launch_bounds__(kGatThreads, 4) gat_chunk_kernel(const GatParams p) {
+    constexpr int U = G < 4 ? G : 4;
     const int64_t gid = ((int64_t)blockIdx.x * kGatThreads + threadIdx.x) / G;
     if (gid >= p.n_chunks) return;
     const int lane = threadIdx.x & 31;
