@@ -35,9 +35,11 @@ def cpu_train_step_ms(name, model, adj, inputs, y):
     from oracle import graph as og
     from oracle import train as ot
     from tests.helpers import export_weights
-    kind = {"BasicGCN": "gcn", "BasicGraphSage": "sage", "BasicLightGCN": "lightgcn"}[name]
+    kind = {"BasicGCN": "gcn", "BasicGraphSage": "sage", "BasicLightGCN": "lightgcn", "BasicGAT": "gat"}.get(name)
+    if kind is None:
+        return None
     w = export_weights(model)
-    if kind == "sage":
+    if kind in ("sage", "gat"):
         ptr, idx, _ = og.reorder_raw(adj)
         graph = (ptr, idx)
     else:
@@ -62,7 +64,7 @@ def main():
     i = rng.randint(0, n_items, size=batch) + n_users
     bert = (rng.standard_normal((n_users + n_items, 768)) * 0.5).astype(np.float32)
     cases = [("BasicGCN", basic, adj, {}), ("BasicGraphSage", basic, adj, {}), ("BasicGAT", basic, adj, {}),
-             ("BasicLightGCN", basic, adj, {}), ("BasicGCN-uip", basic, adj_uip, {}), ("BasicGAT-uip", basic, adj_uip, {}),
+             ("BasicLightGCN", basic, adj, {}), ("BasicDGCF", basic, adj, {}), ("BasicGCN-uip", basic, adj_uip, {}), ("BasicGAT-uip", basic, adj_uip, {}),
              ("HybridBertGCN", hybrid, adj, dict(dense_units=[[48, 48], [256, 64], [64, 64]], feature_based=True))]
     for name, mod, a, extra in cases:
         set_seed(42)
@@ -74,7 +76,8 @@ def main():
             model.set_content_table(bert)
         inputs = (u, i)
         model(inputs)
-        nnz = (model.gnn.gnn_layers.adj_matrix.raw if ("Sage" in name or "GAT" in name) else model.gnn.gnn_layers.adj_matrix.norm).nnz
+        gph = model.gnn.gnn_layers.adj_matrix
+        nnz = (gph.raw if ("Sage" in name or "GAT" in name) else gph.dgcf if "DGCF" in name else gph.norm).nnz
         eager = timeit(lambda: model(inputs))
         g = GraphedForward(model, batch)
         graphed = timeit(lambda: g(inputs))
