@@ -196,10 +196,13 @@ class RowPartition:
         # peer exchange of a GCN stack: "off" = transform+stores, barrier, sparse kernel, in order;
         # "kernel" = the next layer's fused transform+stores of row block b runs on a high-priority side
         # stream while the sparse kernel works on block b+1; "ce" = same, but the rows travel by copy engine
-        self.pipeline = pipeline or os.environ.get("CBRS_PIPELINE", "off")
-        if self.pipeline not in ("off", "kernel", "ce"):
-            raise ValueError("pipeline must be 'off', 'kernel' or 'ce'")
-        self.row_blocks = int(row_blocks or os.environ.get("CBRS_ROW_BLOCKS", "1" if self.pipeline == "off" else "2"))
+        # "fused" (default) = where both layers are 128-wide fp32 GCN layers, layer l's sparse kernel also computes the next
+        # layer's transform row by row and stores it into every rank's copy from its epilogue (cbrs_spmm_gcn_fused): the
+        # exchange is spread over the whole sparse kernel; other shapes fall back to "off"
+        self.pipeline = pipeline or os.environ.get("CBRS_PIPELINE", "fused")
+        if self.pipeline not in ("off", "kernel", "ce", "fused"):
+            raise ValueError("pipeline must be 'off', 'fused', 'kernel' or 'ce'")
+        self.row_blocks = int(row_blocks or os.environ.get("CBRS_ROW_BLOCKS", "1" if self.pipeline in ("off", "fused") else "2"))
         self._side = None
         self._sym = {}
         self.n_rows_by_type = list(n_rows_by_type)
@@ -390,7 +393,25 @@ class RowPartition:
                     heap.barrier()
                 # software pipeline: while the sparse kernel works on row block b+1, the NEXT layer's transform
                 # of block b is computed and stored into every rank's copy on a side stream
-                z_ahead = self.pipeline != "off" and isinstance(nxt, GCNConv)
+                fuse_next = (self.pipeline == "fused" and isinstance(layer, GCNConv) and isinstance(nxt, GCNConv)
+                             and layer.channels == 128 and nxt.channels == 128 and zdt == torch.float32
+                             and getattr(nxt, "feature_dtype", "fp32") == "fp32")
+                if fuse_next:
+                    if not nxt.built:
+                        nxt.build([(n, widths[l + 1]), None])
+                        nxt.built = True
+                    nsb, nz = self._symbuf(("z", l + 1), n, nxt.channels)
+                    for sl in self.csr_slices("norm", graph):
+                        a, b = sl.row_offset, sl.row_offset + sl.n_rows
+                        ov, zv = out[a:b], nz[a:b]
+                        ops.spmm_gcn_fused(sl, z, ov, layer.bias, relu, nxt.kernel, zv, y_peers=out_peers(ov, a),
+                                           z_peers=nsb.peer_addrs(zv))
+                    heap.barrier()
+                    z_ahead = True
+                    x_full = out
+                    hs.append(out)
+                    continue
+                z_ahead = self.pipeline in ("kernel", "ce") and isinstance(nxt, GCNConv)
                 if z_ahead:
                     if not nxt.built:
                         nxt.build([(n, widths[l + 1]), None])

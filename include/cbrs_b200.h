@@ -254,6 +254,14 @@ int cbrs_peer_barrier(void *const *flags_peers_host, int n_ranks, int my_rank, u
 int cbrs_spmm_csr_bcast(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, int64_t ldy, int32_t d,
                         int agg, const float *bias, int relu, int dtype, void *const *y_peers_host,
                         int n_peers, void *workspace, size_t workspace_bytes, void *stream);
+/* GCN layer l fused with layer l+1's transform and its all-gather, 128-wide layers:
+ *   y = relu(A_hat z + bias) -> y (+ y_peers), and z_next[row] = y[row] @ w_next[128,128] -> z_next (+ z_peers),
+ * both from the sparse kernel's epilogue, so the exchange of the next operand is spread over the whole sparse kernel.
+ * z_next has the bits cbrs_dense would produce from y (same k-ascending fmaf chain).  Workspace as cbrs_spmm_csr. */
+int cbrs_spmm_gcn_fused(const cbrs_csr_t *g, const float *z, int64_t ldz_in, float *y, int64_t ldy, const float *bias,
+                        int relu, const float *w_next, float *z_next, int64_t ldz_next, void *const *y_peers_host,
+                        int n_ypeers, void *const *z_peers_host, int n_zpeers, void *workspace,
+                        size_t workspace_bytes, void *stream);
 int cbrs_gat_csr_bcast(const cbrs_csr_t *g, int64_t row_offset, const float *z, int64_t ldz, const float *p,
                        const float *q, float *y, int64_t ldy, int32_t h, const float *bias, int relu,
                        void *const *y_peers_host, int n_peers, void *workspace, size_t workspace_bytes,

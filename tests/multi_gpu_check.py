@@ -65,6 +65,24 @@ def main():
                 seq.partition = None
             if rank == 0:
                 print("ok", name, "even" if even else "ragged", flush=True)
+    # 128-wide GCN stack: the sparse kernel of layer l also produces layer l+1's transform and stores it into every
+    # rank's copy (cbrs_spmm_gcn_fused); must still equal the single-GPU, unfused result bit for bit
+    set_seed(11)
+    model = basic.BasicGCN(adj, n_hiddens=[128, 128, 128], embedding_dim=128, dense_units=[48, 48], clf_units=[64, 64])
+    seq = model.gnn.gnn_layers
+    model((u, i))
+    full = model.gnn(None).clone()
+    for pipeline in ("fused", "off"):
+        part = RowPartition([n_users, n_items, n_props], final_types=[0, 1, 2], exchange="peer", pipeline=pipeline).attach(seq)
+        for rep in range(2):
+            got = model.gnn(None)
+            torch.cuda.synchronize()
+            assert torch.equal(got, full), "128-wide GCN, pipeline=%s rep %d: partitioned result differs" % (pipeline, rep)
+        part.heap.check()
+        part.close()
+        seq.partition = None
+    if rank == 0:
+        print("ok 128-wide GCN fused transform", flush=True)
     # user-sharded catalog top-k: each rank ranks its own users with replicated item rows
     set_seed(7)
     adj2 = random_bipartite(n_users, n_items, 150000, seed=22)
