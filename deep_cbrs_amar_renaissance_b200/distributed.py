@@ -199,7 +199,9 @@ class RowPartition:
         # "fused" (default) = where both layers are 128-wide fp32 GCN layers, layer l's sparse kernel also computes the next
         # layer's transform row by row and stores it into every rank's copy from its epilogue (cbrs_spmm_gcn_fused): the
         # exchange is spread over the whole sparse kernel; other shapes fall back to "off"
-        self.pipeline = pipeline or os.environ.get("CBRS_PIPELINE", "fused")
+        # measured on config 5: the fused sparse kernel is ~10 % slower than the plain one, which pays off once the
+        # transform-with-stores kernel it replaces is NVLink-bound: 8 GPUs 84.0 -> 94.2 G edges/s, 2 GPUs 27.1 -> 26.2
+        self.pipeline = pipeline or os.environ.get("CBRS_PIPELINE", "fused" if dist.get_world_size(group) >= 4 else "off")
         if self.pipeline not in ("off", "kernel", "ce", "fused"):
             raise ValueError("pipeline must be 'off', 'fused', 'kernel' or 'ce'")
         self.row_blocks = int(row_blocks or os.environ.get("CBRS_ROW_BLOCKS", "1" if self.pipeline in ("off", "fused") else "2"))
