@@ -279,9 +279,12 @@ __global__ void __launch_bounds__(kSpmmThreads) spmm_heavy_kernel(const SpmmPara
 // mbarrier that each warp waits on only when it reaches its epilogue - the copy hides behind the edge loop and no
 // CTA-wide barrier follows it.  The row x matrix product walks k ascending with one fmaf chain per output element,
 // exactly like dense_fast_kernel, so Z^(l+1) has the same bits as the unfused path.
-// Measured (profiles/r01_scaling_exchange_modes.json): the sparse kernel gets ~10 % slower (the 64 KB matrix is
-// re-read from shared memory for every row; batching 4 rows per pass was tried and was slower still), which pays
-// off once the transform-with-stores kernel it replaces is NVLink-bound, i.e. from 4 GPUs up.
+// Measured on one GPU at config 5 (profiles/r01_layer_rooflines_c5.jsonl): 152 ms against 133.6 (sparse) + 10.6
+// (transform) separately - the row x W product is a 128-step dependent fmaf chain per output that the warp runs after
+// its gather, and it costs more in the sparse kernel than in the tiled dense kernel.  Two cheaper-looking forms were
+// tried and were SLOWER: 4 rows per pass over W (170 ms: a warp's critical path gets 4x longer) and the packed
+// fma.rn.f32x2 pipe with y duplicated in shared memory (171 ms).  The fusion pays off once the transform-with-stores
+// kernel it replaces is NVLink-bound, i.e. from 4 GPUs up (profiles/r01_scaling_exchange_modes.json).
 struct FusedParams {
     SpmmParams sp;
     const float *w_next;   // [128, 128] row-major (Keras kernel [in, out])
