@@ -205,6 +205,7 @@ def run_b200(args):
     part = None
     if world > 1:
         part = RowPartition([n_users, n_items], final_types=[1]).attach(seq)  # CBRS_EXCHANGE=nccl|peer
+        os.environ["CBRS_EXCHANGE"] = part.exchange + ("+fused-transform" if part.exchange == "peer" and part.pipeline == "fused" else "")
         part.csr_slices("norm", graph)
         part.release_full_views(graph)
     else:
@@ -330,6 +331,9 @@ def run_b200(args):
     model.cache_propagation = False
     model.invalidate()
 
+    if part is not None and part.heap is not None:
+        part.heap.check()  # raises if any flag barrier timed out during the run
+        torch.cuda.synchronize()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

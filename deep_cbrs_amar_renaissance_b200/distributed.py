@@ -106,9 +106,14 @@ class PeerHeap:
             raise L.CbrsError("peer exchange supports up to {} ranks (one NVSwitch box)".format(L.MAX_PEERS))
         self._lib = L.load()
         self._owned, self._opened = [], []
+        self._open_error = None
         self.flags = self.alloc(L.MAX_PEERS * 8)
         self.status = torch.zeros(1, dtype=torch.int32, device="cuda")
         self.epoch = 0
+        ok = torch.tensor([0 if self._open_error else 1], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) != 1:  # every rank raises together (nobody is left spinning in the flag barrier)
+            raise L.CbrsError("peer mapping failed: {}".format(self._open_error or "on another rank"))
         self.barrier()
         self.check()
 
@@ -131,8 +136,15 @@ class PeerHeap:
                 ptrs.append(ptr.value)
                 continue
             q = ctypes.c_void_p()
-            L.check(self._lib.cbrs_peer_open((ctypes.c_ubyte * L.IPC_HANDLE_BYTES).from_buffer_copy(h),
-                                             ctypes.byref(q)), "cbrs_peer_open")
+            try:
+                L.check(self._lib.cbrs_peer_open((ctypes.c_ubyte * L.IPC_HANDLE_BYTES).from_buffer_copy(h),
+                                                 ctypes.byref(q)), "cbrs_peer_open")
+            except L.CbrsError as e:
+                if getattr(self, "status", None) is not None:
+                    raise  # after construction every rank already knows P2P works; a later failure is fatal
+                self._open_error = e
+                ptrs.append(0)
+                continue
             self._opened.append(q.value)
             ptrs.append(q.value)
         return SymmetricBuffer(self, nbytes, ptrs)
@@ -192,7 +204,25 @@ class RowPartition:
         if exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.exchange = exchange
-        self.heap = PeerHeap(group) if exchange == "peer" else None
+        self.heap = None
+        if exchange == "peer":
+            # mapping a peer's memory can fail on boxes without P2P between some GPU pair; the ranks agree on the
+            # outcome (the handle exchange inside PeerHeap is collective, so every rank gets this far) and fall back to
+            # the NCCL all-gather together rather than one of them raising while the others wait
+            heap, ok = None, 1
+            try:
+                heap = PeerHeap(group)
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, e
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.heap = heap
+            else:
+                import warnings
+                warnings.warn("peer-memory exchange unavailable ({}); using the NCCL all-gather".format(
+                    why if not ok else "another rank could not map its peers"))
+                self.exchange = "nccl"
         # peer exchange of a GCN stack: "off" = transform+stores, barrier, sparse kernel, in order;
         # "kernel" = the next layer's fused transform+stores of row block b runs on a high-priority side
         # stream while the sparse kernel works on block b+1; "ce" = same, but the rows travel by copy engine
