@@ -48,7 +48,9 @@ def parse():
     ap.add_argument("--cpu-scale", default="c5-hundredth", choices=sorted(SCALES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the bf16-operand variant of the step")
-    ap.add_argument("--catalog-users", type=int, default=2048)
+    ap.add_argument("--catalog-users", type=int, default=4736,
+                    help="users per rank scored against the whole catalog (4736 = 148 SMs x 2 CTAs x 16 users: one full wave of "
+                         "the fp32 kernel; the bf16 kernel gets 4x as many)")
     return ap.parse_args()
 
 
@@ -324,7 +326,7 @@ def run_b200(args):
     cat_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users), 1, 1)
     pairs_per_s = world * cu * n_items / (cat_ms * 1e-3)
     # bf16 tensor-core scorer (tcgen05): more users per launch so the grid fills the chip
-    cu_tc = min(args.catalog_users * 8, u_hi - u_lo)
+    cu_tc = min(args.catalog_users * 4, u_hi - u_lo)
     users_tc = torch.arange(u_lo, u_lo + cu_tc, device=dev)
     tc_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users_tc, precision="bf16"), 1, 1)
     pairs_tc = world * cu_tc * n_items / (tc_ms * 1e-3)
