@@ -95,7 +95,8 @@ _SIGS = {
     "cbrs_scale_rows_inv_degree": (c_int, [P, c_int64, P, c_int64, c_int32, P, c_int64, P]),
     "cbrs_axpby2d": (c_int, [P, c_int64, c_float, P, c_int64, c_float, c_int64, c_int32, P, c_int64, P]),
     "cbrs_bce": (c_int, [P, P, c_int64, P, P, P, P]),
-    "cbrs_sum_squares": (c_int, [P, c_int64, c_float, P, c_int, P]),
+    "cbrs_sum_squares_workspace_bytes": (c_size_t, []),
+    "cbrs_sum_squares": (c_int, [P, c_int64, c_float, P, c_int, P, c_size_t, P]),
     "cbrs_adam_step": (c_int, [P, P, P, P, c_int64, c_float, P, c_float, c_float, c_float, c_float, P]),
     "cbrs_attn_fuse": (c_int, [P, c_int64, P, c_int64, P, P, c_int64, c_int32, P, c_int64, P]),
     "cbrs_attn_fuse_grad": (c_int, [P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int32, P, P, P, P, P]),

@@ -261,18 +261,30 @@ __global__ void __launch_bounds__(1024) bce_kernel(const float *__restrict__ p, 
     }
 }
 
-__global__ void __launch_bounds__(1024) sum_squares_kernel(const float *__restrict__ w, int64_t n, float scale,
-                                                          float *__restrict__ out, int accumulate) {
+// two levels, both in a fixed order => reproducible: each CTA reduces a contiguous slice (strided + tree), one CTA
+// then adds the per-CTA partials in ascending order
+constexpr int kSsqBlocks = 592;  // 148 SMs x 4
+__global__ void __launch_bounds__(1024) sum_squares_partial_kernel(const float *__restrict__ w, int64_t n, int64_t per_block,
+                                                                  float *__restrict__ partial) {
     __shared__ float sh[1024];
+    const int64_t b = (int64_t)blockIdx.x * per_block;
+    const int64_t e = b + per_block < n ? b + per_block : n;
     float acc = 0.f;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) acc = fmaf(w[i], w[i], acc);
+    for (int64_t i = b + threadIdx.x; i < e; i += 1024) acc = fmaf(w[i], w[i], acc);
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int s = 512; s; s >>= 1) {
         if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *out = (accumulate ? *out : 0.f) + scale * sh[0];
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void sum_squares_finish_kernel(const float *__restrict__ partial, int blocks, float scale, float *__restrict__ out,
+                                          int accumulate) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float acc = 0.f;
+    for (int b = 0; b < blocks; ++b) acc += partial[b];
+    *out = (accumulate ? *out : 0.f) + scale * acc;
 }
 
 // Keras Adam (optimizer_v2): lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m, v moving averages;
@@ -502,10 +514,21 @@ extern "C" int cbrs_bce(const float *p, const float *y, int64_t n, float *loss_o
     return CBRS_OK;
 }
 
-extern "C" int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int accumulate, void *stream) {
+extern "C" size_t cbrs_sum_squares_workspace_bytes(void) { return kSsqBlocks * sizeof(float) + 256; }
+
+extern "C" int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int accumulate, void *workspace,
+                                size_t workspace_bytes, void *stream) {
     CBRS_REQUIRE(w && out && n > 0, CBRS_E_INVALID, "sum_squares: bad argument");
-    sum_squares_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w, n, scale, out, accumulate);
-    CBRS_CHECK_LAUNCH("sum_squares");
+    CBRS_REQUIRE(workspace && workspace_bytes >= cbrs_sum_squares_workspace_bytes(), CBRS_E_WORKSPACE,
+                 "sum_squares: workspace too small");
+    int64_t per_block = cdiv(n, kSsqBlocks);
+    per_block = cdiv(per_block, 1024) * 1024;
+    const int blocks = (int)cdiv(n, per_block);
+    cudaStream_t s = (cudaStream_t)stream;
+    sum_squares_partial_kernel<<<blocks, 1024, 0, s>>>(w, n, per_block, (float *)workspace);
+    CBRS_CHECK_LAUNCH("sum_squares_partial");
+    sum_squares_finish_kernel<<<1, 32, 0, s>>>((const float *)workspace, blocks, scale, out, accumulate);
+    CBRS_CHECK_LAUNCH("sum_squares_finish");
     return CBRS_OK;
 }
 

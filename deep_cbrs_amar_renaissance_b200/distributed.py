@@ -197,7 +197,7 @@ class RowPartition:
     After the last layer only the node types in `final_types` (default: everything but users)
     are exchanged, because scoring is sharded by user."""
 
-    def __init__(self, n_rows_by_type, group=None, final_types=None, col_splits=1, exchange=None, pipeline=None,
+    def __init__(self, n_rows_by_type, group=None, final_types=None, exchange=None, pipeline=None,
                  row_blocks=None):
         self.group = group
         exchange = exchange or os.environ.get("CBRS_EXCHANGE") or ("peer" if torch.cuda.is_available() else "nccl")
@@ -238,8 +238,6 @@ class RowPartition:
         self._side = None
         self._sym = {}
         self.n_rows_by_type = list(n_rows_by_type)
-        self.col_splits = int(os.environ.get("CBRS_COL_SPLITS", col_splits))  # GCN: the all-gather of column block s+1 overlaps the SpMM of block s
-        self._comm = None
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.ranges = block_ranges(n_rows_by_type, self.world)
@@ -304,40 +302,6 @@ class RowPartition:
             ops.PROFILE.append(("exchange", e0, e1, x.numel() * 4))
             return x
         return exchange_rows(x, ranges, self.group)
-
-    def _pipelined_ok(self, layer):
-        return self.col_splits > 1 and layer.channels % (4 * self.col_splits) == 0
-
-    def _gcn_pipelined(self, layer, l, x_full, out, graph, relu):
-        """GCN layer with the exchange hidden behind the sparse kernel: Z = X W is produced and
-        all-gathered in `col_splits` column blocks on a side stream, and the SpMM of block s runs
-        while block s+1 is still on the wire.  Columns are independent, so the bits are the same
-        as the unsplit layer's."""
-        from . import ops
-        n, dev = x_full.shape[0], x_full.device
-        S, hs = self.col_splits, layer.channels // self.col_splits
-        if self._comm is None:
-            self._comm = torch.cuda.Stream(device=dev)
-        main = torch.cuda.current_stream(dev)
-        zs = [self._buf(("zs", l, s), n, hs, dev) for s in range(S)]
-        ready = []
-        for s in range(S):
-            w_s = layer.kernel[:, s * hs:(s + 1) * hs].contiguous()
-            for a, b in self.mine:
-                ops.dense(x_full[a:b], w_s, out=zs[s][a:b])
-            produced = torch.cuda.Event()
-            produced.record(main)
-            with torch.cuda.stream(self._comm):
-                self._comm.wait_event(produced)
-                self._exchange(zs[s])
-                done = torch.cuda.Event()
-                done.record(self._comm)
-            ready.append(done)
-        for s in range(S):
-            main.wait_event(ready[s])
-            bias = layer.bias[s * hs:(s + 1) * hs] if layer.bias is not None else None
-            for sl in self.csr_slices("norm", graph):
-                ops.spmm(sl, zs[s], out[sl.row_offset:sl.row_offset + sl.n_rows, s * hs:(s + 1) * hs], bias=bias, relu=relu)
 
     # ------------------------------------------------------------------ peer exchange
     def _symbuf(self, key, n, w, dtype=torch.float32):
@@ -546,9 +510,7 @@ class RowPartition:
             else:
                 out = self._buf(("h", l), n, widths[l + 1], dev)  # own rows valid
             relu = getattr(layer, "activation", None) == "relu"
-            if isinstance(layer, GCNConv) and self._pipelined_ok(layer):
-                self._gcn_pipelined(layer, l, x_full, out, graph, relu)
-            elif isinstance(layer, (GCNConv, RGCNConv)):
+            if isinstance(layer, (GCNConv, RGCNConv)):
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
                 zdt = torch.bfloat16 if getattr(layer, "feature_dtype", "fp32") == "bf16" else torch.float32
                 z = self._buf(("z", l), len(kernels) * n, layer.channels, dev, zdt)

@@ -501,9 +501,10 @@ def bce(p, y, want_grad=True):
 
 def sum_squares(w, scale, out, accumulate=True):
     lib = L.load()
+    ws = _ws(lib.cbrs_sum_squares_workspace_bytes(), w.device)
     L.check(lib.cbrs_sum_squares(_ptr(w, torch.float32), w.numel(), float(scale), _ptr(out, torch.float32),
-                                 1 if accumulate else 0, _stream()), "cbrs_sum_squares")
-    _count(1)
+                                 1 if accumulate else 0, _ptr(ws), ws.numel(), _stream()), "cbrs_sum_squares")
+    _count(2)
     return out
 
 

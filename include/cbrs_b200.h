@@ -347,8 +347,10 @@ int cbrs_axpby2d(const float *a, int64_t lda, float ca, const float *b, int64_t 
  * dLoss/dp_i (0 where the clip is active); *correct_out = #((p > .5) == (y > .5)).  dp/correct may be NULL */
 int cbrs_bce(const float *p, const float *y, int64_t n, float *loss_out, float *dp_out, float *correct_out,
              void *stream);
-/* *out = (accumulate ? *out : 0) + scale * sum w^2 */
-int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int accumulate, void *stream);
+/* *out = (accumulate ? *out : 0) + scale * sum w^2; two-level fixed-order reduction (reproducible) */
+size_t cbrs_sum_squares_workspace_bytes(void);
+int cbrs_sum_squares(const float *w, int64_t n, float scale, float *out, int accumulate, void *workspace,
+                     size_t workspace_bytes, void *stream);
 /* Keras Adam: g' = g + 2*l2*w; m,v updated in place; w -= lr_t * m / (sqrt(v) + eps).  lr_t = lr*sqrt(1-b2^t)/(1-b1^t)
  * is computed by the host; lr_t_dev (device float, may be NULL) overrides the immediate so that a captured
  * CUDA graph of the whole step can be replayed with the rate of step t                                        */

@@ -170,4 +170,12 @@ def test_sum_squares():
     w = np.random.RandomState(7).standard_normal(70001).astype(np.float32)
     out = torch.full((1,), 2.0, device="cuda")
     ops.sum_squares(_cu(w), 1e-2, out, accumulate=True)
-    assert abs(float(out.item()) - (2.0 + 1e-2 * (w.astype(np.float64) ** 2).sum())) <= 1e-4
+    want = 2.0 + 1e-2 * (w.astype(np.float64) ** 2).sum()
+    assert abs(float(out.item()) - want) <= 1e-5 * want
+    out2 = torch.full((1,), 2.0, device="cuda")
+    ops.sum_squares(_cu(w), 1e-2, out2, accumulate=True)
+    assert torch.equal(out, out2)  # fixed two-level order: reproducible
+    big = np.random.RandomState(8).standard_normal(3_000_001).astype(np.float32)  # several CTAs
+    o3 = torch.zeros(1, device="cuda")
+    ops.sum_squares(_cu(big), 1.0, o3, accumulate=False)
+    assert abs(float(o3.item()) - (big.astype(np.float64) ** 2).sum()) <= 1e-5 * 3e6
