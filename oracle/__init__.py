@@ -29,7 +29,12 @@ PARITY PINNING STATUS
     bit-for-bit against the reference's own numpy/scipy code run unmodified
     under oracle/tf_stub (fixtures in tests/golden/, generator
     tests/golden/make_golden.py).
-  * Spektral layer arithmetic, Keras Dense, top-k: PARITY UNPINNED - the
+  * reductions (reduction.py), attention fusion (fusion.py), the DGCF operator recipe and layer
+    (dgcf_conv.py), pair-list top-k (metrics.py): PINNED - the reference's own modules run
+    unmodified over numpy-backed tf/keras/spektral stand-ins (oracle/tf_np_stub, generator
+    tests/golden/make_golden_layers.py, vectors tests/golden/layers/).
+  * Spektral layer arithmetic (GCNConv, GraphSageConv, GATConv, gcn_filter), Keras Dense, the
+    training step: PARITY UNPINNED - the
     reference ships no tests, golden vectors or fixtures and TF/Spektral cannot
     run here.  Pinned only by known-answer parameter counts (doc.pdf Table 17)
     and algebraic identities (tests/test_oracle_identities.py).
