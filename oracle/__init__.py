@@ -33,6 +33,9 @@ PARITY PINNING STATUS
     (dgcf_conv.py), pair-list top-k (metrics.py): PINNED - the reference's own modules run
     unmodified over numpy-backed tf/keras/spektral stand-ins (oracle/tf_np_stub, generator
     tests/golden/make_golden_layers.py, vectors tests/golden/layers/).
+  * model wiring end to end (SequentialGNN loop, family builders, lookups, BasicRS, HybridCBRS in all
+    modes, dense builders): PINNED - src/models/*.py run unmodified over the same stand-ins
+    (tests/golden/make_golden_models.py, tests/golden/models/); leaves are stand-ins.
   * Spektral layer arithmetic (GCNConv, GraphSageConv, GATConv, gcn_filter), Keras Dense, the
     training step: PARITY UNPINNED - the
     reference ships no tests, golden vectors or fixtures and TF/Spektral cannot

@@ -1,1 +1,2 @@
-from tensorflow.keras import layers  # noqa: F401  (`from keras import layers` in src/layers/dgcf_conv.py)
+# `from keras import models, layers, regularizers` (src/models/gnn.py:4, src/layers/dgcf_conv.py:1)
+from tensorflow.keras import layers, models, regularizers  # noqa: F401

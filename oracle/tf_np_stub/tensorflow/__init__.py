@@ -1,7 +1,8 @@
 """numpy float32 stand-in for the handful of TensorFlow ops the reference's own layer code calls (see ../README.md)."""
 import numpy as np
 
-from . import keras, math  # noqa: F401
+from . import keras, math, nn, sparse  # noqa: F401
+from .sparse import SparseTensor  # noqa: F401
 
 float32 = np.float32
 
@@ -51,3 +52,14 @@ def reduce_sum(x, axis=None):
 
 def argmin(values):
     return int(np.argmin(np.asarray(values, dtype=np.float64)))   # first minimum, like tf.argmin
+
+
+def cast(x, dtype):
+    if isinstance(x, SparseTensor):
+        x.values = x.values.astype(np.float32)
+        return x
+    return np.asarray(x).astype(dtype)
+
+
+def convert_to_tensor(x, dtype=None):
+    return np.asarray(x, dtype=dtype)

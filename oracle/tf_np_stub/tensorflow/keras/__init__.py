@@ -1,1 +1,1 @@
-from . import layers, utils  # noqa: F401
+from . import layers, models, regularizers, utils  # noqa: F401

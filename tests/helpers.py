@@ -60,10 +60,10 @@ def assert_topk_equivalent(ids, vals, oracle_scores, k, tol=2e-6):
     return float(clear.mean()) if clear.size else 1.0
 
 
-def export_weights(model):
-    """Model weights as the numpy structures the oracle takes (Keras layouts: kernel [in,out])."""
-    named = [(n, w.detach().cpu().numpy()) for n, w in model.named_weights()]
-    w = dict(named)
+def weights_struct(w, proj_first=None):
+    """{product weight path: array} -> the numpy structures the oracle takes (Keras layouts: kernel [in,out]).
+    proj_first: {fusion layer name: bool} for attention fusions that project."""
+    w = dict(w)
 
     def stack(prefix):
         ks = sorted({int(n[len(prefix):].split("/")[0]) for n in w if n.startswith(prefix)})
@@ -81,9 +81,7 @@ def export_weights(model):
             lw["attn_neigh"] = lw.pop("attn_kernel_neigh").reshape(-1)
         out["layers"].append(lw)
         k += 1
-    n_layers = len(model.gnn.gnn_layers.seq_layers)
-    out["layers"] += [{} for _ in range(n_layers - len(out["layers"]))]  # weight-free LightGCN layers
-    if any(n.startswith("rs/unet/") for n in w) or hasattr(model.rs, "unet"):
+    if any(n.startswith("rs/unet/") or n.startswith("rs/inet/") for n in w) or not any(n.startswith("rs/dense1a/") for n in w):
         out.update(unet=stack("rs/unet/layers."), inet=stack("rs/inet/layers."), clf=stack("rs/clf/layers."))
     else:
         for name in ("dense1a", "dense1b", "dense2a", "dense2b", "dense3a", "dense3b", "clf"):
@@ -92,7 +90,17 @@ def export_weights(model):
             out["residual"] = stack("rs/residual/layers.")
         for name in ("fuse1a", "fuse1b", "fuse2"):
             if "rs/%s/att_weight" % name in w:
-                layer = getattr(model.rs, name)
                 out[name] = dict(att_weight=w["rs/%s/att_weight" % name], proj_weight=w.get("rs/%s/proj_weight" % name),
-                                 proj_first=layer.proj_first)
+                                 proj_first=(proj_first or {}).get(name))
+    return out
+
+
+def export_weights(model):
+    """Model weights as the numpy structures the oracle takes."""
+    named = {n: w.detach().cpu().numpy() for n, w in model.named_weights()}
+    pf = {name: getattr(model.rs, name).proj_first for name in ("fuse1a", "fuse1b", "fuse2")
+          if hasattr(model.rs, name) and getattr(getattr(model.rs, name), "proj_first", None) is not None}
+    out = weights_struct(named, pf)
+    n_layers = len(model.gnn.gnn_layers.seq_layers)
+    out["layers"] += [{} for _ in range(n_layers - len(out["layers"]))]  # weight-free LightGCN layers
     return out
