@@ -8,7 +8,7 @@ import numpy as np
 import pandas as pd
 
 from .datasets import UserItemGraph, UserItemGraphEmbeddings
-from .preprocess import build_adjacency_matrix
+from .preprocess import build_adjacency_matrix, get_user_properties
 
 
 def _read(path, sep):
@@ -105,12 +105,13 @@ def load_user_item_graph(train_ratings_filepath, test_ratings_filepath, props_tr
                          sep='\t', type_adjacency='unary', sparse_adjacency=True,
                          symmetric_adjacency=True, user_properties=False, shuffle=True,
                          train_batch_size=1024, test_batch_size=2048):
-    if user_properties and type_adjacency != 'unary-uip':
-        raise NotImplementedError("user-properties graphs feed only the Two-Way variant (out of scope)")
     (train, test), (users, items), adj = load_train_test_ratings(
         train_ratings_filepath, test_ratings_filepath, props_triples_filepath, sep=sep,
         return_adjacency=True, type_adjacency=type_adjacency, sparse_adjacency=sparse_adjacency,
         symmetric_adjacency=symmetric_adjacency)
+    if user_properties and type_adjacency != 'unary-uip':  # loaders.py:319-322 / :427-430
+        ui_adj, ip_adj = adj
+        adj = (ui_adj, ip_adj, get_user_properties(ui_adj, ip_adj, len(users), len(items)))
     return (UserItemGraph(train, users, items, adj, batch_size=train_batch_size, shuffle=shuffle),
             UserItemGraph(test, users, items, adj, batch_size=test_batch_size, shuffle=False))
 
@@ -121,12 +122,13 @@ def load_user_item_graph_bert_embeddings(train_ratings_filepath, test_ratings_fi
                                          sparse_adjacency=True, symmetric_adjacency=True, shuffle=True,
                                          train_batch_size=1024, test_batch_size=2048,
                                          user_properties=None):
-    if user_properties and type_adjacency != 'unary-uip':
-        raise NotImplementedError("user-properties graphs feed only the Two-Way variant (out of scope)")
     (train, test), (users, items), adj = load_train_test_ratings(
         train_ratings_filepath, test_ratings_filepath, props_triples_filepath, sep=sep,
         return_adjacency=True, type_adjacency=type_adjacency, sparse_adjacency=sparse_adjacency,
         symmetric_adjacency=symmetric_adjacency)
+    if user_properties and type_adjacency != 'unary-uip':  # loaders.py:319-322 / :427-430
+        ui_adj, ip_adj = adj
+        adj = (ui_adj, ip_adj, get_user_properties(ui_adj, ip_adj, len(users), len(items)))
     bert = load_bert_user_item_embeddings(bert_user_filepath, bert_item_filepath, users, items)
     return (UserItemGraphEmbeddings(train, users, items, adj, bert, batch_size=train_batch_size, shuffle=shuffle),
             UserItemGraphEmbeddings(test, users, items, adj, bert, batch_size=test_batch_size, shuffle=False))

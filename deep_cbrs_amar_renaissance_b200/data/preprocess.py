@@ -1,14 +1,34 @@
 """Adjacency construction on the host (mirror of /root/reference/src/data/preprocess.py:44-170).
 
 Only the adjacency types on the hot path are built: 'unary' and 'unary-uip'
-(SURVEY.md section 2 row 1); 'binary' is kept because it is one line; 'unary-kg' and
-get_user_properties belong to the Two-Step / Two-Way variants and are out of
-scope (they raise).
+(SURVEY.md section 2 row 1); 'binary' is kept because it is one line; 'unary-kg' (two graphs)
+feeds the Two-Step variants, get_user_properties (the third graph) the Two-Way variants (scope row (f)-4).
 """
 import numpy as np
 from scipy import sparse
 
 from ..utilities.math import symmetrize_matrix
+
+
+def get_user_properties(ui_adj, ip_adj, n_users, n_items):
+    """User-property adjacency over [U+P] nodes: user u and property p are linked when some item is linked to both
+    (preprocess.py:9-41).  The reference squares the stacked [U+I+P] adjacency, sets every stored value to one,
+    DENSIFIES the square and copies two blocks into a dense [U+P, U+P] array - the reason the Two-Way variants run out
+    of memory on real graphs.  Here everything stays sparse; the result is the same COO matrix: float64 ones, entries
+    in row-major order (what sparse.coo_matrix(dense) yields)."""
+    n_props = ip_adj.shape[0] - n_items
+    n = n_users + n_items + n_props
+    ui, ip = ui_adj.tocoo(), ip_adj.tocoo()
+    uip = sparse.coo_matrix((np.concatenate([ui.data, ip.data]),
+                             (np.concatenate([ui.row, ip.row + n_users]), np.concatenate([ui.col, ip.col + n_users]))),
+                            shape=(n, n)).tocsr()
+    two_hop = uip.dot(uip).tocsr()
+    two_hop.eliminate_zeros()  # a stored zero is a zero in the reference's dense copy
+    two_hop.data = np.ones(len(two_hop.data))
+    up = sparse.bmat([[None, two_hop[:n_users, n_users + n_items:]],
+                      [two_hop[n_users + n_items:, :n_users], None]], format='csr', dtype=np.float64)
+    up.sort_indices()
+    return up.tocoo()
 
 
 def _coo(data, rows, cols, n, symmetric, as_sparse):
@@ -44,5 +64,10 @@ def build_adjacency_matrix(bi_ratings, users, items, props_triples=None, props=N
                     np.concatenate([liked[:, 1], props_triples[:, 1] + shift]),
                     n_ui + len(props), symmetric_adjacency, sparse_adjacency)
     if type_adjacency == 'unary-kg':
-        raise NotImplementedError("'unary-kg' feeds only the Two-Step/Two-Way variants (out of scope, DESIGN.md)")
+        # two graphs (preprocess.py:113-145): user-item over [U+I] and item-property over [I+P] (items first)
+        if props is None or props_triples is None:
+            raise ValueError("KG adjacency matrix requires properties info")
+        return (_coo(liked[:, 2], liked[:, 0], liked[:, 1], n_ui, symmetric_adjacency, sparse_adjacency),
+                _coo(props_triples[:, 2], props_triples[:, 0], props_triples[:, 1], len(items) + len(props),
+                     symmetric_adjacency, sparse_adjacency))
     raise ValueError("Unknown adjacency matrix type named {}".format(type_adjacency))

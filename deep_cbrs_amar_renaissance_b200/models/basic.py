@@ -13,6 +13,8 @@ from .. import ops
 from ..keras_like import Model, default_device
 from .dense import build_dense_classifier, build_dense_network
 from .gnn import GAT, GCN, DGCF, RGCN, GraphSage, LightGCN
+from .tsgnn import TwoStepDGCF, TwoStepGAT, TwoStepGCN, TwoStepGraphSage, TwoStepLightGCN
+from .twgnn import TwoWayDGCF, TwoWayGAT, TwoWayGCN, TwoWayGraphSage, TwoWayLightGCN
 
 
 def _ids(x):
@@ -57,8 +59,8 @@ class BasicGNN(Model, abc.ABC):
 
     def build_weights(self):
         """Create all weights (what the reference's first `model(batch)` does, experiment.py:166)."""
-        self.gnn.gnn_layers.build_layers()
-        self.rs.build_for(self.gnn.gnn_layers.out_dim)
+        self.gnn.build_layers()
+        self.rs.build_for(self.gnn.out_dim)
         return self
 
     def propagate(self):
@@ -111,13 +113,17 @@ def BasicGNNFactory(name, Parent, GNN):
     return type(name, (Parent,), {"gnn_class": GNN, "__init__": __init__})
 
 
-BASIC_GNNS = [(BasicGNN, [GCN, GAT, GraphSage, LightGCN, DGCF, RGCN], None)]
+BASIC_GNNS = [(BasicGNN, [GCN, GAT, GraphSage, LightGCN, DGCF, RGCN], None),
+              (BasicTSGNN, [TwoStepGCN, TwoStepGraphSage, TwoStepGAT, TwoStepLightGCN, TwoStepDGCF],
+               lambda name: 'BasicTS' + name[7:]),
+              (BasicTWGNN, [TwoWayGCN, TwoWayGraphSage, TwoWayGAT, TwoWayLightGCN, TwoWayDGCF],
+               lambda name: 'BasicTW' + name[6:])]
 
 
 def generate_basics():
     for parent, gnns, name_getter in BASIC_GNNS:
         for gnn in gnns:
-            name = 'Basic' + gnn.__name__
+            name = name_getter(gnn.__name__) if name_getter is not None else 'Basic' + gnn.__name__
             globals()[name] = BasicGNNFactory(name, parent, gnn)
 
 

@@ -28,7 +28,11 @@ class SequentialGNN(Model):
         self.embedding_dim = int(embedding_dim)
         self.embeddings = self.add_weight('embeddings', (adj_matrix.shape[0], embedding_dim), 'glorot_uniform',
                                           regularizer)
+        self._finish_init(adj_matrix, seq_layers, final_node)
+
+    def _finish_init(self, adj_matrix, seq_layers, final_node):
         self.adj_matrix = convert_to_tensor(adj_matrix, device=default_device())
+        self.n_nodes = int(adj_matrix.shape[0])
         self.dropout = None
         self.final_node = final_node
         self.reduce = ReductionLayer(final_node)
@@ -59,7 +63,7 @@ class SequentialGNN(Model):
         f = self.embedding_dim
         for layer in self.seq_layers:
             if not layer.built:
-                layer.build([(self.embeddings.shape[0], f), None])
+                layer.build([(self.n_nodes, f), None])
                 layer.built = True
             f = getattr(layer, "channels", f)
 
@@ -74,7 +78,10 @@ class SequentialGNN(Model):
     def call(self, inputs, **kwargs):
         if self.partition is not None:
             return self.partition.propagate(self)
-        x = self.embeddings
+        return self._run(self.embeddings)
+
+    def _run(self, x):
+        """the layer loop + reduction of gnn.py:74-84 on the initial node features x"""
         n = x.shape[0]
         if self.final_node == 'concatenation':
             widths = self._widths()
@@ -99,6 +106,63 @@ class SequentialGNN(Model):
         return self.reduce(hs)
 
 
+class HalfInputSequentialGNN(SequentialGNN):
+    """gnn.py:87-147: the first `n_random_embeddings` node rows are learnable embeddings, the remaining rows come in
+    as the call's input (the item rows produced by the first step of a Two-Step model)."""
+
+    def __init__(self, adj_matrix, seq_layers, n_random_embeddings, final_node='concatenation', dropout=None,
+                 embedding_dim=8, regularizer=None, cache_neighbours=False):
+        Model.__init__(self, "half_input_sequential_gnn")
+        if cache_neighbours:
+            raise NotImplementedError("Multi-hops neighbours caching is not yet completely supported!")
+        if dropout:
+            raise NotImplementedError("layer dropout is None in every reference grid (forward path only)")
+        self.cache_neighbours = cache_neighbours
+        self.embedding_dim = int(embedding_dim)
+        self.embeddings = self.add_weight('embeddings', (n_random_embeddings, embedding_dim), 'glorot_uniform', regularizer)
+        self._finish_init(adj_matrix, seq_layers, final_node)
+
+    def call(self, inputs, **kwargs):
+        if inputs.shape[1] != self.embedding_dim:
+            raise ValueError("input rows are {} wide, the embeddings {}".format(inputs.shape[1], self.embedding_dim))
+        x = torch.cat([self.embeddings, inputs], dim=0)
+        if x.shape[0] != self.n_nodes:
+            raise ValueError("{} embedding rows + {} input rows != {} graph nodes".format(
+                self.embeddings.shape[0], inputs.shape[0], self.n_nodes))
+        return self._run(x)
+
+
+class FullInputSequentialGNN(SequentialGNN):
+    """gnn.py:150-207: no embeddings of its own; every node row comes in as the call's input (the user rows and item
+    rows the two ways of a Two-Way model produce).  `embedding_dim` is the width of that input: the reference learns
+    it at the first call, here the owner states it so that the weights can be created before any kernel runs."""
+
+    def __init__(self, adj_matrix, seq_layers, final_node='concatenation', dropout=None, cache_neighbours=False,
+                 embedding_dim=None):
+        Model.__init__(self, "full_input_sequential_gnn")
+        if cache_neighbours:
+            raise NotImplementedError("Multi-hops neighbours caching is not yet completely supported!")
+        if dropout:
+            raise NotImplementedError("layer dropout is None in every reference grid (forward path only)")
+        self.cache_neighbours = cache_neighbours
+        self.embedding_dim = int(embedding_dim) if embedding_dim is not None else None
+        self.embeddings = None
+        self._finish_init(adj_matrix, seq_layers, final_node)
+
+    def build_layers(self):
+        if self.embedding_dim is None:
+            raise ValueError("the input width is unknown before the first call; pass embedding_dim")
+        super().build_layers()
+
+    def call(self, inputs, **kwargs):
+        if self.embedding_dim is None:
+            self.embedding_dim = int(inputs.shape[1])
+        if inputs.shape != (self.n_nodes, self.embedding_dim):
+            raise ValueError("input is {}, the graph has {} nodes of width {}".format(
+                tuple(inputs.shape), self.n_nodes, self.embedding_dim))
+        return self._run(inputs if inputs.is_contiguous() else inputs.contiguous())
+
+
 class GNN(Model, abc.ABC):
     def __init__(self, adj_matrix, n_hops, embedding_dim=8, final_node="concatenation", dropout=None,
                  l2_regularizer=None, cache_neighbours=False, **kwargs):
@@ -112,6 +176,13 @@ class GNN(Model, abc.ABC):
     @abc.abstractmethod
     def build_gnn_layer(self, i, **kwargs):
         pass
+
+    def build_layers(self):
+        self.gnn_layers.build_layers()
+
+    @property
+    def out_dim(self):
+        return self.gnn_layers.out_dim
 
     def call(self, inputs, **kwargs):
         return self.gnn_layers(None)

@@ -18,6 +18,8 @@ from .. import ops
 from ..layers.dense import materialize
 from .dense import build_dense_classifier, build_dense_network, build_residual_dense_network
 from .gnn import GAT, GCN, DGCF, RGCN, GraphSage, LightGCN
+from .tsgnn import TwoStepDGCF, TwoStepGAT, TwoStepGCN, TwoStepGraphSage, TwoStepLightGCN
+from .twgnn import TwoWayDGCF, TwoWayGAT, TwoWayGCN, TwoWayGraphSage, TwoWayLightGCN
 
 
 def _rows(x):
@@ -116,8 +118,8 @@ class HybridBertGNN(Model, abc.ABC):
         self.built = True
 
     def build_weights(self, content_dim=768):
-        self.gnn.gnn_layers.build_layers()
-        self.rs.build_for(self.gnn.gnn_layers.out_dim, content_dim)
+        self.gnn.build_layers()
+        self.rs.build_for(self.gnn.out_dim, content_dim)
         return self
 
     def set_content_table(self, table):
@@ -171,13 +173,17 @@ class HybridBertTWGNN(HybridBertGNN):
     pass
 
 
-HYBRID_GNNS = [(HybridBertGNN, [GCN, GAT, GraphSage, LightGCN, DGCF, RGCN], None)]
+HYBRID_GNNS = [(HybridBertGNN, [GCN, GAT, GraphSage, LightGCN, DGCF, RGCN], None),
+               (HybridBertTSGNN, [TwoStepGCN, TwoStepGraphSage, TwoStepGAT, TwoStepLightGCN, TwoStepDGCF],
+                lambda name: 'HybridBertTS' + name[7:]),
+               (HybridBertTWGNN, [TwoWayGCN, TwoWayGraphSage, TwoWayGAT, TwoWayLightGCN, TwoWayDGCF],
+                lambda name: 'HybridBertTW' + name[6:])]
 
 
 def generate_hybrids():
     for parent, gnns, name_getter in HYBRID_GNNS:
         for gnn in gnns:
-            name = 'HybridBert' + gnn.__name__
+            name = name_getter(gnn.__name__) if name_getter is not None else 'HybridBert' + gnn.__name__
             globals()[name] = BasicGNNFactory(name, parent, gnn)
 
 

@@ -86,6 +86,37 @@ def build_adjacency(train, n_users, n_items, props_triples=None, n_props=0,
     return sparse.coo_matrix((data, (rows, cols)), shape=(n, n), dtype=np.float32)
 
 
+def build_kg_adjacencies(train, n_users, n_items, props_triples, n_props, symmetric=True):
+    """'unary-kg' (preprocess.py:113-145): the user-item graph over [U+I] and the item-property graph over [I+P]
+    (items first: triples carry (item index, n_items + property index)), each symmetrised separately."""
+    ui = build_adjacency(train, n_users, n_items, symmetric=symmetric)
+    rows, cols = props_triples[:, 0].astype(np.int32), props_triples[:, 1].astype(np.int32)
+    data = props_triples[:, 2].astype(np.float32)
+    if symmetric:
+        rows, cols = np.concatenate([rows, cols]), np.concatenate([cols, rows])
+        data = np.concatenate([data, data])
+    n = n_items + n_props
+    return ui, sparse.coo_matrix((data, (rows, cols)), shape=(n, n), dtype=np.float32)
+
+
+def user_properties(ui_adj, ip_adj, n_users, n_items):
+    """get_user_properties (preprocess.py:9-41), restated with its dense detour (small graphs only): stack the two
+    graphs over [U+I+P], square, set every stored value to one, densify, copy the property x user and the
+    user x property blocks into a dense [U+P]^2 array, and return its COO form (float64, row-major order)."""
+    n_props = ip_adj.shape[0] - n_items
+    n = n_users + n_items + n_props
+    stacked = sparse.coo_matrix((np.concatenate([ui_adj.data, ip_adj.data]),
+                                 (np.concatenate([ui_adj.row, ip_adj.row + n_users]),
+                                  np.concatenate([ui_adj.col, ip_adj.col + n_users]))), shape=(n, n))
+    sq = stacked.dot(stacked)
+    sq.data = np.ones(len(sq.data))
+    sq = np.asarray(sq.todense())
+    up = np.zeros((n_users + n_props, n_users + n_props))
+    up[n_users:, :n_users] = sq[n_users + n_items:, :n_users]
+    up[:n_users, n_users:] = sq[:n_users, n_users + n_items:]
+    return sparse.coo_matrix(up)
+
+
 # --------------------------------------------------------------------------- G2
 def inv_sqrt_degree(deg):
     """d = deg^(-1/2) as float32, inf -> 0.

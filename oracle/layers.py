@@ -247,6 +247,30 @@ def propagate(kind, emb, graph, layer_weights, final_node="concatenation", aggre
     return reduce_layers(hs, final_node)
 
 
+# ------------------------------------------------------------------------- (f)-4 Two-Step / Two-Way
+def two_step(kind, step_one, step_two, n_items, item_node="mean", final_node="concatenation", aggregate="mean"):
+    """TwoStepGNN.call, models/tsgnn.py:92-94 with HalfInputSequentialGNN.call, models/gnn.py:136-147:
+    x = SequentialGNN_kg(None) reduced by item_node; second input = concat([user embeddings, x[:n_items]], axis 0);
+    the second loop runs over the user-item graph and is reduced by final_node.
+    step_one / step_two = dict(embeddings=, graph=, layers=[...])."""
+    x = propagate(kind, step_one["embeddings"], step_one["graph"], step_one["layers"], item_node, aggregate)
+    if kind in ("lightgcn", "dgcf") and item_node != "mean":
+        raise ValueError("propagate() forces 'mean' for weight-free families; item_node must be 'mean' there")
+    x2 = np.concatenate([np.asarray(step_two["embeddings"], F32), x[:n_items]], axis=0)
+    return propagate(kind, x2, step_two["graph"], step_two["layers"], final_node, aggregate)
+
+
+def two_way(kind, way_one, way_two, step_two, n_users, n_items, user_item_node="mean", final_node="concatenation",
+            aggregate="mean"):
+    """TwoWayGNN.call, models/twgnn.py:93-100 with FullInputSequentialGNN.call, models/gnn.py:198-207:
+    users = SequentialGNN_up(None)[:n_users]; items = SequentialGNN_ip(None)[:n_items]; the stacked rows are the whole
+    input of the third loop over the user-item graph (no embeddings of its own)."""
+    users = propagate(kind, way_one["embeddings"], way_one["graph"], way_one["layers"], user_item_node, aggregate)
+    items = propagate(kind, way_two["embeddings"], way_two["graph"], way_two["layers"], user_item_node, aggregate)
+    x = np.concatenate([users[:n_users], items[:n_items]], axis=0)
+    return propagate(kind, x, step_two["graph"], step_two["layers"], final_node, aggregate)
+
+
 # ------------------------------------------------------------------------- R
 def rgcn_conv(x, rel_graphs, kernels, bias, act="relu"):
     """Relational extension (no reference counterpart).

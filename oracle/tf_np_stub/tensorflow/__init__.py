@@ -63,3 +63,9 @@ def cast(x, dtype):
 
 def convert_to_tensor(x, dtype=None):
     return np.asarray(x, dtype=dtype)
+
+
+def slice(input_, begin, size):  # noqa: A001  (tf.slice; -1 in `size` = to the end of that axis)
+    x = np.asarray(input_)
+    idx = tuple(np.s_[b:(None if s == -1 else b + s)] for b, s in zip(begin, size))
+    return x[idx]

@@ -32,42 +32,42 @@ def _dense_stack(x, layers, last_sigmoid=False):
     return x
 
 
-def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregate="mean", l2=0.0, hybrid=False,
-                 feature_based=False, dtype=torch.float64):
-    """w: the export_weights() structure (numpy); graph: scipy CSR A_hat (gcn/lightgcn) or
-    (indptr, indices) of the raw adjacency (sage).  Returns (loss, bce, probs, leaves) where
-    leaves maps names to the torch leaf tensors whose .grad the caller reads after backward()."""
-    leaves = {}
-    emb = leaves["embeddings"] = _t(w["embeddings"], dtype)
-    n = emb.shape[0]
+def _operator(kind, graph, n, dtype):
+    """the propagation operator of one SequentialGNN as torch tensors"""
     if kind in ("gcn", "lightgcn", "dgcf"):
-        a = _csr_torch(graph.indptr, graph.indices, graph.data, n, dtype)
-    elif kind == "gat":
+        return dict(a=_csr_torch(graph.indptr, graph.indices, graph.data, n, dtype))
+    if kind == "gat":
         from .graph import gat_edges
         gptr, gcols = gat_edges(np.asarray(graph[0]), np.asarray(graph[1]))
-        g_rows = torch.tensor(np.repeat(np.arange(n), np.diff(gptr)), dtype=torch.int64)
-        g_cols = torch.tensor(np.asarray(gcols), dtype=torch.int64)
-    else:
-        a = _csr_torch(graph[0], graph[1], np.ones(len(graph[1]), np.float32), n, dtype)
-        deg = torch.tensor(np.diff(graph[0]).astype(np.float64), dtype=dtype).clamp(min=1.0).reshape(-1, 1)
-    x, hs, reg = emb, [emb], []
-    reg.append(emb)
-    for li, lw in enumerate(w["layers"]):
+        return dict(g_rows=torch.tensor(np.repeat(np.arange(n), np.diff(gptr)), dtype=torch.int64),
+                    g_cols=torch.tensor(np.asarray(gcols), dtype=torch.int64))
+    return dict(a=_csr_torch(graph[0], graph[1], np.ones(len(graph[1]), np.float32), n, dtype),
+                deg=torch.tensor(np.diff(graph[0]).astype(np.float64), dtype=dtype).clamp(min=1.0).reshape(-1, 1))
+
+
+def _propagate(kind, x, layers, graph, final_node, aggregate, leaves, reg, prefix, dtype):
+    """SequentialGNN's loop + reduction (models/gnn.py:74-84) on torch tensors, starting from node features x.
+    New leaves are registered as prefix + 'layers.<l>.<name>'; regularised tensors are appended to reg."""
+    n = x.shape[0]
+    op = _operator(kind, graph, n, dtype)
+    a, deg, g_rows, g_cols = op.get("a"), op.get("deg"), op.get("g_rows"), op.get("g_cols")
+    hs = [x]
+    for li, lw in enumerate(layers):
         if kind == "gcn":
-            k = leaves["layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
-            b = leaves["layers.%d.bias" % li] = _t(lw["bias"], dtype)
+            k = leaves[prefix + "layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
+            b = leaves[prefix + "layers.%d.bias" % li] = _t(lw["bias"], dtype)
             reg += [k, b]
             x = torch.relu(torch.sparse.mm(a, x @ k) + b)
         elif kind == "lightgcn":
             x = torch.sparse.mm(a, x)
         elif kind == "dgcf":
-            gw = leaves["layers.%d.locality_adaptive/locality-adaptive-weights" % li] = _t(
+            gw = leaves[prefix + "layers.%d.locality_adaptive/locality-adaptive-weights" % li] = _t(
                 lw["locality_adaptive/locality-adaptive-weights"], dtype)
             reg.append(gw)
             x = torch.sparse.mm(a, x * torch.sigmoid(gw))
         elif kind == "sage":
-            k = leaves["layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
-            b = leaves["layers.%d.bias" % li] = _t(lw["bias"], dtype)
+            k = leaves[prefix + "layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
+            b = leaves[prefix + "layers.%d.bias" % li] = _t(lw["bias"], dtype)
             reg += [k, b]
             s = torch.sparse.mm(a, x)
             agg = s / deg if aggregate == "mean" else s
@@ -76,10 +76,10 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
             x = torch.relu(o)
         elif kind == "gat":
             # spektral GATConv, single head, dropout 0; autograd also differentiates the max shift
-            k = leaves["layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
-            a_s = leaves["layers.%d.attn_kernel_self" % li] = _t(lw["attn_self"], dtype)
-            a_n = leaves["layers.%d.attn_kernel_neigh" % li] = _t(lw["attn_neigh"], dtype)
-            b = leaves["layers.%d.bias" % li] = _t(lw["bias"], dtype)
+            k = leaves[prefix + "layers.%d.kernel" % li] = _t(lw["kernel"], dtype)
+            a_s = leaves[prefix + "layers.%d.attn_kernel_self" % li] = _t(lw["attn_self"], dtype)
+            a_n = leaves[prefix + "layers.%d.attn_kernel_neigh" % li] = _t(lw["attn_neigh"], dtype)
+            b = leaves[prefix + "layers.%d.bias" % li] = _t(lw["bias"], dtype)
             reg += [k, b]  # attention kernels carry no regulariser in the reference (gnn.py:321-328)
             z = x @ k
             p_, q_ = z @ a_s, z @ a_n
@@ -96,14 +96,54 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
     if kind in ("lightgcn", "dgcf"):
         final_node = "mean"
     if final_node == "concatenation":
-        red = torch.cat(hs, dim=1)
-    elif final_node == "mean":
-        red = sum(hs) / len(hs)
-    elif final_node == "sum":
-        red = sum(hs)
-    else:
-        red = hs[-1]
+        return torch.cat(hs, dim=1)
+    if final_node == "mean":
+        return sum(hs) / len(hs)
+    if final_node == "sum":
+        return sum(hs)
+    return hs[-1]
 
+
+def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregate="mean", l2=0.0, hybrid=False,
+                 feature_based=False, dtype=torch.float64):
+    """w: the export_weights() structure (numpy); graph: scipy CSR A_hat (gcn/lightgcn) or
+    (indptr, indices) of the raw adjacency (sage).  Returns (loss, bce, probs, leaves) where
+    leaves maps names to the torch leaf tensors whose .grad the caller reads after backward()."""
+    leaves = {}
+    emb = leaves["embeddings"] = _t(w["embeddings"], dtype)
+    reg = [emb]
+    red = _propagate(kind, emb, w["layers"], graph, final_node, aggregate, leaves, reg, "", dtype)
+    return _score_and_loss(red, w, inputs, y, leaves, reg, l2, hybrid, feature_based, dtype)
+
+
+def forward_loss_kg(kind, parts, w, inputs, y, n_users, n_items, final_node="concatenation", side_node="mean",
+                    aggregate="mean", l2=0.0, hybrid=False, feature_based=False, dtype=torch.float64):
+    """The Two-Step / Two-Way variants (models/tsgnn.py:92-94, models/twgnn.py:93-100) under autograd.
+    parts: {'step_one' | 'way_one', 'way_two', 'step_two': dict(embeddings=, layers=, graph=)}; two-way when
+    'way_one' is present.  side_node = item_node / user_item_node.  Leaves are named '<part>.embeddings',
+    '<part>.layers.<l>.<name>'.  The embeddings of HalfInputSequentialGNN carry no regulariser
+    (tsgnn.py:79-83 does not pass one); FullInputSequentialGNN has none at all."""
+    leaves, reg = {}, []
+
+    def side(part):
+        emb = leaves[part + ".embeddings"] = _t(parts[part]["embeddings"], dtype)
+        reg.append(emb)
+        return _propagate(kind, emb, parts[part]["layers"], parts[part]["graph"], side_node, aggregate, leaves, reg,
+                          part + ".", dtype)
+
+    if "way_one" in parts:
+        x = torch.cat([side("way_one")[:n_users], side("way_two")[:n_items]], dim=0)
+    else:
+        items = side("step_one")[:n_items]
+        emb2 = leaves["step_two.embeddings"] = _t(parts["step_two"]["embeddings"], dtype)
+        x = torch.cat([emb2, items], dim=0)
+    red = _propagate(kind, x, parts["step_two"]["layers"], parts["step_two"]["graph"], final_node, aggregate, leaves,
+                     reg, "step_two.", dtype)
+    return _score_and_loss(red, w, inputs, y, leaves, reg, l2, hybrid, feature_based, dtype)
+
+
+def _score_and_loss(red, w, inputs, y, leaves, reg, l2, hybrid, feature_based, dtype):
+    """lookups + BasicRS / HybridCBRS + binary cross-entropy + l2 penalty on `reg`"""
     def stack(name):
         out = []
         for k, (kern, bias) in enumerate(w[name]):
@@ -164,9 +204,17 @@ def forward_loss(kind, w, graph, inputs, y, final_node="concatenation", aggregat
     return loss, bce, p, leaves
 
 
+def gradients_kg(kind, parts, w, inputs, y, n_users, n_items, **kw):
+    """gradients() for the Two-Step / Two-Way variants"""
+    return _grads(*forward_loss_kg(kind, parts, w, inputs, y, n_users, n_items, **kw))
+
+
 def gradients(kind, w, graph, inputs, y, **kw):
     """{leaf name: dLoss/dleaf (numpy float64)} plus the loss value and the probabilities."""
-    loss, bce, p, leaves = forward_loss(kind, w, graph, inputs, y, **kw)
+    return _grads(*forward_loss(kind, w, graph, inputs, y, **kw))
+
+
+def _grads(loss, bce, p, leaves):
     loss.backward()
     grads = {k: (v.grad.detach().numpy().astype(np.float64) if v.grad is not None else np.zeros(tuple(v.shape)))
              for k, v in leaves.items()}

@@ -104,3 +104,44 @@ def export_weights(model):
     n_layers = len(model.gnn.gnn_layers.seq_layers)
     out["layers"] += [{} for _ in range(n_layers - len(out["layers"]))]  # weight-free LightGCN layers
     return out
+
+
+def kg_graphs(n_users=40, n_items=30, n_props=25, n_pos=420, n_links=150, dup_links=12):
+    """Seeded (user-item [U+I], item-property [I+P]) adjacencies in the layout of type_adjacency='unary-kg'
+    (preprocess.py:113-145): both symmetrised, the second with `dup_links` repeated (item, property) links - the
+    same pair under two predicates - which GCN-type layers sum and GraphSage / GAT keep as separate edges."""
+    ui = random_bipartite(n_users, n_items, n_pos, seed=13)
+    ip = random_bipartite(n_items, n_props, n_links, seed=5)
+    half = ip.nnz // 2
+    pick = np.random.RandomState(9).randint(0, half, size=dup_links)
+    r = np.concatenate([ip.row[:half], ip.row[pick]])
+    c = np.concatenate([ip.col[:half], ip.col[pick]])
+    rows, cols = np.concatenate([r, c]).astype(np.int32), np.concatenate([c, r]).astype(np.int32)
+    ip = sparse.coo_matrix((np.ones(len(rows), np.float32), (rows, cols)), shape=ip.shape, dtype=np.float32)
+    return ui, ip
+
+
+KG_GRAPHS = {"default": dict(), "sparse": dict(n_pos=120, n_links=40, dup_links=4)}  # tests/golden/make_golden_models_kg.py
+
+
+KG_COMMON = dict(n_layers=2, embedding_dim=8, l2_regularizer=1e-4, aggregate="mean", dropout_rate=0.0,
+                 final_node="concatenation", activation="relu")
+
+
+def kg_model(case, graphs, n_users, n_items):
+    """the constructor call of tests/golden/make_golden_models_kg.py on the product's classes"""
+    from deep_cbrs_amar_renaissance_b200.models import basic, hybrid
+    name = case.split("-")[0]
+    kw = dict(KG_COMMON, n_hiddens=[8, 8])
+    if name.startswith("Hybrid"):
+        kw.update(dense_units=[[12, 12], [14, 6], [16, 16]], clf_units=[16, 16], feature_based=True)
+    else:
+        kw.update(dense_units=[12, 12], clf_units=[16, 16])
+    if case.endswith("-itemconcat"):
+        kw["item_node"] = "concatenation"
+    if case.endswith("-uiconcat"):
+        kw["user_item_node"] = "concatenation"
+    if case.endswith("-mean"):
+        kw.update(final_node="mean", aggregate="sum")
+    adjs = graphs if "TW" in name else graphs[:2]
+    return getattr(hybrid if name.startswith("Hybrid") else basic, name)(n_users, n_items, adjs, **kw), kw

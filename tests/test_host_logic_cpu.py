@@ -72,3 +72,59 @@ def test_hybrid_cbrs_parameter_counts_for_the_tweaks():
     assert res.count_params() == n_plain
     with pytest.raises(ValueError):
         HybridCBRS(dense_units=[[48], [64], [32]], clf_units=[64], residual=True)
+
+
+# ---------------------------------------------------------------- Two-Step / Two-Way wiring (scope row (f)-4)
+class _ShapeOnlyGraph:
+    def __init__(self, adj):
+        self.shape = tuple(adj.shape)
+        self.n_nodes = self.shape[0]
+
+
+@pytest.fixture
+def shape_only_graphs(monkeypatch):
+    """no GPU here: the adjacency upload is replaced by a shape holder, so constructors and build_weights() run"""
+    from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
+    monkeypatch.setattr(DeviceGraph, "from_scipy", classmethod(lambda cls, adj, device=None, chunk_edges=None:
+                                                               adj if isinstance(adj, _ShapeOnlyGraph) else _ShapeOnlyGraph(adj)))
+
+
+def _kg_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "models", "golden_models_kg.npz"))
+    return g, sorted({k.split("/")[0] for k in g.files if "/out/" in k})
+
+
+def test_two_step_two_way_weights_follow_the_reference_run(shape_only_graphs):
+    """same weight paths and shapes as the reference's own models built with the same keywords (goldens), and the
+    n_hiddens bookkeeping of tsgnn.py:66-77 / twgnn.py:70-77 - made on a copy, the caller's list is left alone"""
+    from deep_cbrs_amar_renaissance_b200.data.preprocess import get_user_properties
+    from tests.helpers import kg_graphs, kg_model
+    g, cases = _kg_cases()
+    n_users, n_items, n_props = int(g["n_users"]), int(g["n_items"]), int(g["n_props"])
+    ui, ip = kg_graphs(n_users, n_items, n_props)
+    graphs = (ui, ip, get_user_properties(ui, ip, n_users, n_items))
+    for case in cases:
+        model, kw = kg_model(case, graphs, n_users, n_items)
+        model.build_weights(10) if case.startswith("Hybrid") else model.build_weights()
+        got = {nm: tuple(w.shape) for nm, w in model.named_weights()}
+        want = {k[len(case) + 1:]: tuple(g[k].shape) for k in g.files if k.startswith(case + "/") and "/out/" not in k}
+        assert got == want, (case, sorted(set(got.items()) ^ set(want.items())))
+        assert list(getattr(model.gnn, "n_hiddens", [])) == list(g[case + "/out/n_hiddens"])
+        assert kw["n_hiddens"] == [8, 8]
+        assert model.gnn.out_dim == g[case + "/out/embeddings"].shape[1]
+
+
+def test_two_step_two_way_constructor_errors(shape_only_graphs):
+    from deep_cbrs_amar_renaissance_b200.models import basic
+    from tests.helpers import kg_graphs
+    ui, ip = kg_graphs()
+    with pytest.raises(ValueError, match="two adjacency"):
+        basic.BasicTSGCN(40, 30, (ui,), n_hiddens=[8, 8])
+    with pytest.raises(ValueError, match="three adjacency"):
+        basic.BasicTWGCN(40, 30, (ui, ip), n_hiddens=[8, 8])
+    with pytest.raises(NotImplementedError):
+        basic.BasicTSGCN(40, 30, (ui, ip), n_hiddens=[8, 8], cache_neighbours=True)
+    # experiment.py:139-146 dispatches on these parents
+    assert issubclass(basic.BasicTSGAT, basic.BasicTSGNN) and issubclass(basic.BasicTWDGCF, basic.BasicTWGNN)
+    assert issubclass(basic.BasicTSGNN, basic.BasicGNN)

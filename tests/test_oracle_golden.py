@@ -79,6 +79,51 @@ def test_host_loaders_match_reference(golden_dir, case):
         assert np.array_equal(x[0], g["test_ep0_b%d_u" % b]) and np.array_equal(x[1], g["test_ep0_b%d_i" % b])
 
 
+@pytest.mark.parametrize("sym", [True, False])
+def test_kg_graphs_match_reference(golden_dir, sym):
+    """'unary-kg' + user_properties=True (Two-Step / Two-Way inputs): the three adjacencies from the reference's own
+    loader (tests/golden/make_golden_kg.py) vs the oracle's restatement and the product's all-sparse host code."""
+    root = os.path.join(golden_dir, "uip_small")
+    g = np.load(os.path.join(root, "golden_kg.npz"))
+    tag = "sym" if sym else "dir"
+    train, _, users, items = og.compact_ids(_tsv(os.path.join(root, "train2id.tsv")), _tsv(os.path.join(root, "test2id.tsv")))
+    triples, props = og.compact_props(_tsv(os.path.join(root, "props2id.tsv")), items)
+    ui, ip = og.build_kg_adjacencies(train, len(users), len(items), triples, len(props), symmetric=sym)
+    oracle = (ui, ip, og.user_properties(ui, ip, len(users), len(items)))
+    trainset, _ = loaders.load_user_item_graph(
+        os.path.join(root, "train2id.tsv"), os.path.join(root, "test2id.tsv"), os.path.join(root, "props2id.tsv"),
+        type_adjacency="unary-kg", user_properties=True, symmetric_adjacency=sym)
+    assert len(trainset.adj_matrix) == 3
+    for mats in (oracle, trainset.adj_matrix):
+        for name, m in zip(("ui", "ip", "up"), mats):
+            assert tuple(m.shape) == tuple(g["%s_%s_shape" % (tag, name)])
+            for field in ("row", "col", "data"):
+                want = g["%s_%s_%s" % (tag, name, field)]
+                got = getattr(m, field)
+                assert got.dtype == want.dtype and np.array_equal(got, want), (name, field)
+    # without user_properties the loader hands over the pair (loaders.py:319)
+    pair, _ = loaders.load_user_item_graph(
+        os.path.join(root, "train2id.tsv"), os.path.join(root, "test2id.tsv"), os.path.join(root, "props2id.tsv"),
+        type_adjacency="unary-kg", symmetric_adjacency=sym)
+    assert len(pair.adj_matrix) == 2 and np.array_equal(pair.adj_matrix[1].row, g[tag + "_ip_row"])
+
+
+def test_user_properties_on_a_larger_graph_stays_sparse():
+    """the all-sparse product == the oracle's dense restatement on a seeded graph with duplicate item-property links"""
+    from deep_cbrs_amar_renaissance_b200.data.preprocess import get_user_properties
+    from tests.helpers import random_bipartite
+    n_users, n_items, n_props = 120, 70, 45
+    ui = random_bipartite(n_users, n_items, 900, seed=3)
+    ip = random_bipartite(n_items, n_props, 260, seed=4)
+    dup = np.arange(0, 40)
+    ip = type(ip)((np.concatenate([ip.data, ip.data[dup]]), (np.concatenate([ip.row, ip.row[dup]]),
+                                                              np.concatenate([ip.col, ip.col[dup]]))), shape=ip.shape)
+    want = og.user_properties(ui, ip, n_users, n_items)
+    got = get_user_properties(ui, ip, n_users, n_items)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert np.array_equal(got.row, want.row) and np.array_equal(got.col, want.col) and np.array_equal(got.data, want.data)
+
+
 def test_unknown_test_id_raises(golden_dir, tmp_path):
     root, _ = _load(golden_dir, "ui_small")
     test = _tsv(os.path.join(root, "test2id.tsv")).copy()

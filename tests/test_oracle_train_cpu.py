@@ -126,6 +126,77 @@ def test_autograd_matches_finite_differences(kind, hybrid, tweak):
             assert abs(fd - g) <= 1e-4 * max(abs(g), 1e-3), (kind, tweak, name, int(j), fd, g)
 
 
+def _kg_parts(kind, rng, two_way, graphs, n_users, n_items, d=6, side_node="mean"):
+    """weights of every SequentialGNN of a Two-Step / Two-Way model (float64) + the scorer"""
+    ui, ip, up = graphs
+    n_props = ip.shape[0] - n_items
+    d2 = d if (side_node == "mean" or kind in ("lightgcn", "dgcf")) else 3 * d
+
+    def part(n, width, adj, with_emb=True, n_emb=None):
+        w = _weights(kind, rng, n, d=width)
+        return dict(embeddings=glorot(rng, (n_emb or n, width)) if with_emb else None, layers=w["layers"], graph=_graph(kind, adj))
+
+    if two_way:
+        parts = dict(way_one=part(n_users + n_props, d, up), way_two=part(n_items + n_props, d, ip),
+                     step_two=part(n_users + n_items, d2, ui, with_emb=False))
+    else:
+        parts = dict(step_one=part(n_items + n_props, d, ip), step_two=part(n_users + n_items, d2, ui, n_emb=n_users))
+    d_out = d2 if kind in ("lightgcn", "dgcf") else 3 * d2
+    scorer = _weights("lightgcn", rng, 4, d=d_out)   # 'lightgcn' -> towers sized for a d_out-wide table
+    return _to64({k: {kk: vv for kk, vv in v.items() if kk != "graph"} for k, v in parts.items()}), \
+        {k: v["graph"] for k, v in parts.items()}, _to64({k: scorer[k] for k in ("unet", "inet", "clf")})
+
+
+@pytest.mark.parametrize("kind,two_way,side_node", [("gcn", False, "mean"), ("gcn", False, "concatenation"), ("sage", False, "mean"),
+                                                    ("gat", True, "mean"), ("gcn", True, "concatenation"),
+                                                    ("lightgcn", True, "mean"), ("dgcf", False, "mean")])
+def test_kg_autograd_matches_finite_differences(kind, two_way, side_node):
+    """the Two-Step / Two-Way training oracle (forward_loss_kg) against central differences of its own loss"""
+    from deep_cbrs_amar_renaissance_b200.data.preprocess import get_user_properties
+    from tests.helpers import kg_graphs
+    rng = np.random.RandomState(5)
+    n_users, n_items, n_props = 12, 9, 7
+    ui, ip = kg_graphs(n_users, n_items, n_props, n_pos=40, n_links=14, dup_links=2)
+    graphs = (ui, ip, get_user_properties(ui, ip, n_users, n_items))
+    parts, gr, w = _kg_parts(kind, rng, two_way, graphs, n_users, n_items, side_node=side_node)
+    for k in parts:
+        parts[k]["graph"] = gr[k]
+    u = rng.randint(0, n_users, 16)
+    i = rng.randint(0, n_items, 16) + n_users
+    y = rng.randint(0, 2, 16)
+    kw = dict(l2=1e-3, side_node=side_node)
+    grads, loss, _ = ot.gradients_kg(kind, parts, w, (u, i), y, n_users, n_items, **kw)
+    first = "way_one" if two_way else "step_one"
+    probes = [(first + ".embeddings", parts[first]["embeddings"])]
+    if two_way:
+        probes.append(("way_two.embeddings", parts["way_two"]["embeddings"]))
+    else:
+        probes.append(("step_two.embeddings", parts["step_two"]["embeddings"]))
+    for part in (first, "step_two"):
+        lw = parts[part]["layers"][0]
+        for key, leaf in (("kernel", "kernel"), ("attn_neigh", "attn_kernel_neigh"),
+                          ("locality_adaptive/locality-adaptive-weights", "locality_adaptive/locality-adaptive-weights")):
+            if key in lw:
+                probes.append(("%s.layers.0.%s" % (part, leaf), lw[key]))
+    assert set(grads) >= {name for name, _ in probes}
+    eps = 1e-6
+    for name, arr in probes:
+        flat = arr.reshape(-1)
+        for j in rng.choice(flat.size, size=min(4, flat.size), replace=False):
+            old = flat[j]
+            flat[j] = old + eps
+            hi = float(ot.forward_loss_kg(kind, parts, w, (u, i), y, n_users, n_items, **kw)[0].detach())
+            flat[j] = old - eps
+            lo = float(ot.forward_loss_kg(kind, parts, w, (u, i), y, n_users, n_items, **kw)[0].detach())
+            flat[j] = old
+            fd = (hi - lo) / (2 * eps)
+            g = grads[name].reshape(-1)[j]
+            assert abs(fd - g) <= 1e-4 * max(abs(g), 1e-3), (kind, two_way, name, int(j), fd, g)
+    # rows of the side graphs that the next step never reads (properties) still get gradient through propagation,
+    # user rows of the step-two embeddings get theirs directly
+    assert np.abs(grads[first + ".embeddings"]).max() > 0
+
+
 def test_adam_update_is_the_keras_formula():
     w, g = np.array([1.0, -2.0]), np.array([0.5, -0.25])
     m = v = np.zeros(2)
