@@ -309,9 +309,59 @@ def _gat_train(tape, layer, x_node, graph, out):
     return node
 
 
-def gnn_train(tape, seq):
-    """SequentialGNN.call (/root/reference/src/models/gnn.py:74-84) on the tape -> Node of [N, D_out]."""
-    emb = seq.embeddings
+def embeddings_train(tape, emb):
+    """A learnable table as a tape value; its gradient is handed to the optimiser once every consumer recorded
+    after this point has run its backward (the sink sits before them on the tape)."""
+    node = Node(emb)
+
+    def bwd():
+        if node.grad is not None:
+            g = node.grad
+            tape.wgrad(emb, g if g.is_contiguous() else g.contiguous())
+
+    tape.ops.append(bwd)
+    return node
+
+
+def head_rows_train(tape, node, n):
+    """x[:n] (tsgnn.py:94, twgnn.py:96-99): the rows past n get no gradient from this consumer"""
+    out = Node(node.x[:n])
+
+    def bwd():
+        if out.grad is None:
+            return
+        g = torch.zeros(node.x.shape, dtype=torch.float32, device=node.x.device)
+        g[:n].copy_(out.grad)
+        node.add_grad(g)
+
+    tape.ops.append(bwd)
+    return out
+
+
+def concat_rows_train(tape, nodes):
+    """tf.concat(..., axis=0) of node-row blocks (gnn.py:137, twgnn.py:96-99)"""
+    out = Node(torch.cat([nd.x for nd in nodes], dim=0))
+
+    def bwd():
+        if out.grad is None:
+            return
+        o = 0
+        for nd in nodes:
+            r = nd.x.shape[0]
+            nd.add_grad(out.grad[o:o + r])
+            o += r
+
+    tape.ops.append(bwd)
+    return out
+
+
+def gnn_train(tape, seq, x_node=None):
+    """SequentialGNN.call (/root/reference/src/models/gnn.py:74-84) on the tape -> Node of [N, D_out].
+    x_node: the initial node features when they are not the GNN's own embeddings alone
+    (HalfInputSequentialGNN / FullInputSequentialGNN, gnn.py:136-147,198-207)."""
+    if x_node is None:
+        x_node = embeddings_train(tape, seq.embeddings)
+    emb = x_node.x
     n = emb.shape[0]
     widths = seq._widths()
     graph = seq.adj_matrix
@@ -321,12 +371,10 @@ def gnn_train(tape, seq):
     if seq.final_node not in ('concatenation', 'mean', 'sum', 'last'):
         raise NotImplementedError("training with final_node='%s'" % seq.final_node)
     buf = torch.empty(n, sum(widths), dtype=torch.float32, device=emb.device) if concat else None
-    e_node = Node(emb)
-    nodes = [e_node]
+    nodes = [x_node]
     off = widths[0]
     if concat:
         buf[:, :widths[0]].copy_(emb)
-    x_node = e_node
     for layer, w in zip(seq.seq_layers, widths[1:]):
         if not layer.built:
             layer.build([(n, x_node.x.shape[1]), None])
@@ -371,16 +419,27 @@ def gnn_train(tape, seq):
             for nd in nodes:
                 nd.add_grad(gs)
 
-    # order on the tape: embeddings sink first (runs last), then the layers (appended above, already
-    # in forward order), then the reduction (runs first)
-    def bwd_embeddings():
-        if e_node.grad is not None:
-            g = e_node.grad
-            tape.wgrad(emb, g if g.is_contiguous() else g.contiguous())
-
-    tape.ops.insert(0, bwd_embeddings)
+    # order on the tape: the embeddings sink (appended by embeddings_train before the layers, so it runs after
+    # them), the layers in forward order, then the reduction (runs first)
     tape.ops.append(bwd_reduce)
     return red_node
+
+
+def model_gnn_train(tape, gnn):
+    """model.gnn(None) on the tape for every family: GNN (gnn.py:262-264), TwoStepGNN (tsgnn.py:92-94),
+    TwoWayGNN (twgnn.py:93-100)."""
+    from .models.tsgnn import TwoStepGNN
+    from .models.twgnn import TwoWayGNN
+    if isinstance(gnn, TwoStepGNN):
+        items = head_rows_train(tape, gnn_train(tape, gnn.step_one_gnn_layers), gnn.n_embeddings)
+        two = gnn.step_two_gnn_layers
+        x = concat_rows_train(tape, [embeddings_train(tape, two.embeddings), items])
+        return gnn_train(tape, two, x)
+    if isinstance(gnn, TwoWayGNN):
+        users = head_rows_train(tape, gnn_train(tape, gnn.way_one_gnn_layers), gnn.n_users)
+        items = head_rows_train(tape, gnn_train(tape, gnn.way_two_gnn_layers), gnn.n_items)
+        return gnn_train(tape, gnn.step_two_gnn_layers, concat_rows_train(tape, [users, items]))
+    return gnn_train(tape, gnn.gnn_layers)
 
 
 def lookup_train(tape, table_node, ids_list):
@@ -455,7 +514,7 @@ def forward_backward(model, inputs, y):
     from .models.basic import BasicGNN, _ids
     from .models.hybrid import HybridBertGNN, _rows
     tape = Tape()
-    red = gnn_train(tape, model.gnn.gnn_layers)
+    red = model_gnn_train(tape, model.gnn)
     if isinstance(model, BasicGNN):
         u, i = _ids(inputs[0]), _ids(inputs[1])
         model.rs.build_for(red.x.shape[1])
