@@ -1,4 +1,4 @@
-"""Batch sequences (mirror of /root/reference/src/data/datasets.py:8-77,146-213,309-373).
+"""Batch sequences (mirror of /root/reference/src/data/datasets.py:8-143,146-213,309-373).
 
 They define the gather indices of the hot path: batch b of epoch e is
 ratings[perm_e[b*B:(b+1)*B]] with perm_e drawn from ONE persistent
@@ -70,6 +70,28 @@ class UserItemEmbeddings(_RatingBatches):
     def __getitem__(self, idx):
         r = self._rows(idx)
         return (self.embeddings[r[:, 0]], self.embeddings[r[:, 1]]), r[:, 2]
+
+
+class HybridUserItemEmbeddings(Sequence):
+    """((graph[user], graph[item], bert[user], bert[item]), ratings): the pre-computed-embedding hybrid baseline
+    (datasets.py:80-143).  Two UserItemEmbeddings with the same seed, hence the same permutation."""
+
+    def __init__(self, ratings, users, items, graph_embeddings, bert_embeddings, batch_size=512, shuffle=False, seed=42):
+        self.ratings, self.users, self.items = ratings, users, items
+        self.graph_embeddings = UserItemEmbeddings(ratings, users, items, graph_embeddings, batch_size, shuffle, seed)
+        self.bert_embeddings = UserItemEmbeddings(ratings, users, items, bert_embeddings, batch_size, shuffle, seed)
+
+    def __len__(self):
+        return len(self.graph_embeddings)
+
+    def __getitem__(self, idx):
+        (ug, ig), y = self.graph_embeddings[idx]
+        (ub, ib), _ = self.bert_embeddings[idx]
+        return (ug, ig, ub, ib), y
+
+    def on_epoch_end(self):
+        self.graph_embeddings.on_epoch_end()
+        self.bert_embeddings.on_epoch_end()
 
 
 class UserItemGraphEmbeddings(Sequence):

@@ -4,10 +4,12 @@ Same function names, keyword arguments and return values as the reference for
 the loaders on the hot path, so `Experimenter.build_dataset`
 (experiment.py:120-128) can call them by name with signature-filtered kwargs.
 """
+import json
+
 import numpy as np
 import pandas as pd
 
-from .datasets import UserItemGraph, UserItemGraphEmbeddings
+from .datasets import HybridUserItemEmbeddings, UserItemEmbeddings, UserItemGraph, UserItemGraphEmbeddings
 from .preprocess import build_adjacency_matrix, get_user_properties
 
 
@@ -99,6 +101,46 @@ def load_bert_user_item_embeddings(user_filepath, item_filepath, users, items):
         return np.stack([np.asarray(lut[int(i)], dtype=np.float32) for i in ids])
     return np.concatenate([table(user_filepath, 'profile_embedding', users),
                            table(item_filepath, 'embedding', items)], axis=0)
+
+
+def load_graph_user_item_embeddings(filepath, users, items):
+    """[U+I, dim] float32 rows of the pre-computed knowledge-graph embeddings, users first (loaders.py:85-120):
+    the JSON holds {'ent_embeddings': [[...], ...]} indexed by the ORIGINAL (OpenKE) entity id."""
+    with open(filepath) as fp:
+        table = np.array(json.load(fp)['ent_embeddings'], dtype=np.float32)
+    return np.concatenate([table[users], table[items]], axis=0)
+
+
+def _ratings_only(train_ratings_filepath, test_ratings_filepath, sep):
+    return load_train_test_ratings(train_ratings_filepath, test_ratings_filepath, sep=sep, return_adjacency=False)
+
+
+def load_graph_embeddings(train_ratings_filepath, test_ratings_filepath, graph_filepath, sep='\t', shuffle=True,
+                          train_batch_size=1024, test_batch_size=2048):
+    """Sequences of pre-computed graph-embedding rows for basic.BasicRS (loaders.py:147-184)."""
+    (train, test), (users, items) = _ratings_only(train_ratings_filepath, test_ratings_filepath, sep)
+    emb = load_graph_user_item_embeddings(graph_filepath, users, items)
+    return (UserItemEmbeddings(train, users, items, emb, batch_size=train_batch_size, shuffle=shuffle),
+            UserItemEmbeddings(test, users, items, emb, batch_size=test_batch_size, shuffle=False))
+
+
+def load_bert_embeddings(train_ratings_filepath, test_ratings_filepath, bert_user_filepath, bert_item_filepath, sep='\t',
+                         shuffle=True, train_batch_size=1024, test_batch_size=2048):
+    """Sequences of BERT content rows for basic.BasicRS (loaders.py:187-226)."""
+    (train, test), (users, items) = _ratings_only(train_ratings_filepath, test_ratings_filepath, sep)
+    emb = load_bert_user_item_embeddings(bert_user_filepath, bert_item_filepath, users, items)
+    return (UserItemEmbeddings(train, users, items, emb, batch_size=train_batch_size, shuffle=shuffle),
+            UserItemEmbeddings(test, users, items, emb, batch_size=test_batch_size, shuffle=False))
+
+
+def load_hybrid_embeddings(train_ratings_filepath, test_ratings_filepath, graph_filepath, bert_user_filepath,
+                           bert_item_filepath, sep='\t', shuffle=True, train_batch_size=1024, test_batch_size=2048):
+    """Sequences of (graph, BERT) rows for hybrid.HybridCBRS (loaders.py:229-271)."""
+    (train, test), (users, items) = _ratings_only(train_ratings_filepath, test_ratings_filepath, sep)
+    graph = load_graph_user_item_embeddings(graph_filepath, users, items)
+    bert = load_bert_user_item_embeddings(bert_user_filepath, bert_item_filepath, users, items)
+    return (HybridUserItemEmbeddings(train, users, items, graph, bert, batch_size=train_batch_size, shuffle=shuffle),
+            HybridUserItemEmbeddings(test, users, items, graph, bert, batch_size=test_batch_size, shuffle=False))
 
 
 def load_user_item_graph(train_ratings_filepath, test_ratings_filepath, props_triples_filepath=None,

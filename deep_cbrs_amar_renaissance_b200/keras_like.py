@@ -234,7 +234,7 @@ class Model(Layer):
             for step, b in enumerate(order):
                 x, y = sequence[int(b)]
                 fire("on_train_batch_begin", step, {})
-                if cuda_graph and len(x) == 2:
+                if cuda_graph and len(x) == 2 and hasattr(self, 'gnn'):
                     if graphed is None and len(sequence) > 1:
                         graphed = self.make_graphed_train_step(len(sequence[0][1]))
                     if graphed is not None and len(y) == graphed.batch_size:

@@ -24,6 +24,13 @@ def _ids(x):
     return torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(default_device(), non_blocking=True)
 
 
+def _rows(x):
+    """float rows (numpy from the Sequence, or tensors) -> CUDA float32 tensor (the per-batch H2D copy)"""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=default_device(), dtype=torch.float32, non_blocking=True)
+    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(default_device(), non_blocking=True)
+
+
 class BasicRS(Model):
     def __init__(self, dense_units=(512, 256, 128), clf_units=(64, 64), activation='relu', **kwargs):
         super().__init__("basic_rs")
@@ -38,8 +45,10 @@ class BasicRS(Model):
         self.clf.build_for(du + di)
 
     def call(self, inputs, **kwargs):
+        """as a model of its own (config.yaml:6, experiment.py:152): inputs = the (user rows, item rows) batches of
+        data.datasets.UserItemEmbeddings"""
         u, i = inputs
-        return self.call_sources((u, None), (i, None))
+        return self.call_sources((_rows(u), None), (_rows(i), None))
 
     def call_sources(self, u_src, i_src):
         u = self.unet.call_sources([u_src])

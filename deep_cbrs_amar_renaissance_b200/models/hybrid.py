@@ -13,19 +13,13 @@ import torch
 
 from ..keras_like import Model, default_device
 from ..layers.fusion import FusionLayer
-from .basic import _ids
+from .basic import _ids, _rows
 from .. import ops
 from ..layers.dense import materialize
 from .dense import build_dense_classifier, build_dense_network, build_residual_dense_network
 from .gnn import GAT, GCN, DGCF, RGCN, GraphSage, LightGCN
 from .tsgnn import TwoStepDGCF, TwoStepGAT, TwoStepGCN, TwoStepGraphSage, TwoStepLightGCN
 from .twgnn import TwoWayDGCF, TwoWayGAT, TwoWayGCN, TwoWayGraphSage, TwoWayLightGCN
-
-
-def _rows(x):
-    if isinstance(x, torch.Tensor):
-        return x.to(device=default_device(), dtype=torch.float32, non_blocking=True)
-    return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(default_device(), non_blocking=True)
 
 
 class HybridCBRS(Model):
@@ -74,7 +68,7 @@ class HybridCBRS(Model):
 
     def call(self, inputs, **kwargs):
         ug, ig, ub, ib = inputs
-        return self.call_sources((ug, None), (ig, None), (ub, None), (ib, None))
+        return self.call_sources((_rows(ug), None), (_rows(ig), None), (_rows(ub), None), (_rows(ib), None))
 
     def call_sources(self, ug_src, ig_src, ub_src, ib_src):
         ug = (self.dense1a.call_sources([ug_src]), None)

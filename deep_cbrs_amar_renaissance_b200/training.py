@@ -511,16 +511,26 @@ class Adam:
 # ------------------------------------------------------------------ one step
 def forward_backward(model, inputs, y):
     """Forward with saved activations, loss, backward.  Returns (tape, loss [1], correct [1], probs)."""
-    from .models.basic import BasicGNN, _ids
-    from .models.hybrid import HybridBertGNN, _rows
+    from .models.basic import BasicGNN, BasicRS, _ids, _rows
+    from .models.hybrid import HybridBertGNN, HybridCBRS
     tape = Tape()
-    red = model_gnn_train(tape, model.gnn)
-    if isinstance(model, BasicGNN):
+    const = lambda rows: Node(_rows(rows), None, needs_grad=False)  # noqa: E731  (a batch input, not differentiated)
+    if isinstance(model, BasicRS):  # the scorer alone over pre-computed embedding rows (config.yaml:6)
+        u, i = const(inputs[0]), const(inputs[1])
+        model.build_for(u.x.shape[1])
+        p = basic_rs_train(tape, model, u, i)
+    elif isinstance(model, HybridCBRS):
+        ug, ig, ub, ib = (const(t) for t in inputs)
+        model.build_for(ug.x.shape[1], ub.x.shape[1])
+        p = hybrid_rs_train(tape, model, ug, ig, ub, ib)
+    elif isinstance(model, BasicGNN):
+        red = model_gnn_train(tape, model.gnn)
         u, i = _ids(inputs[0]), _ids(inputs[1])
         model.rs.build_for(red.x.shape[1])
         us, is_ = lookup_train(tape, red, [u, i])
         p = basic_rs_train(tape, model.rs, us, is_)
     elif isinstance(model, HybridBertGNN):
+        red = model_gnn_train(tape, model.gnn)
         if len(inputs) == 2:
             if model.content_table is None:
                 raise ValueError("ids-only call needs set_content_table(...) first")
@@ -528,7 +538,7 @@ def forward_backward(model, inputs, y):
             ub, ib = Node(model.content_table, u, needs_grad=False), Node(model.content_table, i, needs_grad=False)
         else:
             u, i = _ids(inputs[0]), _ids(inputs[1])
-            ub, ib = Node(_rows(inputs[2]), None, needs_grad=False), Node(_rows(inputs[3]), None, needs_grad=False)
+            ub, ib = const(inputs[2]), const(inputs[3])
         model.rs.build_for(red.x.shape[1], ub.x.shape[1])
         us, is_ = lookup_train(tape, red, [u, i])
         p = hybrid_rs_train(tape, model.rs, us, is_, ub, ib)

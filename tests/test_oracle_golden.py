@@ -141,3 +141,28 @@ def test_unknown_adjacency_type_raises(golden_dir):
     with pytest.raises(ValueError):
         loaders.load_user_item_graph(os.path.join(root, "train2id.tsv"), os.path.join(root, "test2id.tsv"),
                                      type_adjacency="nope")
+
+
+def test_embedding_loaders_match_reference(golden_dir):
+    """load_graph_embeddings / load_bert_embeddings / load_hybrid_embeddings (the pre-computed-embedding baselines,
+    loaders.py:147-271) against batches produced by the reference's own loaders (tests/golden/make_golden_kge.py)"""
+    root = os.path.join(golden_dir, "hybrid_small")
+    g = np.load(os.path.join(root, "golden_kge.npz"))
+    base = dict(train_ratings_filepath=os.path.join(root, "train2id.tsv"), test_ratings_filepath=os.path.join(root, "test2id.tsv"),
+                train_batch_size=128, test_batch_size=64)
+    bert = dict(bert_user_filepath=os.path.join(root, "user-lastlayer.json"), bert_item_filepath=os.path.join(root, "item-lastlayer.json"))
+    graph = dict(graph_filepath=os.path.join(root, "768TransH.json"))
+    for name, fn, kw, width in (("graph", loaders.load_graph_embeddings, graph, 2), ("bert", loaders.load_bert_embeddings, bert, 2),
+                                ("hybrid", loaders.load_hybrid_embeddings, dict(graph, **bert), 4)):
+        tr, te = fn(**base, **kw)
+        assert [len(tr), len(te)] == list(g[name + "_n_batches"])
+        for tag, seq, epochs in (("train", tr, 2), ("test", te, 1)):
+            for ep in range(epochs):
+                for b in range(len(seq)):
+                    x, y = seq[b]
+                    assert len(x) == width
+                    for k, arr in enumerate(x):
+                        want = g["%s_%s_ep%d_b%d_x%d" % (name, tag, ep, b, k)]
+                        assert arr.dtype == want.dtype and np.array_equal(arr, want)
+                    assert np.array_equal(y, g["%s_%s_ep%d_b%d_y" % (name, tag, ep, b)])
+                seq.on_epoch_end()
