@@ -46,6 +46,9 @@ _SIGS = {
                            P, P, P, P, P, c_int64, P]),
     "cbrs_dense_ex": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int, c_int,
                               P, P, P, P, P, c_int64, c_int, POINTER(c_void_p), POINTER(c_void_p), c_int, P]),
+    "cbrs_dense_tc_image_bytes": (c_size_t, [c_int32, c_int32]),
+    "cbrs_dense_tc_prepare": (c_int, [P, c_int32, c_int32, P, P]),
+    "cbrs_dense_tc": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int, P, c_int64, P]),
     "cbrs_reduce_layers": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int32, POINTER(c_float), c_float,
                                    c_int64, c_int32, P, c_int64, P]),
     "cbrs_gather_rows": (c_int, [P, c_int64, P, c_int64, c_int32, P, c_int64, P]),

@@ -12,6 +12,9 @@ class Dense(Layer):
         super().__init__(name or "dense")
         self.units, self.activation = int(units), activation
         self.kernel = self.bias = None
+        # "fp32": the FFMA kernel (1e-5 parity path).  "bf16": operands rounded to bf16, product on the tensor cores
+        # (cbrs_dense_tc) for the shapes it takes, inference only - set through set_scorer_precision().
+        self.precision = "fp32"
 
     def build(self, input_shape):
         self.build_for(int(input_shape[-1]))
@@ -23,15 +26,34 @@ class Dense(Layer):
             self.built = True
 
     def call(self, x, **kwargs):
-        return ops.dense(x, self.kernel, self.bias, self.activation)
+        return self.call_sources([(x, None)])
 
     def call_sources(self, sources):
         """sources: one or two (matrix, row_index_or_None); concatenated along features
         and (when indexed) gathered inside the kernel, never materialised."""
         (x1, i1) = sources[0]
         x2, i2 = (sources[1] if len(sources) > 1 else (None, None))
-        self.build_for(x1.shape[1] + (x2.shape[1] if x2 is not None else 0))
+        f1, f2 = x1.shape[1], (x2.shape[1] if x2 is not None else 0)
+        self.build_for(f1 + f2)
+        if self.precision == "bf16" and ops.dense_tc_eligible(f1, f2, self.units) and _aligned(x1) and _aligned(x2):
+            return ops.dense_tc(x1, self.kernel, self.bias, self.activation, x2=x2, idx1=i1, idx2=i2)
         return ops.dense(x1, self.kernel, self.bias, self.activation, x2=x2, idx1=i1, idx2=i2)
+
+
+def _aligned(x):
+    """rows start on 16-byte boundaries (what the tensor-core kernel's 128-bit loads need)"""
+    return x is None or (x.data_ptr() % 16 == 0 and (x.shape[0] <= 1 or x.stride(0) % 4 == 0))
+
+
+def set_scorer_precision(layer, precision):
+    """'fp32' | 'bf16' on every Dense below `layer` (a scorer: BasicRS / HybridCBRS).  bf16 = tensor-core towers and
+    classifier for inference (BASELINE config 4); layers whose shapes the kernel does not take stay on the fp32 kernel."""
+    if precision not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if isinstance(layer, Dense):
+        layer.precision = precision
+    for _, sub in layer._sublayers():
+        set_scorer_precision(sub, precision)
 
 
 class DenseStack(Layer):

@@ -131,6 +131,13 @@ class HybridBertGNN(Model, abc.ABC):
     def invalidate(self):
         self._cached = None
 
+    def set_scorer_precision(self, precision):
+        """'bf16': the scorer's Dense layers run on the tensor cores (bf16 operands, fp32 accumulate; inference only,
+        tolerance in tests/test_zz_gpu_dense_tc.py); 'fp32' (default): the reference's arithmetic."""
+        from ..layers.dense import set_scorer_precision
+        set_scorer_precision(self.rs, precision)
+        return self
+
     def call(self, inputs, **kwargs):
         updated_embeddings = self.propagate()
         return self.embed_recommend(updated_embeddings, inputs)

@@ -247,6 +247,46 @@ def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_
     return out
 
 
+def dense_tc_eligible(f1, f2, n):
+    """shapes cbrs_dense_tc takes: source widths multiples of 8, at most 256 outputs"""
+    return f1 > 0 and f1 % 8 == 0 and f2 % 8 == 0 and 0 < n <= 256
+
+
+def dense_tc(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, out=None, image=None):
+    """cbrs_dense on the tensor cores: act(bf16([x1[idx1] || x2[idx2]]) @ bf16(w) + b), fp32 accumulate and output.
+    `image` = a previously prepared operand image of w (dense_tc_image); built here (one small kernel) when absent."""
+    lib = L.load()
+    x1, ld1 = _rowmajor(x1)
+    f1, f2, ld2 = x1.shape[1], 0, 0
+    if x2 is not None:
+        x2, ld2 = _rowmajor(x2)
+        f2 = x2.shape[1]
+    m = idx1.numel() if idx1 is not None else x1.shape[0]
+    if w.dim() != 2 or w.shape[0] != f1 + f2 or not w.is_contiguous():
+        raise L.CbrsError("dense_tc: kernel must be contiguous [{}, n], got {}".format(f1 + f2, tuple(w.shape)))
+    n = w.shape[1]
+    if image is None:
+        image = dense_tc_image(w)
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=x1.device)
+    out, ldo = _rowmajor(out)
+    code = act if isinstance(act, int) else L.ACTS[act]
+    L.check(lib.cbrs_dense_tc(_ptr(x1), ld1, _ptr(idx1, torch.int64), f1, _ptr(x2), ld2, _ptr(idx2, torch.int64), f2,
+                              _ptr(image), _ptr(b, torch.float32), m, n, code, _ptr(out), ldo, _stream()), "cbrs_dense_tc")
+    _count(1)
+    return out
+
+
+def dense_tc_image(w):
+    """bf16 tensor-core operand image of a Keras kernel [k, n] (cbrs_dense_tc_prepare)"""
+    lib = L.load()
+    k, n = w.shape
+    image = torch.empty(lib.cbrs_dense_tc_image_bytes(k, n), dtype=torch.uint8, device=w.device)
+    L.check(lib.cbrs_dense_tc_prepare(_ptr(w, torch.float32), k, n, _ptr(image), _stream()), "cbrs_dense_tc_prepare")
+    _count(1)
+    return image
+
+
 def reduce_layers(hs, coefs=None, divide_by=1.0, out=None):
     lib = L.load()
     n_rows, d = hs[0].shape

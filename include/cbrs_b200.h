@@ -154,6 +154,18 @@ int cbrs_dense(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, co
                const float *a_neigh, float *p_out, float *q_out, float *out, int64_t ldo,
                void *stream);
 
+/* The same layer on the tensor cores (tcgen05, bf16 operands, fp32 accumulate): the tower GEMMs of the scorers
+ * (src/models/hybrid.py:74-77: Dense 768 -> 256 -> 64 over the BERT rows; src/models/basic.py:33-34).
+ * out = act( bf16([X1[idx1] || X2[idx2]]) @ bf16(W) + b ), out fp32.  W is handed over as the operand image that
+ * cbrs_dense_tc_prepare writes from the Keras kernel [k, n] (cbrs_dense_tc_image_bytes(k, n) bytes, 16-byte
+ * aligned; rewrite it whenever W changes).  Requirements: n <= 256, f1 and f2 multiples of 8, source rows 16-byte
+ * aligned (ld % 4 == 0).  Results differ from cbrs_dense by the bf16 rounding of the operands only.          */
+size_t cbrs_dense_tc_image_bytes(int32_t k, int32_t n);
+int cbrs_dense_tc_prepare(const float *w, int32_t k, int32_t n, void *image, void *stream);
+int cbrs_dense_tc(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1, const float *x2, int64_t ld2,
+                  const int64_t *idx2, int32_t f2, const void *w_image, const float *b, int64_t m, int32_t n,
+                  int act, float *out, int64_t ldo, void *stream);
+
 /* General form of cbrs_dense: the output (and its peer copies) can be written as bf16 (out_dtype =
  * CBRS_DTYPE_BF16, round to nearest even, ldo in elements) so that the GCN transform Z = X W feeds the bf16
  * sparse kernel without a conversion pass; out_peers_host / q_peers_host / n_peers as in cbrs_dense_bcast.  */
