@@ -7,8 +7,9 @@
 // product on the 5th-generation tensor cores.  One CTA owns 128 output rows:
 //   * K is walked in blocks of 64.  For every block the 128 threads build the A operand tile - 128 rows x 64 bf16 in
 //     the canonical K-major SWIZZLE_128B layout - straight from the fp32 rows in HBM (8 threads per row, 32 B of fp32
-//     each, so a warp reads four 256-byte row segments: coalesced) and copy the matching block of the pre-swizzled
-//     bf16 image of W (cbrs_dense_tc_prepare) next to it;
+//     each, so a warp reads four 256-byte row segments: coalesced; a thread's 16 loads are all in flight before the
+//     first is used) while one cp.async.bulk brings the matching block of the pre-swizzled bf16 image of W
+//     (cbrs_dense_tc_prepare) next to it, counted on an mbarrier the MMA-issuing thread waits on;
 //   * one thread issues four tcgen05.mma (M=128, N=n_pad, K=16) per block into ONE TMEM accumulator and commits to the
 //     block's mbarrier; tiles are double buffered, so the tensor core works on block b while the CTA builds b+1;
 //   * thread t reads accumulator row t back with tcgen05.ld (warp w owns TMEM lanes 32w..32w+31), adds the bias,
@@ -60,6 +61,22 @@ __device__ __forceinline__ float dt_act(float v, int act) {
     }
 }
 
+// 1-D bulk copy global -> shared through the async proxy (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void dt_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void dt_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ float dt_or(float v, uint32_t z) { return __uint_as_float(__float_as_uint(v) | z); }
+__device__ __forceinline__ float4 dt_ld_stream4(const float *p) {   // read-once rows: keep them out of L1
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
 __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_constant__ DenseTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
     const int n_pad = (p.n + 15) / 16 * 16;
@@ -70,8 +87,10 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
     unsigned char *Bs = As + 2 * 16384;                    // [2][n_pad][128 B]
     const float **row1 = reinterpret_cast<const float **>(Bs + 2 * b_bytes);   // [128] start of the row in source 1
     const float **row2 = row1 + kDtRows;                                          // [128] ... in source 2
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(row2 + kDtRows);                // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 2);
+    uint64_t *mma_done = reinterpret_cast<uint64_t *>(row2 + kDtRows);            // [2] MMAs that read buffer b completed
+    uint64_t *b_full = mma_done + 2;                                              // [2] bulk copy of the B tile landed
+    float *bias_s = reinterpret_cast<float *>(b_full + 2);                        // [n_pad]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bias_s + n_pad);
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int64_t m0 = (int64_t)blockIdx.x * kDtRows;
@@ -80,19 +99,18 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
     if (tid == 0) {
-        tc::mbar_init(mbar, 1);
-        tc::mbar_init(mbar + 1, 1);
+        tc::mbar_init(mma_done, 1);
+        tc::mbar_init(mma_done + 1, 1);
+        tc::mbar_init(b_full, 1);
+        tc::mbar_init(b_full + 1, 1);
         tc::fence_mbar_init();
     }
-    {   // gather indices are resolved once per row: pointer to the row's first element in each source (null = zeros)
-        const int64_t m = m0 + tid;
-        const float *r1 = nullptr, *r2 = nullptr;
-        if (m < p.m) {
-            r1 = p.x1 + (p.idx1 ? __ldg(p.idx1 + m) : m) * p.ld1;
-            if (p.x2) r2 = p.x2 + (p.idx2 ? __ldg(p.idx2 + m) : m) * p.ld2;
-        }
-        row1[tid] = r1;
-        row2[tid] = r2;
+    {   // gather indices are resolved once per row: pointer to the row's first element in each source.  Rows past m
+        // read row m-1 again (valid memory; their accumulator rows are never written out)
+        const int64_t m = (m0 + tid < p.m) ? m0 + tid : p.m - 1;
+        row1[tid] = p.x1 + (p.idx1 ? __ldg(p.idx1 + m) : m) * p.ld1;
+        row2[tid] = p.x2 ? p.x2 + (p.idx2 ? __ldg(p.idx2 + m) : m) * p.ld2 : p.x1;
+        for (int e = tid; e < n_pad; e += kDtThreads) bias_s[e] = (p.b && e < p.n) ? __ldg(p.b + e) : 0.f;
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -102,48 +120,64 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
     const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs);
     if ((a_addr & 1023u) != 0u) __trap();  // the runtime honours the declared alignment; fail loudly if not
     const uint32_t idesc = tc::idesc_bf16_f32(kDtRows, n_pad);
+    const uint32_t zero_rt = (uint32_t)p.n >> 20;   // 0 (n <= 256), but not to the compiler: see the scheduling fence below
 
     for (int kb = 0; kb < kb_count; ++kb) {
         const int buf = kb & 1, use = kb >> 1;
-        if (use > 0) {  // the MMAs that read this buffer two blocks ago must have completed
-            tc::mbar_wait(mbar + buf, (uint32_t)(use - 1) & 1u);
+        if (use > 0) {  // the MMAs that read this buffer pair two blocks ago must have completed
+            tc::mbar_wait(mma_done + buf, (uint32_t)(use - 1) & 1u);
             tc::tc_fence_after_sync();
         }
-        // ---- A tile: 128 rows x 8 chunks of 8 bf16; thread -> (row, chunk) with 8 consecutive threads per row ----
+        // ---- B tile: block kb of the image (already in operand layout) by bulk copy; lands while A is being built ----
+        if (tid == 0) {
+            dt_expect_tx(b_full + buf, (uint32_t)b_bytes);
+            const unsigned char *src = p.w_image + (size_t)kb * b_bytes;
+            unsigned char *dst = Bs + buf * b_bytes;
+            const int half = b_bytes / 2;   // n_pad * 64: a multiple of 16 bytes, at most 16 KB per copy
+            dt_bulk_g2s(dst, src, (uint32_t)half, b_full + buf);
+            dt_bulk_g2s(dst + half, src + half, (uint32_t)half, b_full + buf);
+        }
+        // ---- A tile: 128 rows x 8 chunks of 8 bf16; thread -> (row, chunk), 8 consecutive threads per row.  All 16
+        //      loads of a thread are issued before the first is used (the block costs one memory round trip). ----
         unsigned char *a = As + buf * 16384;
+        const float *src[8];
+        bool ok[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int e = it * kDtThreads + tid;
             const int r = e >> 3, c = e & 7;
             const int kk = kb * kDtKB + c * 8;      // f1 and f2 are multiples of 8: a chunk never straddles the sources
-            const float *src = nullptr;
-            if (kk < p.f1) {
-                src = row1[r];
-                if (src) src += kk;
-            } else if (kk < k_total) {
-                src = row2[r];
-                if (src) src += kk - p.f1;
-            }
-            uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-            if (src) {
-                const float4 v0 = ldg4(src), v1 = ldg4(src + 4);
-                packed.x = tc::pack_bf16x2(v0.x, v0.y);
-                packed.y = tc::pack_bf16x2(v0.z, v0.w);
-                packed.z = tc::pack_bf16x2(v1.x, v1.y);
-                packed.w = tc::pack_bf16x2(v1.z, v1.w);
-            }
-            *reinterpret_cast<uint4 *>(a + tc::sw128_offset(r, c)) = packed;
+            ok[it] = kk < k_total;
+            src[it] = !ok[it] ? p.x1 : (kk < p.f1 ? row1[r] + kk : row2[r] + (kk - p.f1));
         }
-        // ---- B tile: block kb of the image, already in operand layout ----
-        {
-            const int4 *src = reinterpret_cast<const int4 *>(p.w_image + (size_t)kb * b_bytes);
-            int4 *dst = reinterpret_cast<int4 *>(Bs + buf * b_bytes);
-            for (int e = tid; e < n_pad * 8; e += kDtThreads) dst[e] = __ldg(src + e);
+        float4 v[16];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            v[2 * it] = dt_ld_stream4(src[it]);
+            v[2 * it + 1] = dt_ld_stream4(src[it] + 4);
+        }
+        // scheduling fence: ptxas otherwise interleaves conversions with the loads and each pair of loads waits for the
+        // previous pair's round trip.  One operand of every conversion ORs in a (run-time) zero derived from ALL 16
+        // loads, so no conversion can be scheduled before every load has been issued.
+        uint32_t z = 0u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) z ^= __float_as_uint(v[j].x);
+        z &= zero_rt;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int e = it * kDtThreads + tid;
+            const int r = e >> 3, c = e & 7;
+            const float4 v0 = v[2 * it], v1 = v[2 * it + 1];
+            uint4 packed = make_uint4(tc::pack_bf16x2(dt_or(v0.x, z), v0.y), tc::pack_bf16x2(dt_or(v0.z, z), v0.w),
+                                      tc::pack_bf16x2(dt_or(v1.x, z), v1.y), tc::pack_bf16x2(dt_or(v1.z, z), v1.w));
+            if (!ok[it]) packed = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4 *>(a + tc::sw128_offset(r, c)) = packed;
         }
         tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core
         tc::tc_fence_before_sync();
         __syncthreads();
         if (tid == 0) {
+            tc::mbar_wait(b_full + buf, (uint32_t)use & 1u);
             tc::tc_fence_after_sync();
 #pragma unroll
             for (int s = 0; s < 4; ++s) {           // 4 x K=16 inside the 64-wide block (zero padded past k_total)
@@ -151,11 +185,11 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
                 tc::mma_bf16_ss(tmem_base, tc::smem_desc_sw128(a_addr + buf * 16384 + koff),
                                 tc::smem_desc_sw128(b_addr + buf * b_bytes + koff), idesc, (kb > 0 || s > 0) ? 1u : 0u);
             }
-            tc::mma_commit(mbar + buf);
+            tc::mma_commit(mma_done + buf);
         }
     }
-    // the last commit covers every MMA issued before it
-    tc::mbar_wait(mbar + ((kb_count - 1) & 1), (uint32_t)((kb_count - 1) >> 1) & 1u);
+    // the last commit covers every MMA issued before it (and every bulk copy was waited for before its MMAs)
+    tc::mbar_wait(mma_done + ((kb_count - 1) & 1), (uint32_t)((kb_count - 1) >> 1) & 1u);
     tc::tc_fence_after_sync();
 
     // ---- epilogue: accumulator row `tid` -> bias, activation, fp32 row ----
@@ -169,10 +203,7 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
         if (m < p.m) {
             float o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = cb + j;
-                o[j] = dt_act(__uint_as_float(v[j]) + ((p.b && col < p.n) ? __ldg(p.b + col) : 0.f), p.act);
-            }
+            for (int j = 0; j < 16; ++j) o[j] = dt_act(__uint_as_float(v[j]) + bias_s[cb + j], p.act);
             if (vec_ok && cb + 16 <= p.n) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
@@ -193,7 +224,7 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
 }
 
 static size_t dense_tc_smem_bytes(int n_pad) {
-    return 2 * 16384 + 2 * (size_t)n_pad * 128 + 2 * kDtRows * sizeof(void *) + 2 * sizeof(uint64_t) + 16;
+    return 2 * 16384 + 2 * (size_t)n_pad * 128 + 2 * kDtRows * sizeof(void *) + 4 * sizeof(uint64_t) + (size_t)n_pad * 4 + 16;
 }
 
 }  // namespace cbrs
@@ -236,7 +267,7 @@ extern "C" int cbrs_dense_tc(const float *x1, int64_t ld1, const int64_t *idx1, 
     const size_t smem = dense_tc_smem_bytes(n_pad);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 101 * 1024);
         CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "cbrs_dense_tc: %s", cudaGetErrorString(e));
         attr_set = true;
     }
