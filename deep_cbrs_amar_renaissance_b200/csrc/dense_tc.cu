@@ -11,7 +11,8 @@
 //     first is used) while one cp.async.bulk brings the matching block of the pre-swizzled bf16 image of W
 //     (cbrs_dense_tc_prepare) next to it, counted on an mbarrier the MMA-issuing thread waits on;
 //   * one thread issues four tcgen05.mma (M=128, N=n_pad, K=16) per block into ONE TMEM accumulator and commits to the
-//     block's mbarrier; tiles are double buffered, so the tensor core works on block b while the CTA builds b+1;
+//     block's mbarrier; tiles are double buffered, so the tensor core works on block b while the CTA builds b+1, and
+//     the fp32 rows of block b+1 are already on their way into a second register set while block b is converted;
 //   * thread t reads accumulator row t back with tcgen05.ld (warp w owns TMEM lanes 32w..32w+31), adds the bias,
 //     applies the activation and writes its fp32 output row.
 // HBM-side the kernel reads every A row once (fp32) and W once per CTA (L2 resident: <= 393 KB at 768 x 256).
@@ -77,7 +78,7 @@ __device__ __forceinline__ float4 dt_ld_stream4(const float *p) {   // read-once
     return v;
 }
 
-__global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_constant__ DenseTcParams p) {
+__global__ void __launch_bounds__(kDtThreads, 2) dense_tc_kernel(const __grid_constant__ DenseTcParams p) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];  // SWIZZLE_128B tiles need 1024-byte alignment
     const int n_pad = (p.n + 15) / 16 * 16;
     const int k_total = p.f1 + p.f2;
@@ -120,45 +121,30 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
     const uint32_t a_addr = tc::smem_u32(As), b_addr = tc::smem_u32(Bs);
     if ((a_addr & 1023u) != 0u) __trap();  // the runtime honours the declared alignment; fail loudly if not
     const uint32_t idesc = tc::idesc_bf16_f32(kDtRows, n_pad);
-    const uint32_t zero_rt = (uint32_t)p.n >> 20;   // 0 (n <= 256), but not to the compiler: see the scheduling fence below
+    const uint32_t zero_rt = (uint32_t)p.n >> 20;   // 0 (n <= 256), but not to the compiler: see finish()
 
-    for (int kb = 0; kb < kb_count; ++kb) {
-        const int buf = kb & 1, use = kb >> 1;
-        if (use > 0) {  // the MMAs that read this buffer pair two blocks ago must have completed
-            tc::mbar_wait(mma_done + buf, (uint32_t)(use - 1) & 1u);
-            tc::tc_fence_after_sync();
-        }
-        // ---- B tile: block kb of the image (already in operand layout) by bulk copy; lands while A is being built ----
-        if (tid == 0) {
-            dt_expect_tx(b_full + buf, (uint32_t)b_bytes);
-            const unsigned char *src = p.w_image + (size_t)kb * b_bytes;
-            unsigned char *dst = Bs + buf * b_bytes;
-            const int half = b_bytes / 2;   // n_pad * 64: a multiple of 16 bytes, at most 16 KB per copy
-            dt_bulk_g2s(dst, src, (uint32_t)half, b_full + buf);
-            dt_bulk_g2s(dst + half, src + half, (uint32_t)half, b_full + buf);
-        }
-        // ---- A tile: 128 rows x 8 chunks of 8 bf16; thread -> (row, chunk), 8 consecutive threads per row.  All 16
-        //      loads of a thread are issued before the first is used (the block costs one memory round trip). ----
-        unsigned char *a = As + buf * 16384;
+    // A tile of block kb: 128 rows x 8 chunks of 8 bf16; thread -> (row, chunk), 8 consecutive threads per row.
+    // issue(): all 16 loads of the thread (two float4 per chunk) go out back to back.
+    auto issue = [&](int kb, float4 (&v)[16]) {
         const float *src[8];
-        bool ok[8];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             const int e = it * kDtThreads + tid;
             const int r = e >> 3, c = e & 7;
             const int kk = kb * kDtKB + c * 8;      // f1 and f2 are multiples of 8: a chunk never straddles the sources
-            ok[it] = kk < k_total;
-            src[it] = !ok[it] ? p.x1 : (kk < p.f1 ? row1[r] + kk : row2[r] + (kk - p.f1));
+            src[it] = kk >= k_total ? p.x1 : (kk < p.f1 ? row1[r] + kk : row2[r] + (kk - p.f1));
         }
-        float4 v[16];
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
             v[2 * it] = dt_ld_stream4(src[it]);
             v[2 * it + 1] = dt_ld_stream4(src[it] + 4);
         }
-        // scheduling fence: ptxas otherwise interleaves conversions with the loads and each pair of loads waits for the
-        // previous pair's round trip.  One operand of every conversion ORs in a (run-time) zero derived from ALL 16
-        // loads, so no conversion can be scheduled before every load has been issued.
+    };
+    // finish(): convert to bf16 and store in operand layout.  Scheduling fence: ptxas otherwise interleaves conversions
+    // with the loads and each pair of loads waits for the previous pair's round trip - one operand of every conversion
+    // ORs in a (run-time) zero derived from ALL 16 loads, so no conversion is scheduled before every load was issued.
+    auto finish = [&](int kb, float4 (&v)[16]) {
+        unsigned char *a = As + (kb & 1) * 16384;
         uint32_t z = 0u;
 #pragma unroll
         for (int j = 0; j < 16; ++j) z ^= __float_as_uint(v[j].x);
@@ -170,9 +156,28 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
             const float4 v0 = v[2 * it], v1 = v[2 * it + 1];
             uint4 packed = make_uint4(tc::pack_bf16x2(dt_or(v0.x, z), v0.y), tc::pack_bf16x2(dt_or(v0.z, z), v0.w),
                                       tc::pack_bf16x2(dt_or(v1.x, z), v1.y), tc::pack_bf16x2(dt_or(v1.z, z), v1.w));
-            if (!ok[it]) packed = make_uint4(0u, 0u, 0u, 0u);
+            if (kb * kDtKB + c * 8 >= k_total) packed = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4 *>(a + tc::sw128_offset(r, c)) = packed;
         }
+    };
+    // one K block: B tile by bulk copy, prefetch of the NEXT block's A rows into the other register set (their round
+    // trip overlaps this block's conversion, barrier and MMA issue), conversion of this block, MMAs
+    auto block = [&](int kb, float4 (&cur)[16], float4 (&nxt)[16]) {
+        const int buf = kb & 1, use = kb >> 1;
+        if (use > 0) {  // the MMAs that read this buffer pair two blocks ago must have completed
+            tc::mbar_wait(mma_done + buf, (uint32_t)(use - 1) & 1u);
+            tc::tc_fence_after_sync();
+        }
+        if (tid == 0) {   // block kb of the image (already in operand layout); lands while A is being built
+            dt_expect_tx(b_full + buf, (uint32_t)b_bytes);
+            const unsigned char *src = p.w_image + (size_t)kb * b_bytes;
+            unsigned char *dst = Bs + buf * b_bytes;
+            const int half = b_bytes / 2;   // n_pad * 64: a multiple of 16 bytes, at most 16 KB per copy
+            dt_bulk_g2s(dst, src, (uint32_t)half, b_full + buf);
+            dt_bulk_g2s(dst + half, src + half, (uint32_t)half, b_full + buf);
+        }
+        if (kb + 1 < kb_count) issue(kb + 1, nxt);
+        finish(kb, cur);
         tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core
         tc::tc_fence_before_sync();
         __syncthreads();
@@ -186,6 +191,14 @@ __global__ void __launch_bounds__(kDtThreads) dense_tc_kernel(const __grid_const
                                 tc::smem_desc_sw128(b_addr + buf * b_bytes + koff), idesc, (kb > 0 || s > 0) ? 1u : 0u);
             }
             tc::mma_commit(mma_done + buf);
+        }
+    };
+    {
+        float4 va[16], vb[16];
+        issue(0, va);
+        for (int kb = 0; kb < kb_count; kb += 2) {
+            block(kb, va, vb);
+            if (kb + 1 < kb_count) block(kb + 1, vb, va);
         }
     }
     // the last commit covers every MMA issued before it (and every bulk copy was waited for before its MMAs)
