@@ -356,6 +356,17 @@ def run_b200(args):
                                    "tensor_flops_per_pair": 2 * CLF_UNITS[0] * CLF_UNITS[1],
                                    "frac_of_bf16_peak": pairs_tc / world * 2 * CLF_UNITS[0] * CLF_UNITS[1] / 1e12 / (peaks.get("bf16_tflops_sustained") or 1398.0)}},
     }
+    if world == 1:
+        # hybrid scorer towers (BASELINE config 4: Dense 768 -> 256 -> 64 over BERT rows, bf16): cbrs_dense_tc (tcgen05)
+        # next to the fp32 FFMA kernel, 2^20 rows (3.2 GB of fp32 input: larger than L2).  Reported, not part of `value`.
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("cbrs_dense_tc_bench", os.path.join(REPO, "tools", "dense_tc_bench.py"))
+            towers = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(towers)
+            line["hybrid_towers"] = towers.run(1 << 20)
+        except Exception as e:  # noqa: BLE001  (never let the side measurement take the headline line down)
+            line["hybrid_towers"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         r = cpu_reference_run(args.cpu_scale, 2, 1, threads)
