@@ -18,25 +18,12 @@
 // HBM-side the kernel reads every A row once (fp32) and W once per CTA (L2 resident: <= 393 KB at 768 x 256).
 // Precision: operands rounded to bf16 (nearest even), products and sums fp32 - the parity tests compare against an
 // oracle that rounds the same operands (tolerance stated there); the fp32 FFMA kernel stays the 1e-5 parity path.
-#include "common.cuh"
-#include "tc05.cuh"
+#include "dense_tc.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace cbrs {
-
-constexpr int kDtThreads = 128;
-constexpr int kDtRows = 128;   // output rows per CTA = MMA M
-constexpr int kDtKB = 64;      // K elements per block = one 128-byte swizzle row
-
-struct DenseTcParams {
-    const float *x1; int64_t ld1; const int64_t *idx1; int32_t f1;
-    const float *x2; int64_t ld2; const int64_t *idx2; int32_t f2;
-    const uint8_t *w_image;   // [kb][n_pad][128 B] bf16, SWIZZLE_128B
-    const float *b;
-    int64_t m; int32_t n; int32_t act;
-    float *out; int64_t ldo;
-};
 
 // W [k, n] fp32 (Keras [in,out]) -> B operand image: element (col, kk) = bf16(W[kk][col]), K-major, SWIZZLE_128B,
 // zero padded to n_pad columns and kb_count * 64 rows of K
@@ -51,31 +38,6 @@ __global__ void dense_tc_prep_kernel(const float *__restrict__ w, int k, int n, 
         const uint32_t off = (uint32_t)kb * n_pad * 128 + tc::sw128_offset(col, kk >> 3) + (kk & 7) * 2;
         *reinterpret_cast<__nv_bfloat16 *>(image + off) = __float2bfloat16_rn(v);
     }
-}
-
-__device__ __forceinline__ float dt_act(float v, int act) {
-    switch (act) {
-        case CBRS_ACT_RELU: return fmaxf(v, 0.f);
-        case CBRS_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
-        case CBRS_ACT_TANH: return tanhf(v);
-        default: return v;
-    }
-}
-
-// 1-D bulk copy global -> shared through the async proxy (TMA engine), completion counted in bytes on an mbarrier
-__device__ __forceinline__ void dt_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void dt_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(tc::smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(tc::smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ float dt_or(float v, uint32_t z) { return __uint_as_float(__float_as_uint(v) | z); }
-__device__ __forceinline__ float4 dt_ld_stream4(const float *p) {   // read-once rows: keep them out of L1
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
 }
 
 __global__ void __launch_bounds__(kDtThreads, 2) dense_tc_kernel(const __grid_constant__ DenseTcParams p) {
@@ -288,6 +250,8 @@ extern "C" int cbrs_dense_tc(const float *x1, int64_t ld1, const int64_t *idx1, 
     p.x1 = x1; p.ld1 = ld1; p.idx1 = idx1; p.f1 = f1;
     p.x2 = x2; p.ld2 = ld2; p.idx2 = idx2; p.f2 = f2;
     p.w_image = (const uint8_t *)w_image; p.b = b; p.m = m; p.n = n; p.act = act; p.out = out; p.ldo = ldo;
+    static const int variant = getenv("CBRS_DENSE_TC_VARIANT") ? atoi(getenv("CBRS_DENSE_TC_VARIANT")) : 3;
+    if (variant == 4) return dense_tc_launch_x(p, (cudaStream_t)stream);   // experimental, see dense_tc_x.cu
     dense_tc_kernel<<<(unsigned)cdiv(m, kDtRows), kDtThreads, smem, (cudaStream_t)stream>>>(p);
     CBRS_CHECK_LAUNCH("cbrs_dense_tc");
     return CBRS_OK;

@@ -3,6 +3,10 @@ rounds the same operands to bf16 and sums in float64.  Tolerance 1e-4 of the out
 accumulation order inside the tensor core is not specified; a layout or descriptor bug gives O(1) errors).
 Model level: a hybrid model with set_scorer_precision('bf16') against the same rounding oracle, and against its own
 fp32 scores within 2e-2."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -126,3 +130,13 @@ def test_hybrid_scorer_on_tensor_cores():
     x2 = stack(np.concatenate([ub, ib], 1), w["dense3b"])
     want = stack(np.concatenate([x1, x2], 1), w["clf"], last="sigmoid")
     close(got, want, "bf16 hybrid scores", rtol=2e-3)   # bf16 re-rounding of near-tie activations between layers
+
+
+@pytest.mark.skipif(os.environ.get("CBRS_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental kernel variant (csrc/dense_tc_x.cu), not yet run on a GPU: opt in with CBRS_TEST_EXPERIMENTAL=1")
+def test_experimental_variant():
+    """the same parity cases through CBRS_DENSE_TC_VARIANT=4 (read once per process, hence the child process)"""
+    env = dict(os.environ, CBRS_DENSE_TC_VARIANT="4", CBRS_TEST_EXPERIMENTAL="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
+                        "single_source or gather_concat or hybrid_scorer"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
