@@ -86,6 +86,8 @@ def top_k_metrics(test_filepath, predictions_path, relevance_threshold=1, sep='\
                                          cutoff, relevance_threshold) for f in preds]
         res = {m: float(np.mean([r[m] for r in rows])) for m in ("precision", "recall", "f1")}
         with open(os.path.join(root, "results.tsv"), "w") as fp:
-            fp.write("cutoff\tprecision\trecall\tf1\n%d\t%.6f\t%.6f\t%.6f\n" % (cutoff, res["precision"], res["recall"], res["f1"]))
+            # one headerless row (label, precision, recall, f1): what the reference's caller reads back with
+            # read_csv(header=None).drop(0, axis=1).squeeze() -> [P, R, F1]  (experiment.py:211-213)
+            fp.write("top_%d\t%.6f\t%.6f\t%.6f\n" % (cutoff, res["precision"], res["recall"], res["f1"]))
         out[cutoff] = res
     return out

@@ -8,6 +8,7 @@ import os
 import sys
 import types
 
+import numpy as np
 import pytest
 
 from deep_cbrs_amar_renaissance_b200 import experiment as ex
@@ -105,3 +106,76 @@ def test_multi_experimenter_lists_the_reference_grid(tmp_path, capsys):
     assert len(m.experiments) == 90   # 6 grids x 5 families x 3 l2 values (econfigs/basic-gnn.yaml)
     first = next(iter(m.experiments.values()))
     assert first["model"]["name"] == "basic.BasicGCN" and first["dataset"]["load_function_name"] == "load_user_item_graph"
+
+
+@needs_reference
+def test_log_callback_times_the_same_batches_as_the_reference(monkeypatch):
+    """utilities/keras.py:LogCallback is the reference's only timing instrumentation; its trace flags make it time every
+    batch from index 500 of the first epoch on (the closing branch is unreachable once tracing started).  The
+    reference's own class, imported unmodified over in-test stand-ins for mlflow / keras, and ours are driven through the
+    same two epochs with a scripted clock and must record the same batch times and training time."""
+    import importlib.util
+    import logging
+    import time
+
+    from deep_cbrs_amar_renaissance_b200.utilities import keras as ours
+
+    logged = {}
+    fake = {"mlflow": types.ModuleType("mlflow"), "keras": types.ModuleType("keras"), "keras.utils": types.ModuleType("keras.utils"),
+            "keras.utils.layer_utils": types.ModuleType("keras.utils.layer_utils"), "tensorflow": types.ModuleType("tensorflow"),
+            "tensorflow.keras": types.ModuleType("tensorflow.keras")}
+    fake["mlflow"].log_metric = lambda k, v, **kw: logged.__setitem__(k, v)
+    fake["mlflow"].log_metrics = lambda d, **kw: None
+    fake["keras.utils.layer_utils"].count_params = lambda ws: int(sum(int(w.numel()) for w in ws))
+    fake["tensorflow.keras"].callbacks = types.SimpleNamespace(Callback=object)
+    fake["tensorflow"].keras = fake["tensorflow.keras"]
+    for name, mod in fake.items():
+        monkeypatch.setitem(sys.modules, name, mod)
+    spec = importlib.util.spec_from_file_location("reference_utilities_keras", os.path.join(REF, "src", "utilities", "keras.py"))
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+
+    now = [0.0]
+    monkeypatch.setattr(time, "perf_counter", lambda: now[0])
+    monkeypatch.setattr(ours, "_device_sync", lambda: None)
+    log = logging.getLogger("cbrs.test.logcallback")
+    log.addHandler(logging.NullHandler())
+    log.propagate = False
+    cbs = [ref.LogCallback(log, 100), ours.LogCallback(log, 100)]
+    t = 0.0
+    for cb in cbs:
+        now[0] = 5.0
+        cb.on_train_begin({})
+    for epoch in range(2):
+        for cb in cbs:
+            cb.on_epoch_begin(epoch, {})
+        for b in range(530):
+            dur = 1.0 + 0.001 * b + 10.0 * epoch
+            for cb in cbs:
+                now[0] = t
+                cb.on_train_batch_begin(b, {})
+                now[0] = t + dur
+                cb.on_train_batch_end(b, {})
+            t += dur + 0.25
+        for cb in cbs:
+            cb.on_epoch_end(epoch, {"loss": 0.5, "accuracy": 0.7})
+    for cb in cbs:
+        now[0] = 5.0 + t
+        cb.on_train_end({})
+    assert len(cbs[0].batch_times) == 30 + 530
+    assert np.allclose(cbs[0].batch_times, cbs[1].batch_times, rtol=0, atol=1e-9)
+    assert abs(cbs[0].get_batch_time() - cbs[1].get_batch_time()) < 1e-12
+    assert abs(logged["batch_time"] - cbs[1].get_batch_time()) < 1e-12      # what the reference sends to MLflow
+    assert abs(logged["training_time"] - cbs[1].training_time) < 1e-9
+
+    class W:   # parameter counting (keras.py:10-22)
+        def __init__(self, n):
+            self.n = n
+
+        def numel(self):
+            return self.n
+
+    class Model:
+        trainable_weights, non_trainable_weights = [W(12), W(5)], [W(2)]
+
+    assert ref.get_total_parameters(Model()) == ours.get_total_parameters(Model()) == (17, 2)

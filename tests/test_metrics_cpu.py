@@ -24,4 +24,9 @@ def test_top_k_metrics_writes_results(tmp_path):
     np.savetxt(d / "predictions_1.tsv", np.array([[1, 10, 0.9], [1, 11, 0.8], [2, 10, 0.7]]), fmt="%g", delimiter="\t")
     out = top_k_metrics(str(tmp_path / "test.tsv"), str(tmp_path / "preds"))
     assert abs(out[5]["recall"] - 1.0) < 1e-12 and abs(out[5]["precision"] - (2 / 5 + 1 / 5) / 2) < 1e-12
-    assert (d / "results.tsv").read_text().startswith("cutoff\tprecision")
+    # read back exactly as the reference's Experimenter.evaluate does (experiment.py:211-213)
+    import pandas as pd
+    results = pd.read_csv(d / "results.tsv", sep='\t', header=None)
+    results = results.drop(0, axis=1).to_numpy().squeeze()
+    assert results.shape == (3,) and abs(results[0] - out[5]["precision"]) < 1e-6 and abs(results[1] - 1.0) < 1e-6
+    assert abs(results[2] - out[5]["f1"]) < 1e-6
