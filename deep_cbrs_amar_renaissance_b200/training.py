@@ -176,14 +176,16 @@ def hybrid_rs_train(tape, rs, ug, ig, ub, ib):
 # ------------------------------------------------------------------ GNN layers
 def _gcn_train(tape, layer, x_node, graph, out):
     """GCNConv / RGCNConv: y = act(A_hat (x W) + b).  Backward: dPre = dY*act'(y); db = colsum dPre;
-    dZ = A_hat dPre (A_hat symmetric; for the relational operator the per-relation blocks of its
-    transpose are the same operator on the stacked layout, see below); dW = x^T dZ; dx = dZ W^T."""
+    dZ = A_hat dPre (A_hat symmetric); dW = x^T dZ; dx = dZ W^T.
+    Relational operator (stacked layout: column r*N + j carries relation r): dZ_r = A_hat_r^T dPre = A_hat_r dPre when
+    every relation's block is symmetric (relation tags of (i,j) and (j,i) agree, as for relations defined by node
+    ranges on a symmetrised graph), which is one pass of the same sparse kernel per relation over a stacked operand
+    that is dPre in block r and zero elsewhere.  EXPERIMENTAL: the relational backward has not run on a GPU yet
+    (tests/test_zz_gpu_kg_training.py::test_rgcn_gradients, opt-in with CBRS_TEST_EXPERIMENTAL=1)."""
     x = x_node.x
     csr = graph.norm
     n = x.shape[0]
     relational = isinstance(layer, RGCNConv)
-    if relational:
-        raise NotImplementedError("training the relational extension needs the transposed per-relation operator")
     kernels = layer.kernels if relational else [layer.kernel]
     z = torch.empty(len(kernels) * n, layer.channels, dtype=torch.float32, device=x.device)
     for r, w in enumerate(kernels):
@@ -197,11 +199,24 @@ def _gcn_train(tape, layer, x_node, graph, out):
         dpre = ops.act_grad(node.grad, y, layer.activation)
         if layer.bias is not None:
             tape.wgrad(layer.bias, ops.colsum(dpre))
-        dz = torch.empty(n, layer.channels, dtype=torch.float32, device=x.device)
-        ops.spmm(csr, dpre, dz)
-        dw, _ = ops.dense_grad_w(x, dz, want_bias=False)
-        tape.wgrad(layer.kernel, dw)
-        x_node.add_grad(ops.dense(dz, ops.transpose(layer.kernel)))
+        if not relational:
+            dz = torch.empty(n, layer.channels, dtype=torch.float32, device=x.device)
+            ops.spmm(csr, dpre, dz)
+            dw, _ = ops.dense_grad_w(x, dz, want_bias=False)
+            tape.wgrad(layer.kernel, dw)
+            x_node.add_grad(ops.dense(dz, ops.transpose(layer.kernel)))
+            return
+        dx = None
+        for r, w in enumerate(kernels):
+            stacked = torch.zeros(len(kernels) * n, layer.channels, dtype=torch.float32, device=x.device)
+            stacked[r * n:(r + 1) * n].copy_(dpre)
+            dz = torch.empty(n, layer.channels, dtype=torch.float32, device=x.device)
+            ops.spmm(csr, stacked, dz)
+            dw, _ = ops.dense_grad_w(x, dz, want_bias=False)
+            tape.wgrad(w, dw)
+            t = ops.dense(dz, ops.transpose(w))
+            dx = t if dx is None else ops.axpby(dx, 1.0, t, 1.0)
+        x_node.add_grad(dx)
 
     tape.ops.append(bwd)
     return node

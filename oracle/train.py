@@ -36,6 +36,8 @@ def _operator(kind, graph, n, dtype):
     """the propagation operator of one SequentialGNN as torch tensors"""
     if kind in ("gcn", "lightgcn", "dgcf"):
         return dict(a=_csr_torch(graph.indptr, graph.indices, graph.data, n, dtype))
+    if kind == "rgcn":   # graph = one scipy CSR per relation (blocks of the normalised adjacency)
+        return dict(a=[_csr_torch(g.indptr, g.indices, g.data, n, dtype) for g in graph])
     if kind == "gat":
         from .graph import gat_edges
         gptr, gcols = gat_edges(np.asarray(graph[0]), np.asarray(graph[1]))
@@ -58,6 +60,14 @@ def _propagate(kind, x, layers, graph, final_node, aggregate, leaves, reg, prefi
             b = leaves[prefix + "layers.%d.bias" % li] = _t(lw["bias"], dtype)
             reg += [k, b]
             x = torch.relu(torch.sparse.mm(a, x @ k) + b)
+        elif kind == "rgcn":   # relational extension: relu(sum_r A_r (x W_r) + b), oracle.layers.rgcn_conv
+            ks = []
+            for r in range(len(a)):
+                ks.append(_t(lw["kernel_%d" % r], dtype))
+                leaves[prefix + "layers.%d.kernel_%d" % (li, r)] = ks[-1]
+            b = leaves[prefix + "layers.%d.bias" % li] = _t(lw["bias"], dtype)
+            reg += ks + [b]
+            x = torch.relu(sum(torch.sparse.mm(a_r, x @ k_r) for a_r, k_r in zip(a, ks)) + b)
         elif kind == "lightgcn":
             x = torch.sparse.mm(a, x)
         elif kind == "dgcf":

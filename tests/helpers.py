@@ -145,3 +145,13 @@ def kg_model(case, graphs, n_users, n_items):
         kw.update(final_node="mean", aggregate="sum")
     adjs = graphs if "TW" in name else graphs[:2]
     return getattr(hybrid if name.startswith("Hybrid") else basic, name)(n_users, n_items, adjs, **kw), kw
+
+
+def relation_blocks(a_hat, first_rel1_node):
+    """The normalised adjacency split into the two relations of SURVEY row R by node range: an entry belongs to
+    relation 1 when it touches a node >= first_rel1_node (item <-> property links), else to relation 0; self loops ride
+    on relation 0 (the device build's self_rel).  Returns [A_0, A_1] as scipy CSR."""
+    coo = a_hat.tocoo()
+    is_r1 = (coo.row >= first_rel1_node) | (coo.col >= first_rel1_node)
+    is_r1 = np.where(coo.row == coo.col, False, is_r1)
+    return [sparse.csr_matrix((coo.data[pick], (coo.row[pick], coo.col[pick])), shape=coo.shape) for pick in (~is_r1, is_r1)]

@@ -28,6 +28,9 @@ def _weights(kind, rng, n, d=6, hybrid=False, tweak=None):
         elif kind == "gat":
             layers.append(dict(kernel=glorot(rng, (d, d)), bias=(rng.standard_normal(d) * 0.1).astype(np.float32),
                                attn_self=glorot(rng, (d, 1)).reshape(-1), attn_neigh=glorot(rng, (d, 1)).reshape(-1)))
+        elif kind == "rgcn":
+            layers.append(dict(kernel_0=glorot(rng, (d, d)), kernel_1=glorot(rng, (d, d)),
+                               bias=(rng.standard_normal(d) * 0.1).astype(np.float32)))
         elif kind == "dgcf":
             layers.append({"locality_adaptive/locality-adaptive-weights": (1 + 0.3 * rng.standard_normal((n, 1))).astype(np.float32)})
         else:
@@ -69,13 +72,16 @@ def _to64(x):
 def _graph(kind, adj):
     if kind in ("gcn", "lightgcn"):
         return og.gcn_filter(adj)
+    if kind == "rgcn":   # two relations by node range: edges touching the last third of the nodes are relation 1
+        from tests.helpers import relation_blocks
+        return relation_blocks(og.gcn_filter(adj), adj.shape[0] - adj.shape[0] // 3)
     if kind == "dgcf":
         return ol.dgcf_preprocess(adj)[0]
     ptr, idx, _ = og.reorder_raw(adj)
     return (ptr, idx)
 
 
-CASES = [("gcn", False, None), ("sage", False, None), ("gat", False, None), ("lightgcn", False, None), ("dgcf", False, None),
+CASES = [("gcn", False, None), ("rgcn", False, None), ("sage", False, None), ("gat", False, None), ("lightgcn", False, None), ("dgcf", False, None),
          ("gcn", True, None), ("gcn", True, "attention"), ("gcn", True, "residual")]
 
 
@@ -100,7 +106,8 @@ def test_autograd_matches_finite_differences(kind, hybrid, tweak):
     # probe a few entries of a few tensors (the embeddings always, plus every other leaf kind present)
     probes = [("embeddings", w["embeddings"])]
     lw = w["layers"][0]
-    for key, leaf in (("kernel", "layers.0.kernel"), ("bias", "layers.0.bias"), ("attn_self", "layers.0.attn_kernel_self"),
+    for key, leaf in (("kernel", "layers.0.kernel"), ("kernel_1", "layers.0.kernel_1"), ("bias", "layers.0.bias"),
+                      ("attn_self", "layers.0.attn_kernel_self"),
                       ("locality_adaptive/locality-adaptive-weights", "layers.0.locality_adaptive/locality-adaptive-weights")):
         if key in lw:
             probes.append((leaf, lw[key]))

@@ -132,3 +132,37 @@ def test_kg_train_steps_reduce_the_loss_and_replay_matches_eager(case, graphs):
     assert eager == replay
     for a, b in zip(w_eager, w_replay):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CBRS_TEST_EXPERIMENTAL") != "1",
+                    reason="relational backward written after the round's last GPU session: opt in with CBRS_TEST_EXPERIMENTAL=1")
+def test_rgcn_gradients():
+    """training step of the relational extension (row R): one sparse pass per relation over a stacked operand"""
+    from deep_cbrs_amar_renaissance_b200 import training
+    from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
+    from oracle import graph as og
+    from tests.helpers import export_weights, random_bipartite, relation_blocks
+    from tests.test_gpu_models import GRIDS, _build
+    from tests.test_gpu_training import _named_grads
+    n_users, n_items, n_props = 100, 80, 50
+    adj = random_bipartite(n_users, n_items, 2000, seed=5, n_props=n_props, n_links=300, dup_links=30)
+    dev = torch.device("cuda", 0)
+    row, col = torch.from_numpy(adj.row).to(dev), torch.from_numpy(adj.col).to(dev)
+    rel_np = ((adj.row >= n_users + n_items) | (adj.col >= n_users + n_items)).astype(np.int32)
+    g2 = DeviceGraph(row, col, torch.from_numpy(adj.data).to(dev), adj.shape[0], rel=torch.from_numpy(rel_np).to(dev), n_rel=2)
+    model = _build("BasicRGCN", g2, GRIDS[1])
+    u, i, y = _batch(n_users, n_items, 256, 3)
+    model((u, i))
+    _randomise(model, seed=5)
+    named = {n: w.detach().cpu().numpy() for n, w in model.named_weights()}
+    w = export_weights(model)
+    for l, lw in enumerate(w["layers"]):   # export_weights knows 'kernel'; the relational layer names them kernel_<r>
+        for r in range(2):
+            lw["kernel_%d" % r] = named["gnn/gnn_layers/seq_layers.%d/kernel_%d" % (l, r)]
+    tape, loss, _, probs = training.forward_backward(model, (u, i), y)
+    want, want_loss, want_p = ot.gradients("rgcn", w, relation_blocks(og.gcn_filter(adj), n_users + n_items), (u, i), y)
+    assert_close(probs.cpu().numpy().reshape(-1), want_p, rtol=2e-5, what="rgcn probabilities")
+    got = _named_grads(model, tape)
+    assert set(got) == set(want), sorted(set(got) ^ set(want))
+    for k in sorted(want):
+        assert_grad_close(got[k], want[k], "rgcn grad %s" % k)
