@@ -9,7 +9,6 @@ import abc
 import numpy as np
 import torch
 
-from .. import ops
 from ..keras_like import Model, default_device
 from .dense import build_dense_classifier, build_dense_network
 from .gnn import GAT, GCN, DGCF, RGCN, GraphSage, LightGCN

@@ -8,10 +8,7 @@ kept, and `set_content_table` adds the B200 form: the [N,768] table is uploaded 
 and the rows are gathered inside the first Dense kernel from the ids alone."""
 import abc
 
-import numpy as np
-import torch
-
-from ..keras_like import Model, default_device
+from ..keras_like import Model
 from ..layers.fusion import FusionLayer
 from .basic import _ids, _rows
 from .. import ops
