@@ -23,7 +23,7 @@ class CsrDesc(Structure):
         ("chunk_edges", c_int32), ("n_chunks", c_int64),
         ("chunk_row", c_void_p), ("chunk_begin", c_void_p), ("chunk_slot", c_void_p),
         ("n_heavy", c_int64), ("heavy_row", c_void_p), ("heavy_slot_ptr", c_void_p),
-        ("n_slots", c_int64),
+        ("n_slots", c_int64), ("chunk_len", c_void_p),
     ]
 
 
@@ -38,6 +38,10 @@ _SIGS = {
     "cbrs_chunks_workspace_bytes": (c_size_t, [c_int64]),
     "cbrs_chunks_count": (c_int, [P, c_int64, c_int32, P, P, c_size_t, P]),
     "cbrs_chunks_fill": (c_int, [P, c_int64, c_int32, P, P, P, P, P, P, c_size_t, P]),
+    "cbrs_chunks_blocked_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int64]),
+    "cbrs_chunks_blocked_count": (c_int, [P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int64, P, P, c_size_t, P]),
+    "cbrs_chunks_blocked_fill": (c_int, [P, P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int64, P, P, P, P, P, P, P,
+                                         c_size_t, P]),
     "cbrs_spmm_workspace_bytes": (c_size_t, [POINTER(CsrDesc), c_int32]),
     "cbrs_spmm_csr": (c_int, [POINTER(CsrDesc), P, c_int64, P, c_int64, c_int32, c_int, P, c_int, c_int, P, c_size_t, P]),
     "cbrs_gat_workspace_bytes": (c_size_t, [POINTER(CsrDesc), c_int32]),

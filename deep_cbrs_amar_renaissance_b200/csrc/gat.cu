@@ -20,6 +20,7 @@ struct GatParams {
     const int32_t *chunk_row;
     const int64_t *chunk_begin;
     const int32_t *chunk_slot;
+    const int32_t *chunk_len;
     int64_t n_chunks;
     int32_t chunk_edges;
     int64_t row_offset;
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kGatThreads, 4) gat_chunk_kernel(const GatPara
     const int64_t grow = row + p.row_offset;
     const int64_t row_b = p.rowptr[row], row_e = p.rowptr[row + 1];
     const int64_t b = p.chunk_begin[gid];
-    const int64_t e = (b + p.chunk_edges < row_e) ? b + p.chunk_edges : row_e;
+    const int64_t e = p.chunk_len ? b + p.chunk_len[gid] : ((b + p.chunk_edges < row_e) ? b + p.chunk_edges : row_e);
     const int32_t slot = p.chunk_slot[gid];
     const bool first = (b == row_b);  // the first chunk of a row carries the self edge
     const float pi = __ldg(p.p + grow);
@@ -249,7 +250,7 @@ static int gat_impl(const cbrs_csr_t *g, int64_t row_offset, const float *z, int
         CBRS_REQUIRE(workspace && p.part_acc && p.part_ms, CBRS_E_WORKSPACE, "gat: workspace too small");
     }
     p.rowptr = g->rowptr; p.colidx = g->colidx; p.chunk_row = g->chunk_row; p.chunk_begin = g->chunk_begin;
-    p.chunk_slot = g->chunk_slot; p.n_chunks = g->n_chunks; p.chunk_edges = g->chunk_edges; p.row_offset = row_offset;
+    p.chunk_slot = g->chunk_slot; p.chunk_len = g->chunk_len; p.n_chunks = g->n_chunks; p.chunk_edges = g->chunk_edges; p.row_offset = row_offset;
     p.z = z; p.ldz = ldz; p.p = pvec; p.q = qvec; p.y = y; p.ldy = ldy; p.h = h; p.bias = bias; p.relu = relu;
     p.heavy_row = g->heavy_row; p.heavy_slot_ptr = g->heavy_slot_ptr; p.n_heavy = g->n_heavy;
     p.n_peer = n_peers;

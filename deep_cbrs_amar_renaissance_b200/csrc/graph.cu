@@ -232,6 +232,127 @@ __global__ void chunk_fill_kernel(const int64_t *__restrict__ rowptr, int64_t n_
     }
 }
 
+
+// ------------------------------------------------------------------ column-blocked chunks
+// Rows with at least block_min_len edges are cut where their (ascending) column ids cross a multiple of block_cols,
+// and every such segment further into pieces of at most chunk_edges edges.  All their chunks are scheduled AFTER the
+// ordinary rows' chunks and ordered by (column block, row): CTAs are dispatched in chunk order, so at any moment the
+// resident warps gather from one window of block_cols operand rows, which stays in L2 (block_cols * D * 4 bytes)
+// instead of streaming the whole operand table from HBM once per edge.  The cut points depend on the row's own
+// column ids and on (block_cols, chunk_edges) only, so the reduction tree of a row - partials added in ascending
+// column order by the heavy-row kernel - is the same on every launch shape and every row partition.
+__device__ __forceinline__ int64_t lower_bound_col(const int32_t *__restrict__ colidx, int64_t lo, int64_t hi, int64_t key) {
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        if ((int64_t)colidx[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void blocked_classify_kernel(const int64_t *__restrict__ rowptr, int64_t n_rows, int32_t chunk_edges,
+                                        int32_t block_min_len, int64_t *__restrict__ chunk_off,
+                                        int64_t *__restrict__ heavy_off, int64_t *__restrict__ slot_off,
+                                        int64_t *__restrict__ blk_idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t len = rowptr[i + 1] - rowptr[i];
+    const bool blocked = len >= block_min_len;
+    const int64_t nc = len <= chunk_edges ? 1 : (len + chunk_edges - 1) / chunk_edges;
+    blk_idx[i] = blocked ? 1 : 0;
+    chunk_off[i] = blocked ? 0 : nc;
+    heavy_off[i] = (blocked || nc > 1) ? 1 : 0;
+    slot_off[i] = blocked ? 0 : (nc > 1 ? nc : 0);  // blocked rows: filled in by blocked_count_kernel
+}
+
+// hdr[0] = number of blocked rows (from the scan of the flags); mat is [n_blocks][hdr[0]], column-block major
+__global__ void blocked_count_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, int64_t n_rows,
+                                     int32_t chunk_edges, int32_t block_min_len, int64_t block_cols, int64_t n_blocks,
+                                     const int64_t *__restrict__ blk_idx, const int64_t *__restrict__ hdr,
+                                     int64_t *__restrict__ mat, int64_t *__restrict__ slot_off) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t b = rowptr[i], e = rowptr[i + 1];
+    if (e - b < block_min_len) return;
+    const int64_t nb = hdr[0], j = blk_idx[i];
+    int64_t lo = b, total = 0;
+    for (int64_t cb = 0; cb < n_blocks; ++cb) {
+        const int64_t hi = (cb + 1 == n_blocks) ? e : lower_bound_col(colidx, lo, e, (cb + 1) * block_cols);
+        const int64_t n = (hi - lo + chunk_edges - 1) / chunk_edges;
+        mat[cb * nb + j] = n;
+        total += n;
+        lo = hi;
+    }
+    slot_off[i] = total;
+}
+
+// ordinary rows exactly as chunk_fill_kernel (plus the explicit length); blocked rows only register as heavy
+__global__ void blocked_fill_plain_kernel(const int64_t *__restrict__ rowptr, int64_t n_rows, int32_t chunk_edges,
+                                          int32_t block_min_len, const int64_t *__restrict__ chunk_off,
+                                          const int64_t *__restrict__ heavy_off, const int64_t *__restrict__ slot_off,
+                                          int32_t *__restrict__ chunk_row,
+                                          int64_t *__restrict__ chunk_begin, int32_t *__restrict__ chunk_len,
+                                          int32_t *__restrict__ chunk_slot, int32_t *__restrict__ heavy_row,
+                                          int64_t *__restrict__ heavy_slot_ptr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t b = rowptr[i], len = rowptr[i + 1] - b;
+    const bool blocked = len >= block_min_len;
+    const int64_t s0 = slot_off[i];
+    if (!blocked) {
+        const int64_t nc = len <= chunk_edges ? 1 : (len + chunk_edges - 1) / chunk_edges;
+        const int64_t c0 = chunk_off[i];
+        for (int64_t k = 0; k < nc; ++k) {
+            const int64_t cb = b + k * chunk_edges;
+            chunk_row[c0 + k] = (int32_t)i;
+            chunk_begin[c0 + k] = cb;
+            chunk_len[c0 + k] = (int32_t)((len - k * chunk_edges < chunk_edges) ? len - k * chunk_edges : chunk_edges);
+            chunk_slot[c0 + k] = nc > 1 ? (int32_t)(s0 + k) : -1;
+        }
+        if (nc <= 1) return;
+    }
+    const int64_t h = heavy_off[i];
+    heavy_row[h] = (int32_t)i;
+    heavy_slot_ptr[h] = s0;
+}
+
+// heavy_slot_ptr[h + 1] for every heavy row = slot_off of the next heavy row, or the total for the last one: since
+// slot_off is an exclusive scan over ALL rows and non-heavy rows contribute 0, slot_off[i + 1] is exactly that value
+__global__ void blocked_fill_close_kernel(const int64_t *__restrict__ rowptr, int64_t n_rows, int32_t chunk_edges,
+                                          int32_t block_min_len, const int64_t *__restrict__ heavy_off,
+                                          const int64_t *__restrict__ slot_off, const int64_t *__restrict__ slot_total,
+                                          int64_t *__restrict__ heavy_slot_ptr) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t len = rowptr[i + 1] - rowptr[i];
+    if (!(len >= block_min_len || len > chunk_edges)) return;
+    heavy_slot_ptr[heavy_off[i] + 1] = (i + 1 < n_rows) ? slot_off[i + 1] : slot_total[0];
+}
+
+__global__ void blocked_fill_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, int64_t n_rows,
+                                    int32_t chunk_edges, int32_t block_min_len, int64_t block_cols, int64_t n_blocks,
+                                    const int64_t *__restrict__ blk_idx, const int64_t *__restrict__ hdr,
+                                    const int64_t *__restrict__ mat, const int64_t *__restrict__ slot_off,
+                                    int32_t *__restrict__ chunk_row, int64_t *__restrict__ chunk_begin,
+                                    int32_t *__restrict__ chunk_len, int32_t *__restrict__ chunk_slot) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t b = rowptr[i], e = rowptr[i + 1];
+    if (e - b < block_min_len) return;
+    const int64_t nb = hdr[0], n_plain = hdr[1], j = blk_idx[i];
+    int64_t lo = b, slot = slot_off[i];
+    for (int64_t cb = 0; cb < n_blocks; ++cb) {
+        const int64_t hi = (cb + 1 == n_blocks) ? e : lower_bound_col(colidx, lo, e, (cb + 1) * block_cols);
+        int64_t pos = n_plain + mat[cb * nb + j];
+        for (int64_t s = lo; s < hi; s += chunk_edges, ++pos, ++slot) {
+            chunk_row[pos] = (int32_t)i;
+            chunk_begin[pos] = s;
+            chunk_len[pos] = (int32_t)((hi - s < chunk_edges) ? hi - s : chunk_edges);
+            chunk_slot[pos] = (int32_t)slot;
+        }
+        lo = hi;
+    }
+}
+
 }  // namespace cbrs
 
 using namespace cbrs;
@@ -305,5 +426,128 @@ extern "C" int cbrs_chunks_fill(const int64_t *rowptr, int64_t n_rows, int32_t c
         rowptr, n_rows, chunk_edges, chunk_off, heavy_off, slot_off, chunk_row, chunk_begin, chunk_slot, heavy_row,
         heavy_slot_ptr);
     CBRS_CHECK_LAUNCH("chunk_fill");
+    return CBRS_OK;
+}
+
+// ---- column-blocked decomposition (see the kernels above) -------------------------------------------------
+static int64_t blocked_rows_bound(int64_t n_rows, int64_t nnz, int32_t block_min_len) {
+    const int64_t by_len = nnz / (block_min_len > 0 ? block_min_len : 1);
+    return by_len < n_rows ? by_len : n_rows;
+}
+
+extern "C" size_t cbrs_chunks_blocked_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t n_cols, int32_t block_min_len,
+                                                      int64_t block_cols) {
+    if (n_rows <= 0) n_rows = 1;
+    const int64_t n_blocks = block_cols > 0 ? cdiv(n_cols > 0 ? n_cols : 1, block_cols) : 1;
+    const int64_t mat = blocked_rows_bound(n_rows, nnz, block_min_len) * n_blocks + 1;
+    return 4 * align_up((size_t)n_rows * 8) + align_up((size_t)mat * 8) + align_up(64) +
+           scan_i64_workspace_bytes(mat > n_rows ? mat : n_rows) + 1024;
+}
+
+namespace {
+struct BlockedWs {
+    int64_t *chunk_off, *heavy_off, *slot_off, *blk_idx, *mat, *hdr;  // hdr: {n_blocked, n_plain_chunks, n_slots, n_mat}
+    void *sub;
+    size_t sub_bytes;
+    int64_t mat_cap;
+};
+}  // namespace
+
+static int blocked_arrays(void *ws, size_t ws_bytes, int64_t n_rows, int64_t nnz, int64_t n_cols, int32_t block_min_len,
+                          int64_t block_cols, BlockedWs *w) {
+    Arena a(ws, ws_bytes);
+    const int64_t n_blocks = cdiv(n_cols, block_cols);
+    w->mat_cap = blocked_rows_bound(n_rows, nnz, block_min_len) * n_blocks + 1;
+    w->chunk_off = a.take<int64_t>((size_t)n_rows);
+    w->heavy_off = a.take<int64_t>((size_t)n_rows);
+    w->slot_off = a.take<int64_t>((size_t)n_rows);
+    w->blk_idx = a.take<int64_t>((size_t)n_rows);
+    w->mat = a.take<int64_t>((size_t)w->mat_cap);
+    w->hdr = a.take<int64_t>(8);
+    CBRS_REQUIRE(w->chunk_off && w->heavy_off && w->slot_off && w->blk_idx && w->mat && w->hdr, CBRS_E_WORKSPACE,
+                 "chunks_blocked: workspace too small");
+    w->sub = (char *)ws + a.off;
+    w->sub_bytes = ws_bytes - a.off;
+    return CBRS_OK;
+}
+
+extern "C" int cbrs_chunks_blocked_count(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz,
+                                         int64_t n_cols, int32_t chunk_edges, int32_t block_min_len, int64_t block_cols,
+                                         int64_t *counts_out, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CBRS_REQUIRE(rowptr && counts_out && n_rows > 0 && chunk_edges > 0 && (colidx || nnz == 0), CBRS_E_INVALID,
+                 "chunks_blocked_count: bad argument");
+    CBRS_REQUIRE(block_cols > 0 && block_min_len > 0 && n_cols > 0, CBRS_E_INVALID,
+                 "chunks_blocked_count: block_cols=%lld block_min_len=%d n_cols=%lld", (long long)block_cols, block_min_len,
+                 (long long)n_cols);
+    BlockedWs w;
+    int rc = blocked_arrays(workspace, workspace_bytes, n_rows, nnz, n_cols, block_min_len, block_cols, &w);
+    if (rc) return rc;
+    const int64_t n_blocks = cdiv(n_cols, block_cols);
+    const unsigned grid = (unsigned)cdiv(n_rows, kThreads);
+    blocked_classify_kernel<<<grid, kThreads, 0, s>>>(rowptr, n_rows, chunk_edges, block_min_len, w.chunk_off, w.heavy_off,
+                                                      w.slot_off, w.blk_idx);
+    CBRS_CHECK_LAUNCH("blocked_classify");
+    if ((rc = scan_i64_exclusive(w.blk_idx, n_rows, w.hdr + 0, w.sub, w.sub_bytes, s))) return rc;
+    // the matrix is sized by the number of blocked rows: one host round trip (graph build is not a hot path)
+    int64_t n_blocked = 0;
+    cudaError_t e = cudaMemcpyAsync(&n_blocked, w.hdr + 0, 8, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "chunks_blocked_count: %s", cudaGetErrorString(e));
+    const int64_t n_mat = n_blocked * n_blocks;
+    CBRS_REQUIRE(n_mat < w.mat_cap, CBRS_E_WORKSPACE, "chunks_blocked_count: %lld blocked rows exceed the bound",
+                 (long long)n_blocked);
+    if (n_blocked > 0) {
+        blocked_count_kernel<<<grid, kThreads, 0, s>>>(rowptr, colidx, n_rows, chunk_edges, block_min_len, block_cols,
+                                                       n_blocks, w.blk_idx, w.hdr, w.mat, w.slot_off);
+        CBRS_CHECK_LAUNCH("blocked_count");
+    }
+    if ((rc = scan_i64_exclusive(w.chunk_off, n_rows, w.hdr + 1, w.sub, w.sub_bytes, s))) return rc;
+    if ((rc = scan_i64_exclusive(w.heavy_off, n_rows, counts_out + 1, w.sub, w.sub_bytes, s))) return rc;
+    if ((rc = scan_i64_exclusive(w.slot_off, n_rows, w.hdr + 2, w.sub, w.sub_bytes, s))) return rc;
+    e = cudaMemsetAsync(w.hdr + 3, 0, 8, s);
+    CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "chunks_blocked_count: %s", cudaGetErrorString(e));
+    if (n_mat > 0 && (rc = scan_i64_exclusive(w.mat, n_mat, w.hdr + 3, w.sub, w.sub_bytes, s))) return rc;
+    // counts_out = {plain + blocked chunks, heavy rows, slots}
+    int64_t h[4];
+    e = cudaMemcpyAsync(h, w.hdr, 32, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "chunks_blocked_count: %s", cudaGetErrorString(e));
+    const int64_t total = h[1] + h[3];
+    e = cudaMemcpyAsync(counts_out + 0, &total, 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts_out + 2, w.hdr + 2, 8, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // `total` lives on this stack frame
+    CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "chunks_blocked_count: %s", cudaGetErrorString(e));
+    return CBRS_OK;
+}
+
+extern "C" int cbrs_chunks_blocked_fill(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz,
+                                        int64_t n_cols, int32_t chunk_edges, int32_t block_min_len, int64_t block_cols,
+                                        int32_t *chunk_row, int64_t *chunk_begin, int32_t *chunk_len, int32_t *chunk_slot,
+                                        int32_t *heavy_row, int64_t *heavy_slot_ptr, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    CBRS_REQUIRE(rowptr && chunk_row && chunk_begin && chunk_len && chunk_slot && n_rows > 0 && chunk_edges > 0 &&
+                     (colidx || nnz == 0),
+                 CBRS_E_INVALID, "chunks_blocked_fill: bad argument");
+    CBRS_REQUIRE(block_cols > 0 && block_min_len > 0 && n_cols > 0, CBRS_E_INVALID, "chunks_blocked_fill: bad blocking");
+    BlockedWs w;
+    int rc = blocked_arrays(workspace, workspace_bytes, n_rows, nnz, n_cols, block_min_len, block_cols, &w);
+    if (rc) return rc;
+    const int64_t n_blocks = cdiv(n_cols, block_cols);
+    const unsigned grid = (unsigned)cdiv(n_rows, kThreads);
+    blocked_fill_plain_kernel<<<grid, kThreads, 0, s>>>(rowptr, n_rows, chunk_edges, block_min_len, w.chunk_off, w.heavy_off,
+                                                        w.slot_off, chunk_row, chunk_begin, chunk_len, chunk_slot, heavy_row,
+                                                        heavy_slot_ptr);
+    CBRS_CHECK_LAUNCH("blocked_fill_plain");
+    if (heavy_slot_ptr) {
+        blocked_fill_close_kernel<<<grid, kThreads, 0, s>>>(rowptr, n_rows, chunk_edges, block_min_len, w.heavy_off,
+                                                            w.slot_off, w.hdr + 2, heavy_slot_ptr);
+        CBRS_CHECK_LAUNCH("blocked_fill_close");
+    }
+    blocked_fill_kernel<<<grid, kThreads, 0, s>>>(rowptr, colidx, n_rows, chunk_edges, block_min_len, block_cols, n_blocks,
+                                                  w.blk_idx, w.hdr, w.mat, w.slot_off, chunk_row, chunk_begin, chunk_len,
+                                                  chunk_slot);
+    CBRS_CHECK_LAUNCH("blocked_fill");
     return CBRS_OK;
 }

@@ -22,7 +22,7 @@ struct BarrierParams {
     int me;
     unsigned long long epoch;
     unsigned long long timeout_ns;
-    int *status;  // local: set to 1 if a peer did not arrive in time
+    int *status;  // local: set to 1 if a peer did not arrive in time (the kernel then traps)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
@@ -49,8 +49,12 @@ __global__ void peer_barrier_kernel(const BarrierParams p) {
     const unsigned long long *mine = p.flags[p.me] + t;
     while (ld_acquire_sys(mine) < p.epoch) {
         if (globaltimer_ns() - t0 > p.timeout_ns) {
+            // a peer never arrived: the operand buffers the consumer kernels are about to gather from are only partly
+            // written.  Record it and kill the stream (sticky launch failure) so that no later kernel can return
+            // silently wrong embeddings; every following CUDA call of this process raises.
             *p.status = 1;
-            break;
+            __threadfence_system();
+            __trap();
         }
         __nanosleep(200);
     }

@@ -29,6 +29,7 @@ struct SpmmParams {
     const int32_t *chunk_row;
     const int64_t *chunk_begin;
     const int32_t *chunk_slot;
+    const int32_t *chunk_len;  // explicit chunk lengths (column-blocked decomposition) or null
     int64_t n_chunks;
     int32_t chunk_edges;
     const void *x;  // float32, or bf16 when the kernel is instantiated with XT = __nv_bfloat16
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kSpmmThreads, MINB) spmm_chunk_kernel(const Sp
     const int32_t row = p.chunk_row[gid];
     const int64_t row_b = p.rowptr[row], row_e = p.rowptr[row + 1];
     const int64_t b = p.chunk_begin[gid];
-    const int64_t e = (b + p.chunk_edges < row_e) ? b + p.chunk_edges : row_e;
+    const int64_t e = p.chunk_len ? b + p.chunk_len[gid] : ((b + p.chunk_edges < row_e) ? b + p.chunk_edges : row_e);
     const int32_t slot = p.chunk_slot[gid];
     const bool weighted = (p.agg == CBRS_AGG_WEIGHTED) && p.vals != nullptr;
 
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kFusedThreads, 2) spmm_gcn_fused_kernel(const 
     const int32_t row = p.chunk_row[gid];
     const int64_t row_e = p.rowptr[row + 1];
     const int64_t b = p.chunk_begin[gid];
-    const int64_t e = (b + p.chunk_edges < row_e) ? b + p.chunk_edges : row_e;
+    const int64_t e = p.chunk_len ? b + p.chunk_len[gid] : ((b + p.chunk_edges < row_e) ? b + p.chunk_edges : row_e);
     const int32_t slot = p.chunk_slot[gid];
     const bool weighted = p.vals != nullptr;
     const float *xcol = reinterpret_cast<const float *>(p.x) + lane * 4;
@@ -535,7 +536,7 @@ static int spmm_impl(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, i
                  "spmm: workspace %zu < %zu bytes", workspace_bytes, need);
     SpmmParams p;
     p.rowptr = g->rowptr; p.colidx = g->colidx; p.vals = g->vals;
-    p.chunk_row = g->chunk_row; p.chunk_begin = g->chunk_begin; p.chunk_slot = g->chunk_slot;
+    p.chunk_row = g->chunk_row; p.chunk_begin = g->chunk_begin; p.chunk_slot = g->chunk_slot; p.chunk_len = g->chunk_len;
     p.n_chunks = g->n_chunks; p.chunk_edges = g->chunk_edges;
     p.x = x; p.ldx = ldx; p.y = (float *)y; p.ldy = ldy; p.d = d; p.agg = agg;
     p.bias = bias; p.relu = relu; p.partial = (float *)workspace;
@@ -584,7 +585,7 @@ extern "C" int cbrs_spmm_gcn_fused(const cbrs_csr_t *g, const float *z, int64_t 
     FusedParams fp;
     SpmmParams &p = fp.sp;
     p.rowptr = g->rowptr; p.colidx = g->colidx; p.vals = g->vals;
-    p.chunk_row = g->chunk_row; p.chunk_begin = g->chunk_begin; p.chunk_slot = g->chunk_slot;
+    p.chunk_row = g->chunk_row; p.chunk_begin = g->chunk_begin; p.chunk_slot = g->chunk_slot; p.chunk_len = g->chunk_len;
     p.n_chunks = g->n_chunks; p.chunk_edges = g->chunk_edges;
     p.x = z; p.ldx = ldz_in; p.y = y; p.ldy = ldy; p.d = kFusedD; p.agg = CBRS_AGG_WEIGHTED;
     p.bias = bias; p.relu = relu; p.partial = (float *)workspace;

@@ -121,14 +121,23 @@ class PeerHeap:
         from . import _lib as L
         nbytes = (int(nbytes) + 255) // 256 * 256
         ptr = ctypes.c_void_p()
-        L.check(self._lib.cbrs_peer_alloc(nbytes, ctypes.byref(ptr)), "cbrs_peer_alloc")
-        self._owned.append(ptr.value)
         handle = (ctypes.c_ubyte * L.IPC_HANDLE_BYTES)()
-        L.check(self._lib.cbrs_peer_export(ptr, handle), "cbrs_peer_export")
+        # a local failure (cudaMalloc out of memory, export error) must not skip the collective below: the other
+        # ranks would wait in it forever.  Every rank sends (size, handle or None, error) and all decide together.
+        local_error = None
+        try:
+            L.check(self._lib.cbrs_peer_alloc(nbytes, ctypes.byref(ptr)), "cbrs_peer_alloc")
+            self._owned.append(ptr.value)
+            L.check(self._lib.cbrs_peer_export(ptr, handle), "cbrs_peer_export")
+        except L.CbrsError as e:
+            local_error = str(e)
         handles = [None] * self.world
-        dist.all_gather_object(handles, (nbytes, bytes(handle)), group=self.group)
+        dist.all_gather_object(handles, (nbytes, None if local_error else bytes(handle), local_error), group=self.group)
+        failed = [(r, err) for r, (_, _, err) in enumerate(handles) if err]
+        if failed:
+            raise L.CbrsError("symmetric allocation of {} bytes failed on rank {}: {}".format(nbytes, *failed[0]))
         ptrs = []
-        for r, (nb, h) in enumerate(handles):
+        for r, (nb, h, _) in enumerate(handles):
             if nb != nbytes:
                 raise L.CbrsError("symmetric allocation sizes differ: rank {} asked for {} bytes, rank {} for {}"
                                   .format(self.rank, nbytes, r, nb))
@@ -168,13 +177,15 @@ class PeerHeap:
             ops.PROFILE.append(("barrier", e0, e1, None))
 
     def check(self):
-        """Synchronises; raises if any barrier so far timed out."""
+        """Synchronises; raises if any barrier so far timed out.  (A timed-out barrier kernel also traps, so the
+        stream is already dead and this read itself raises a CUDA error: either way the failure is loud.)"""
         from . import _lib as L
         if int(self.status.item()) != 0:
             raise L.CbrsError("peer barrier timed out: a rank did not arrive within 30 s")
 
     def close(self):
         torch.cuda.synchronize()
+        self.check()
         dist.barrier(group=self.group)
         for q in self._opened:
             self._lib.cbrs_peer_close(ctypes.c_void_p(q))

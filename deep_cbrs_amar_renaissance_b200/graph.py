@@ -8,6 +8,8 @@ Two views are built on demand from the same COO entries:
   * raw : row-major sorted, duplicates kept, values ignored          -> GraphSAGE, GAT
           (gnn.py:298-319,331-352 pass the adjacency through untouched)
 """
+import os
+
 import numpy as np
 import torch
 
@@ -16,18 +18,37 @@ from . import ops
 
 DEFAULT_CHUNK_EDGES = 1024
 
+# Column-blocked schedule (cbrs_chunks_blocked_*): used when the gathered operand table cannot stay in L2.  The
+# policy is a function of the GLOBAL column count only, so every rank of a row partition and the single-GPU run
+# cut a row at the same places (bit-identical results).  CBRS_BLOCK_COLS / CBRS_BLOCK_MIN_LEN override it
+# (0 disables); tuned on config 5 (profiles/r02_tune_blocked.log).
+BLOCK_COLS = 98304          # operand rows per window: 48 MB at D = 128 fp32 (L2: 126 MB, two dies)
+BLOCK_MIN_LEN = 1024        # rows shorter than this stay row-major (a partial per segment would cost more than it saves)
+BLOCK_MIN_COLS = 1 << 19    # tables below 2^19 rows (256 MB at D = 128) are left to the L2's own replacement
+
+
+def blocking_policy(n_cols):
+    """(block_cols, block_min_len) for a graph with n_cols columns; (0, 0) = row-major schedule."""
+    cols = int(os.environ.get("CBRS_BLOCK_COLS", BLOCK_COLS))
+    min_len = int(os.environ.get("CBRS_BLOCK_MIN_LEN", BLOCK_MIN_LEN))
+    min_cols = int(os.environ.get("CBRS_BLOCK_MIN_COLS", BLOCK_MIN_COLS))
+    if cols <= 0 or min_len <= 0 or n_cols < min_cols:
+        return 0, 0
+    return cols, min_len
+
 
 class CsrSlice:
     """Rows [row_offset, row_offset + n_rows) of a CSR matrix plus its work decomposition."""
 
-    def __init__(self, rowptr, colidx, vals, n_cols, chunk_edges=DEFAULT_CHUNK_EDGES, row_offset=0):
+    def __init__(self, rowptr, colidx, vals, n_cols, chunk_edges=DEFAULT_CHUNK_EDGES, row_offset=0, blocking=None):
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
         self.n_rows = rowptr.numel() - 1
         self.n_cols = n_cols
         self.nnz = colidx.numel()
         self.row_offset = row_offset
         self.chunk_edges = chunk_edges
-        self.chunks = ops.build_chunks(rowptr, chunk_edges)
+        self.blocking = blocking_policy(n_cols) if blocking is None else tuple(blocking)
+        self.chunks = ops.build_chunks(rowptr, chunk_edges, colidx, n_cols, *self.blocking)
         c = self.chunks
         d = L.CsrDesc()
         d.n_rows, d.nnz = self.n_rows, self.nnz
@@ -39,6 +60,7 @@ class CsrSlice:
         d.n_heavy, d.n_slots = c["n_heavy"], c["n_slots"]
         d.heavy_row = c["heavy_row"].data_ptr() if c["n_heavy"] else None
         d.heavy_slot_ptr = c["heavy_slot_ptr"].data_ptr()
+        d.chunk_len = c["chunk_len"].data_ptr() if c["chunk_len"] is not None else None
         self.desc = d
 
     def row_slice(self, r0, r1, chunk_edges=None):
@@ -47,7 +69,7 @@ class CsrSlice:
         rowptr = (self.rowptr[r0:r1 + 1] - b).contiguous()
         vals = self.vals[b:e].contiguous() if self.vals is not None else None
         return CsrSlice(rowptr, self.colidx[b:e].contiguous(), vals, self.n_cols,
-                        chunk_edges or self.chunk_edges, self.row_offset + r0)
+                        chunk_edges or self.chunk_edges, self.row_offset + r0, blocking=self.blocking)
 
     def to_scipy(self):
         from scipy import sparse

@@ -77,27 +77,45 @@ def graph_build_csr(row, col, val, n_nodes, flags, rel=None, n_rel=1, self_rel=0
     return rowptr, colidx[:n_out], vals[:n_out]
 
 
-def build_chunks(rowptr, chunk_edges):
-    """Chunk decomposition of a CSR row-pointer (see cbrs_csr_t)."""
+def build_chunks(rowptr, chunk_edges, colidx=None, n_cols=0, block_cols=0, block_min_len=0):
+    """Chunk decomposition of a CSR row-pointer (see cbrs_csr_t).  With block_cols > 0 rows of at least
+    block_min_len edges are cut at column-block borders and scheduled by (column block, row)
+    (cbrs_chunks_blocked_*): the gather then works on an L2-resident window of the operand table."""
     lib = L.load()
     dev = rowptr.device
     n_rows = rowptr.numel() - 1
-    ws = _ws(lib.cbrs_chunks_workspace_bytes(n_rows), dev)
+    blocked = block_cols > 0 and colidx is not None and n_rows > 0
     counts = torch.zeros(3, dtype=torch.int64, device=dev)
-    L.check(lib.cbrs_chunks_count(_ptr(rowptr, torch.int64), n_rows, chunk_edges, _ptr(counts), _ptr(ws), ws.numel(),
-                                  _stream()), "cbrs_chunks_count")
+    if blocked:
+        nnz = colidx.numel()
+        geo = (n_rows, nnz, int(n_cols), int(chunk_edges), int(block_min_len), int(block_cols))
+        ws = _ws(lib.cbrs_chunks_blocked_workspace_bytes(n_rows, nnz, int(n_cols), int(block_min_len), int(block_cols)), dev)
+        L.check(lib.cbrs_chunks_blocked_count(_ptr(rowptr, torch.int64), _ptr(colidx, torch.int32), *geo, _ptr(counts),
+                                              _ptr(ws), ws.numel(), _stream()), "cbrs_chunks_blocked_count")
+    else:
+        ws = _ws(lib.cbrs_chunks_workspace_bytes(n_rows), dev)
+        L.check(lib.cbrs_chunks_count(_ptr(rowptr, torch.int64), n_rows, chunk_edges, _ptr(counts), _ptr(ws), ws.numel(),
+                                      _stream()), "cbrs_chunks_count")
     n_chunks, n_heavy, n_slots = (int(v) for v in counts.tolist())
     chunk_row = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
     chunk_begin = torch.empty(max(n_chunks, 1), dtype=torch.int64, device=dev)
     chunk_slot = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
     heavy_row = torch.empty(max(n_heavy, 1), dtype=torch.int32, device=dev)
     heavy_slot_ptr = torch.zeros(n_heavy + 1, dtype=torch.int64, device=dev)
-    L.check(lib.cbrs_chunks_fill(_ptr(rowptr), n_rows, chunk_edges, _ptr(chunk_row), _ptr(chunk_begin),
-                                 _ptr(chunk_slot), _ptr(heavy_row), _ptr(heavy_slot_ptr), _ptr(ws), ws.numel(),
-                                 _stream()), "cbrs_chunks_fill")
+    chunk_len = None
+    if blocked:
+        chunk_len = torch.empty(max(n_chunks, 1), dtype=torch.int32, device=dev)
+        L.check(lib.cbrs_chunks_blocked_fill(_ptr(rowptr), _ptr(colidx), *geo, _ptr(chunk_row), _ptr(chunk_begin),
+                                             _ptr(chunk_len), _ptr(chunk_slot), _ptr(heavy_row), _ptr(heavy_slot_ptr),
+                                             _ptr(ws), ws.numel(), _stream()), "cbrs_chunks_blocked_fill")
+        chunk_len = chunk_len[:n_chunks]
+    else:
+        L.check(lib.cbrs_chunks_fill(_ptr(rowptr), n_rows, chunk_edges, _ptr(chunk_row), _ptr(chunk_begin),
+                                     _ptr(chunk_slot), _ptr(heavy_row), _ptr(heavy_slot_ptr), _ptr(ws), ws.numel(),
+                                     _stream()), "cbrs_chunks_fill")
     return dict(n_chunks=n_chunks, n_heavy=n_heavy, n_slots=n_slots, chunk_row=chunk_row[:n_chunks],
                 chunk_begin=chunk_begin[:n_chunks], chunk_slot=chunk_slot[:n_chunks], heavy_row=heavy_row[:n_heavy],
-                heavy_slot_ptr=heavy_slot_ptr)
+                heavy_slot_ptr=heavy_slot_ptr, chunk_len=chunk_len)
 
 
 # ------------------------------------------------------------------ propagation

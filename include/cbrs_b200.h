@@ -96,6 +96,8 @@ typedef struct cbrs_csr {
     const int32_t *heavy_row;  /* [n_heavy]                                               */
     const int64_t *heavy_slot_ptr; /* [n_heavy+1] slot range of each heavy row            */
     int64_t n_slots;
+    const int32_t *chunk_len;  /* [n_chunks] edges of the chunk, or NULL: the rule given at chunk_begin. Set by the
+                                  column-blocked decomposition below, whose chunks end at column-block borders     */
 } cbrs_csr_t;
 
 /* Pass 1: counts.  counts_out (device int64[3]) = {n_chunks, n_heavy, n_slots}. */
@@ -106,6 +108,26 @@ int cbrs_chunks_count(const int64_t *rowptr, int64_t n_rows, int32_t chunk_edges
 int cbrs_chunks_fill(const int64_t *rowptr, int64_t n_rows, int32_t chunk_edges, int32_t *chunk_row,
                      int64_t *chunk_begin, int32_t *chunk_slot, int32_t *heavy_row,
                      int64_t *heavy_slot_ptr, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Column-blocked decomposition (round 2: cuts the HBM traffic of the gather when the operand table [n_cols, D] is
+ * larger than L2).  Rows with at least block_min_len edges are cut where their ascending column ids cross a multiple
+ * of block_cols and then into pieces of at most chunk_edges edges; they are always "heavy" (partials merged in
+ * ascending column order).  Their chunks follow all other rows' chunks in the list, ordered by (column block, row):
+ * CTAs are dispatched in list order, so the resident warps gather from one window of block_cols operand rows that
+ * stays in L2.  The cut points depend on the row's own column ids, block_cols and chunk_edges only => the reduction
+ * tree of a row is the same on every launch shape and row partition.  chunk_len must be passed in cbrs_csr_t.
+ * Replaces nothing in the reference (tf.sparse.sparse_dense_matmul, src/layers/lightgcn_conv.py:51-54, has no
+ * schedule); counts_out as cbrs_chunks_count.  The count call synchronises the stream.                          */
+size_t cbrs_chunks_blocked_workspace_bytes(int64_t n_rows, int64_t nnz, int64_t n_cols, int32_t block_min_len,
+                                           int64_t block_cols);
+int cbrs_chunks_blocked_count(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz,
+                              int64_t n_cols, int32_t chunk_edges, int32_t block_min_len, int64_t block_cols,
+                              int64_t *counts_out, void *workspace, size_t workspace_bytes, void *stream);
+int cbrs_chunks_blocked_fill(const int64_t *rowptr, const int32_t *colidx, int64_t n_rows, int64_t nnz,
+                             int64_t n_cols, int32_t chunk_edges, int32_t block_min_len, int64_t block_cols,
+                             int32_t *chunk_row, int64_t *chunk_begin, int32_t *chunk_len, int32_t *chunk_slot,
+                             int32_t *heavy_row, int64_t *heavy_slot_ptr, void *workspace,
+                             size_t workspace_bytes, void *stream);
 
 /* ---- propagation kernels (rows P1, P2 aggregate, P4) ---------------------
  * Y[i, 0:D] = epilogue( reduce_j A_ij * X[col_j, 0:D] ), j over row i ascending.
@@ -247,7 +269,9 @@ int cbrs_synth_bipartite(int64_t n_users, int64_t n_items, int64_t n_edges, uint
  * publishes `epoch` (monotonically increasing, same on all ranks) into slot r of every
  * rank's flag array and waits until all slots of its own array reach `epoch`; *status
  * (device int32, zeroed by the caller) becomes 1 if a peer did not arrive within
- * timeout_s.  The reference has no multi-device code; these calls replace the
+ * timeout_s AND the kernel traps: the consumers would otherwise gather from partly written
+ * operand buffers, so the stream fails (every later CUDA call of the process returns an
+ * error) instead of continuing.  The reference has no multi-device code; these calls replace the
  * all-gather + barrier a NCCL-based port would issue per layer.                           */
 #define CBRS_MAX_PEERS 8
 #define CBRS_IPC_HANDLE_BYTES 64
