@@ -48,6 +48,11 @@ def parse():
     ap.add_argument("--cpu-scale", default="c5-hundredth", choices=sorted(SCALES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the bf16-operand variant of the step")
+    ap.add_argument("--unscattered", action="store_true",
+                    help="item id = popularity rank (no scattering of hot items over the id space): the adversarial case for "
+                         "the row partition; cuts are balanced by edge count either way")
+    ap.add_argument("--row-count-cuts", action="store_true", help="N > 1: cut node types at equal ROW counts (round-1 behaviour)")
+    ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the bit-identity self-check that precedes timing")
     ap.add_argument("--catalog-users", type=int, default=4736,
                     help="users per rank scored against the whole catalog (4736 = 148 SMs x 2 CTAs x 16 users: one full wave of "
                          "the fp32 kernel; the bf16 kernel gets 4x as many)")
@@ -128,6 +133,12 @@ def workload_config(scale, gpus):
             "l2": "inputs larger than L2 (no flush needed)"}
 
 
+def mark_variant(cfg, args):
+    if args.unscattered:
+        cfg["item_ids"] = "unscattered (id = popularity rank)"
+    return cfg
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -192,10 +203,27 @@ def run_b200(args):
         pass
     hbm_peak, peak_src = (peaks.get("hbm_gbs"), "measured") if peaks.get("hbm_gbs") else (6650.0, "fallback")
 
+    # ---- multi-GPU self-check BEFORE anything is timed: the row-partitioned propagation must equal the single-GPU
+    # one bit for bit (all layer families, both exchanges, pipelines, fused kernel, blocked schedule; small graphs)
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        from deep_cbrs_amar_renaissance_b200.selfcheck import partition_parity
+        t_par0 = time.perf_counter()
+        parity = partition_parity()
+        parity["seconds"] = time.perf_counter() - t_par0
+        if not parity["bit_identical"]:
+            if rank == 0:
+                print(json.dumps({"metric": "propagation_edges_per_s", "value": None, "n_gpus": world,
+                                  "partition_parity": parity, "error": "partitioned result differs from the single-GPU result"}),
+                      flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(3)
+        torch.cuda.empty_cache()
+
     n_users, n_items, n_edges = SCALES[args.scale]
     n = n_users + n_items
     t_build0 = time.perf_counter()
-    row, col = ops.synth_bipartite(n_users, n_items, n_edges, 42, dev)
+    row, col = ops.synth_bipartite(n_users, n_items, n_edges, 42, dev, scatter_items=not args.unscattered)
     graph = DeviceGraph(row, col, None, n)
     del row, col
     set_seed(42)
@@ -206,7 +234,9 @@ def run_b200(args):
     heavy = graph.norm.chunks["n_heavy"]
     part = None
     if world > 1:
-        part = RowPartition([n_users, n_items], final_types=[1]).attach(seq)  # CBRS_EXCHANGE=nccl|peer
+        # CBRS_EXCHANGE=nccl|peer; each node type is cut into N blocks of equal EDGE count
+        part = RowPartition([n_users, n_items], final_types=[1],
+                            balance_rowptr=None if args.row_count_cuts else graph.norm.rowptr).attach(seq)
         os.environ["CBRS_EXCHANGE"] = part.exchange + ("+fused-transform" if part.exchange == "peer" and part.pipeline == "fused" else "")
         part.csr_slices("norm", graph)
         part.release_full_views(graph)
@@ -269,6 +299,17 @@ def run_b200(args):
         breakdown[name] = breakdown.get(name, 0.0) + a.elapsed_time(b) / args.steps
     ms_per_step = ms / args.steps
     value = LAYERS * nnz_total / (ms_per_step * 1e-3)
+
+    # per-rank time in the sparse kernels (balance of the row partition)
+    rank_sparse = None
+    if world > 1:
+        mine = torch.tensor([sum(spmm_ms) / max(args.steps, 1)], device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per = [float(t.item()) for t in every]
+        rank_sparse = {"ms_per_step": per, "min": min(per), "max": max(per), "max_over_min": max(per) / max(min(per), 1e-9),
+                       "local_edges": part.local_edges("norm"),
+                       "cuts": "equal row counts" if args.row_count_cuts else "equal edge counts per node type"}
 
     # ---- end to end through the public model call with HOST buffers (e2e) --------------------
     def e2e_step():
@@ -343,13 +384,13 @@ def run_b200(args):
     line = {
         "metric": "propagation_edges_per_s", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.scale, world),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": mark_variant(workload_config(args.scale, world), args),
         "edges_per_s_per_gpu": value / world, "nnz_a_hat": nnz_total, "heavy_rows": heavy,
         "graph_build_s": build_s, "gpu_launches": launches, "clocks": clocks,
         "step_breakdown_ms": breakdown, "bf16_operands": bf16_block,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": 2 * PAIR_BATCH * 8,
                 "d2h_bytes_per_step": PAIR_BATCH * 4, "ms_per_step": ms_e2e / args.steps},
-        "roofline": roofline,
+        "roofline": roofline, "partition_parity": parity, "rank_sparse_ms": rank_sparse,
         "pairs": {"value": pairs_per_s, "unit": "pairs/s", "what": "full-catalog BasicRS scoring + top-10, %d users x %d items per rank" % (cu, n_items),
                   "ms": cat_ms,
                   "bf16_tcgen05": {"value": pairs_tc, "unit": "pairs/s", "users_per_rank": cu_tc, "ms": tc_ms,

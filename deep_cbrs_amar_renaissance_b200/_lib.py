@@ -53,6 +53,10 @@ _SIGS = {
     "cbrs_dense_tc_image_bytes": (c_size_t, [c_int32, c_int32]),
     "cbrs_dense_tc_prepare": (c_int, [P, c_int32, c_int32, P, P]),
     "cbrs_dense_tc": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int, P, c_int64, P]),
+    "cbrs_dense_tf32x3_eligible": (c_int, [c_int32, c_int32]),
+    "cbrs_dense_tf32x3_image_bytes": (c_size_t, [c_int32, c_int32]),
+    "cbrs_dense_tf32x3_prepare": (c_int, [P, c_int32, c_int32, P, P]),
+    "cbrs_dense_tf32x3": (c_int, [P, c_int64, P, P, c_int64, c_int32, c_int32, c_int, P, c_int64, POINTER(c_void_p), c_int, P]),
     "cbrs_reduce_layers": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int32, POINTER(c_float), c_float,
                                    c_int64, c_int32, P, c_int64, P]),
     "cbrs_gather_rows": (c_int, [P, c_int64, P, c_int64, c_int32, P, c_int64, P]),
@@ -114,6 +118,7 @@ _SIGS = {
     "cbrs_adam_step_multi": (c_int, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                      POINTER(c_int64), POINTER(c_float), c_float, P, c_float, c_float, c_float, P]),
     "cbrs_synth_bipartite": (c_int, [c_int64, c_int64, c_int64, c_uint64, P, P, P]),
+    "cbrs_synth_bipartite_ex": (c_int, [c_int64, c_int64, c_int64, c_uint64, c_int, P, P, P]),
     "cbrs_sort_workspace_bytes": (c_size_t, [c_int64]),
     "cbrs_sort_pairs_u64": (c_int, [P, P, c_int64, c_int, P, c_size_t, P]),
 }

@@ -1,10 +1,11 @@
-// EXPERIMENTAL variant of the tensor-core Dense kernel (dense_tc.cu), selected with CBRS_DENSE_TC_VARIANT=4.
-// Written at the end of round 1 from the ncu evidence on the shipped kernel (profiles/r01_ncu_dense_tc_v3_stalls.txt:
-// 8 warps per SM, ~535 instructions per warp and K block, 26 % of the stall samples on the row-pointer LDS ->
-// address arithmetic chain) and NOT yet run on a GPU: nothing calls it unless the variable is set, and its test
-// (tests/test_zz_gpu_dense_tc.py::test_experimental_variant) is skipped unless CBRS_TEST_EXPERIMENTAL=1.
+// Second tensor-core Dense kernel (see dense_tc.cu): cbrs_dense_tc uses it for deep layers (f1 + f2 >= 512, e.g. the
+// hybrid scorer's 768 -> 256 BERT tower: 1.54 ms per 2^20 rows against 1.65 ms with dense_tc_kernel,
+// profiles/r02_dense_tc_bench_variant4.jsonl); CBRS_DENSE_TC_VARIANT=3|4 forces one kernel on every shape, which is
+// how tests/test_zz_gpu_dense_tc.py::test_each_kernel_variant_on_every_shape covers both.
+// Written from the ncu evidence on dense_tc_kernel (profiles/r01_ncu_dense_tc_v3_stalls.txt: 8 warps per SM, ~535
+// instructions per warp and K block, 26 % of the stall samples on the row-pointer LDS -> address arithmetic chain).
 //
-// Differences from the shipped kernel:
+// Differences from dense_tc_kernel:
 //   * 256 threads per CTA (16 warps per SM at 2 CTAs): a thread owns 4 (row, chunk) pairs instead of 8;
 //   * a thread's chunk column c = tid & 7 never changes, so its 4 row pointers (per source) and its 4 swizzled
 //     shared-memory offsets live in registers for the whole kernel, and the source selection (source 1 / source 2 /

@@ -133,6 +133,11 @@ extern "C" int cbrs_gather_rows(const float *x, int64_t ldx, const int64_t *idx,
 
 extern "C" int cbrs_synth_bipartite(int64_t n_users, int64_t n_items, int64_t n_edges, uint64_t seed, int32_t *coo_row,
                                     int32_t *coo_col, void *stream) {
+    return cbrs_synth_bipartite_ex(n_users, n_items, n_edges, seed, 1, coo_row, coo_col, stream);
+}
+
+extern "C" int cbrs_synth_bipartite_ex(int64_t n_users, int64_t n_items, int64_t n_edges, uint64_t seed, int scatter_items,
+                                       int32_t *coo_row, int32_t *coo_col, void *stream) {
     CBRS_REQUIRE(coo_row && coo_col, CBRS_E_INVALID, "synth_bipartite: null argument");
     CBRS_REQUIRE(n_users > 0 && n_items > 0 && n_edges >= 0 && n_users + n_items < ((int64_t)1 << 31), CBRS_E_INVALID,
                  "synth_bipartite: bad shape");
@@ -143,6 +148,7 @@ extern "C" int cbrs_synth_bipartite(int64_t n_users, int64_t n_items, int64_t n_
     uint64_t mult = 0x9E3779B1ull % (uint64_t)n_items;
     if (mult == 0) mult = 1;
     while (gcd64(mult, (uint64_t)n_items) != 1) ++mult;
+    if (!scatter_items) mult = 1;  // item id = popularity rank: the hottest items are neighbours in id space
     synth_bipartite_kernel<<<(unsigned)cdiv(n_edges, 256), 256, 0, (cudaStream_t)stream>>>(n_users, n_items, n_edges, seed, c,
                                                                                          levels, mult, coo_row, coo_col);
     CBRS_CHECK_LAUNCH("synth_bipartite");

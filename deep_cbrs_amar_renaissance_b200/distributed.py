@@ -42,6 +42,31 @@ def block_ranges(n_rows_by_type, world_size):
     return out
 
 
+def balanced_ranges(n_rows_by_type, world_size, rowptr):
+    """block_ranges with each node type cut at (about) equal EDGE count instead of equal row count: block r of a type
+    ends at the first row whose prefix edge count reaches r/world of the type's edges.  `rowptr` is the
+    [N+1] row pointer of the CSR view the sparse kernel runs on (host or device tensor); every rank computes the
+    same cuts from it.  Real ids come out of np.unique in id order, so popular items may sit next to each other;
+    equal row counts would then give one rank most of the edges."""
+    out = [[] for _ in range(world_size)]
+    base = 0
+    for n in n_rows_by_type:
+        rp = rowptr[base:base + n + 1]
+        cuts = [0] * (world_size + 1)
+        cuts[world_size] = n
+        if n > 0:
+            lo, hi = int(rp[0].item()), int(rp[-1].item())
+            targets = torch.tensor([lo + (hi - lo) * k // world_size for k in range(1, world_size)], dtype=rp.dtype,
+                                   device=rp.device)
+            mids = torch.searchsorted(rp.contiguous(), targets).tolist() if world_size > 1 else []
+            for k, m in enumerate(mids):
+                cuts[k + 1] = min(max(int(m), cuts[k]), n)
+        for r in range(world_size):
+            out[r].append((base + cuts[r], base + max(cuts[r + 1], cuts[r])))
+        base += n
+    return out
+
+
 def exchange_rows(x, ranges, group=None):
     """All ranks end up with every row block of x (each block is authored by its owner).
 
@@ -209,7 +234,7 @@ class RowPartition:
     are exchanged, because scoring is sharded by user."""
 
     def __init__(self, n_rows_by_type, group=None, final_types=None, exchange=None, pipeline=None,
-                 row_blocks=None):
+                 row_blocks=None, balance_rowptr=None):
         self.group = group
         exchange = exchange or os.environ.get("CBRS_EXCHANGE") or ("peer" if torch.cuda.is_available() else "nccl")
         if exchange not in ("peer", "nccl"):
@@ -251,7 +276,9 @@ class RowPartition:
         self.n_rows_by_type = list(n_rows_by_type)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.ranges = block_ranges(n_rows_by_type, self.world)
+        # balance_rowptr: the CSR row pointer to balance EDGES by (balanced_ranges); None = equal row counts
+        self.ranges = (block_ranges(n_rows_by_type, self.world) if balance_rowptr is None
+                       else balanced_ranges(n_rows_by_type, self.world, balance_rowptr))
         self.mine = [rg for rg in self.ranges[self.rank] if rg[1] > rg[0]]
         self.final_types = list(range(1, len(n_rows_by_type))) if final_types is None else list(final_types)
         self._slices = {}
@@ -396,13 +423,16 @@ class RowPartition:
                     for r, w in enumerate(kernels):
                         for a, b in self.mine:
                             zv = z[r * n + a:r * n + b]
-                            ops.dense(x_full[a:b], w, out=zv, peers=zsb.peer_addrs(zv))
+                            ops.gcn_transform(x_full[a:b], w, n, out=zv, peers=zsb.peer_addrs(zv))
                     heap.barrier()
                 # software pipeline: while the sparse kernel works on row block b+1, the NEXT layer's transform
                 # of block b is computed and stored into every rank's copy on a side stream
+                # (its epilogue is the FFMA chain of dense.cu: only taken when the standalone transform is the FFMA kernel
+                # too, otherwise the partitioned result would differ in the last bits from the single-GPU one)
                 fuse_next = (self.pipeline == "fused" and isinstance(layer, GCNConv) and isinstance(nxt, GCNConv)
                              and layer.channels == 128 and nxt.channels == 128 and zdt == torch.float32
-                             and getattr(nxt, "feature_dtype", "fp32") == "fp32")
+                             and getattr(nxt, "feature_dtype", "fp32") == "fp32"
+                             and not ops.tf32x3_chosen(n, 128, 128))
                 if fuse_next:
                     if not nxt.built:
                         nxt.build([(n, widths[l + 1]), None])
@@ -439,11 +469,11 @@ class RowPartition:
                             self._side.wait_event(done)
                             zv = nz[a:b]
                             if self.pipeline == "ce":
-                                ops.dense(ov, nxt.kernel, out=zv)
+                                ops.gcn_transform(ov, nxt.kernel, n, out=zv)
                                 for addr in nsb.peer_addrs(zv):
                                     ops.peer_copy(addr, zv)
                             else:
-                                ops.dense(ov, nxt.kernel, out=zv, peers=nsb.peer_addrs(zv))
+                                ops.gcn_transform(ov, nxt.kernel, n, out=zv, peers=nsb.peer_addrs(zv))
                 if z_ahead:
                     pushed = torch.cuda.Event()
                     pushed.record(self._side)
@@ -527,7 +557,7 @@ class RowPartition:
                 z = self._buf(("z", l), len(kernels) * n, layer.channels, dev, zdt)
                 for r, w in enumerate(kernels):
                     for a, b in self.mine:
-                        ops.dense(x_full[a:b], w, out=z[r * n + a:r * n + b])
+                        ops.gcn_transform(x_full[a:b], w, n, out=z[r * n + a:r * n + b])
                     self._exchange(z[r * n:(r + 1) * n])
                 for sl in self.csr_slices("norm", graph):
                     ops.spmm(sl, z, out[sl.row_offset:sl.row_offset + sl.n_rows], bias=layer.bias, relu=relu)

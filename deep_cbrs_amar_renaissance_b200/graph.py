@@ -27,8 +27,13 @@ BLOCK_MIN_LEN = 1024        # rows shorter than this stay row-major (a partial p
 BLOCK_MIN_COLS = 1 << 19    # tables below 2^19 rows (256 MB at D = 128) are left to the L2's own replacement
 
 
+FORCED_BLOCKING = None      # (block_cols, block_min_len): tests and the multi-GPU self-check block small graphs with it
+
+
 def blocking_policy(n_cols):
     """(block_cols, block_min_len) for a graph with n_cols columns; (0, 0) = row-major schedule."""
+    if FORCED_BLOCKING is not None:
+        return tuple(FORCED_BLOCKING)
     cols = int(os.environ.get("CBRS_BLOCK_COLS", BLOCK_COLS))
     min_len = int(os.environ.get("CBRS_BLOCK_MIN_LEN", BLOCK_MIN_LEN))
     min_cols = int(os.environ.get("CBRS_BLOCK_MIN_COLS", BLOCK_MIN_COLS))
@@ -71,6 +76,23 @@ class CsrSlice:
         return CsrSlice(rowptr, self.colidx[b:e].contiguous(), vals, self.n_cols,
                         chunk_edges or self.chunk_edges, self.row_offset + r0, blocking=self.blocking)
 
+    def coo_rows(self):
+        """row id of every stored entry (int32 [nnz])"""
+        lens = self.rowptr[1:] - self.rowptr[:-1]
+        return torch.repeat_interleave(torch.arange(self.n_rows, dtype=torch.int32, device=self.rowptr.device), lens)
+
+    def transposed(self):
+        """The transpose as a CsrSlice ([n_cols, n_rows], entries of a row in ascending column order, duplicates
+        kept): what the backward of a sparse layer multiplies by when the adjacency is not symmetric, and, for the
+        relational operator's stacked [N, R*N] layout, the matrix whose one product yields every relation's dZ."""
+        if getattr(self, "_t", None) is None:
+            m = max(self.n_rows, self.n_cols)
+            rowptr, colidx, vals = ops.graph_build_csr(self.colidx, self.coo_rows(), self.vals, m, 0)
+            rowptr = rowptr[:self.n_cols + 1].contiguous()
+            self._t = CsrSlice(rowptr, colidx.contiguous(), vals.contiguous() if self.vals is not None else None,
+                               self.n_rows, self.chunk_edges, blocking=self.blocking)
+        return self._t
+
     def to_scipy(self):
         from scipy import sparse
         vals = (self.vals if self.vals is not None else torch.ones_like(self.colidx, dtype=torch.float32)).cpu().numpy()
@@ -110,6 +132,35 @@ class DeviceGraph:
     def release_coo(self):
         """Drop the COO entries once the needed views exist (frees 12 B per entry)."""
         self.row = self.col = self.val = self.rel = None
+
+    @property
+    def symmetric(self):
+        """True when the entries (row, col[, rel], value) and (col, row[, rel], value) form the same multiset, i.e.
+        A == A^T with duplicates.  The explicit backward of the sparse layers multiplies by the FORWARD operator only
+        in that case (training.py); the loaders build such graphs for `symmetric_adjacency: True`
+        (/root/reference/src/data/preprocess.py:83-84), which every grid of the reference uses."""
+        if getattr(self, "_symmetric", None) is None:
+            if self.row is not None:
+                row, col, val, rel = self.row.long(), self.col.long(), self.val, self.rel
+            else:
+                v = next(iter(self._views.values()))
+                row, col, val, rel = v.coo_rows().long(), v.colidx.long() % self.n_nodes, v.vals, v.colidx.long() // self.n_nodes
+                if self.n_rel == 1:
+                    rel = None
+            n = self.n_nodes
+            r = rel.long() * n * n if rel is not None else 0
+            a, b = r + row * n + col, r + col * n + row
+
+            def canon(k):
+                if val is None:
+                    return torch.sort(k)[0], None
+                o1 = torch.sort(val, stable=True)[1]
+                o2 = torch.sort(k[o1], stable=True)[1]
+                o = o1[o2]
+                return k[o], val[o]
+            (ka, va), (kb, vb) = canon(a), canon(b)
+            self._symmetric = bool(torch.equal(ka, kb) and (va is None or torch.equal(va, vb)))
+        return self._symmetric
 
     @property
     def norm(self):

@@ -49,7 +49,8 @@ class GCNConv(_Conv):
     def call(self, inputs, out=None, csr=None, **kwargs):
         x, a = inputs
         csr = csr or a.norm
-        z = ops.dense(x, self.kernel, out_dtype=torch.bfloat16 if self.feature_dtype == "bf16" else None)
+        z = ops.gcn_transform(x, self.kernel, x.shape[0],
+                              out_dtype=torch.bfloat16 if self.feature_dtype == "bf16" else None)
         return ops.spmm(csr, z, self._out(out, csr.n_rows, x.device), bias=self.bias,
                         relu=self.activation == "relu")
 

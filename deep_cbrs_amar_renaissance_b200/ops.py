@@ -4,6 +4,7 @@ Every function takes CUDA torch tensors, launches on torch's current stream and
 returns torch tensors.  No CPU path exists: a non-CUDA tensor raises.
 """
 import ctypes
+import os
 
 import torch
 
@@ -265,6 +266,59 @@ def dense(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, rowop=L.ROWOP_
     return out
 
 
+# ---- the GCN transform Z = X W: fp32 FFMA kernel or the fp32-accurate tensor-core kernel (3xTF32) ----------------
+# "auto": tensor cores from TF32X3_MIN_ROWS graph nodes up (below that the layer is launch-latency bound and the FFMA
+# kernel keeps the round-1 bits of every MovieLens-sized parity case).  The choice is made on the GLOBAL node count, so
+# all ranks of a row partition and the single-GPU run take the same kernel.  CBRS_GCN_TRANSFORM=ffma|tf32x3 forces one.
+GCN_TRANSFORM = os.environ.get("CBRS_GCN_TRANSFORM", "auto")
+TF32X3_MIN_ROWS = 1 << 16
+
+
+def tf32x3_chosen(rows_total, k, n, x=None, out=None):
+    if GCN_TRANSFORM == "ffma" or (GCN_TRANSFORM == "auto" and rows_total < TF32X3_MIN_ROWS):
+        return False
+    if not L.load().cbrs_dense_tf32x3_eligible(int(k), int(n)):
+        return False
+    for t in (x, out):
+        if t is not None and (t.dtype != torch.float32 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16):
+            return False
+    return True
+
+
+def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None):
+    """act(x @ w + b) with the product as three TF32 tcgen05 MMAs (fp32-accurate, cbrs_dense_tf32x3)."""
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    m, k = x.shape
+    if w.dim() != 2 or w.shape[0] != k or not w.is_contiguous():
+        raise L.CbrsError("dense_tf32x3: kernel must be contiguous [{}, n], got {}".format(k, tuple(w.shape)))
+    n = w.shape[1]
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    out, ldo = _rowmajor(out)
+    image = torch.empty(lib.cbrs_dense_tf32x3_image_bytes(k, n), dtype=torch.uint8, device=x.device)
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(lib.cbrs_dense_tf32x3_prepare(_ptr(w, torch.float32), k, n, _ptr(image), _stream()), "cbrs_dense_tf32x3_prepare")
+    code = act if isinstance(act, int) else L.ACTS[act]
+    L.check(lib.cbrs_dense_tf32x3(_ptr(x), ldx, _ptr(image), _ptr(b, torch.float32), m, k, n, code, _ptr(out), ldo,
+                                  _ptr_array(peers) if peers else None, len(peers) if peers else 0, _stream()),
+            "cbrs_dense_tf32x3")
+    _count(2)
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("dense", e0, e1, m * n))
+    return out
+
+
+def gcn_transform(x, w, rows_total, out=None, out_dtype=None, peers=None):
+    """Z = x @ w for a GCN layer; rows_total = node count of the whole graph (decides the kernel, see above)."""
+    if out_dtype is None and (out is None or out.dtype == torch.float32) and tf32x3_chosen(rows_total, x.shape[1], w.shape[1], x, out):
+        return dense_tf32x3(x, w, out=out, peers=peers)
+    return dense(x, w, out=out, out_dtype=out_dtype, peers=peers)
+
+
 def dense_tc_eligible(f1, f2, n):
     """shapes cbrs_dense_tc takes: source widths multiples of 8, at most 256 outputs"""
     return f1 > 0 and f1 % 8 == 0 and f2 % 8 == 0 and 0 < n <= 256
@@ -407,12 +461,12 @@ def score_catalog_topk(P, Q, w2, b2, w3, b3, k, precision="fp32"):
 
 
 # ------------------------------------------------------------------ misc
-def synth_bipartite(n_users, n_items, n_edges, seed, device):
+def synth_bipartite(n_users, n_items, n_edges, seed, device, scatter_items=True):
     lib = L.load()
     row = torch.empty(2 * n_edges, dtype=torch.int32, device=device)
     col = torch.empty(2 * n_edges, dtype=torch.int32, device=device)
-    L.check(lib.cbrs_synth_bipartite(n_users, n_items, n_edges, seed, _ptr(row), _ptr(col), _stream()),
-            "cbrs_synth_bipartite")
+    L.check(lib.cbrs_synth_bipartite_ex(n_users, n_items, n_edges, seed, 1 if scatter_items else 0, _ptr(row), _ptr(col),
+                                        _stream()), "cbrs_synth_bipartite_ex")
     return row, col
 
 

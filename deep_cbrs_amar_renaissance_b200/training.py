@@ -174,14 +174,19 @@ def hybrid_rs_train(tape, rs, ug, ig, ub, ib):
 
 
 # ------------------------------------------------------------------ GNN layers
+def _bwd_csr(graph, view):
+    """The operator the backward of a sparse layer multiplies by: the forward CSR when the adjacency is symmetric
+    (A^T = A as a multiset of entries, DeviceGraph.symmetric), its transpose otherwise."""
+    csr = getattr(graph, view)
+    return csr if graph.symmetric else csr.transposed()
+
+
 def _gcn_train(tape, layer, x_node, graph, out):
     """GCNConv / RGCNConv: y = act(A_hat (x W) + b).  Backward: dPre = dY*act'(y); db = colsum dPre;
-    dZ = A_hat dPre (A_hat symmetric); dW = x^T dZ; dx = dZ W^T.
-    Relational operator (stacked layout: column r*N + j carries relation r): dZ_r = A_hat_r^T dPre = A_hat_r dPre when
-    every relation's block is symmetric (relation tags of (i,j) and (j,i) agree, as for relations defined by node
-    ranges on a symmetrised graph), which is one pass of the same sparse kernel per relation over a stacked operand
-    that is dPre in block r and zero elsewhere.  EXPERIMENTAL: the relational backward has not run on a GPU yet
-    (tests/test_zz_gpu_kg_training.py::test_rgcn_gradients, opt-in with CBRS_TEST_EXPERIMENTAL=1)."""
+    dZ = A_hat^T dPre (= A_hat dPre on a symmetric graph); dW = x^T dZ; dx = dZ W^T.
+    Relational operator (stacked layout [N, R*N]: column r*N + j carries relation r): ONE product with the transposed
+    stacked operator gives every relation's dZ_r at once (rows r*N .. (r+1)*N of the result), whatever the symmetry of
+    the individual relation blocks."""
     x = x_node.x
     csr = graph.norm
     n = x.shape[0]
@@ -201,17 +206,16 @@ def _gcn_train(tape, layer, x_node, graph, out):
             tape.wgrad(layer.bias, ops.colsum(dpre))
         if not relational:
             dz = torch.empty(n, layer.channels, dtype=torch.float32, device=x.device)
-            ops.spmm(csr, dpre, dz)
+            ops.spmm(_bwd_csr(graph, "norm"), dpre, dz)
             dw, _ = ops.dense_grad_w(x, dz, want_bias=False)
             tape.wgrad(layer.kernel, dw)
             x_node.add_grad(ops.dense(dz, ops.transpose(layer.kernel)))
             return
+        dz_all = torch.empty(len(kernels) * n, layer.channels, dtype=torch.float32, device=x.device)
+        ops.spmm(csr.transposed(), dpre, dz_all)
         dx = None
         for r, w in enumerate(kernels):
-            stacked = torch.zeros(len(kernels) * n, layer.channels, dtype=torch.float32, device=x.device)
-            stacked[r * n:(r + 1) * n].copy_(dpre)
-            dz = torch.empty(n, layer.channels, dtype=torch.float32, device=x.device)
-            ops.spmm(csr, stacked, dz)
+            dz = dz_all[r * n:(r + 1) * n]
             dw, _ = ops.dense_grad_w(x, dz, want_bias=False)
             tape.wgrad(w, dw)
             t = ops.dense(dz, ops.transpose(w))
@@ -232,7 +236,7 @@ def _lightgcn_train(tape, layer, x_node, graph, out):
             return
         dx = torch.empty_like(y) if y.is_contiguous() else torch.empty(y.shape, dtype=torch.float32, device=y.device)
         g = node.grad if node.grad.stride(1) == 1 else node.grad.contiguous()
-        ops.spmm(csr, g, dx)
+        ops.spmm(_bwd_csr(graph, "norm"), g, dx)
         x_node.add_grad(dx)
 
     tape.ops.append(bwd)
@@ -240,7 +244,7 @@ def _lightgcn_train(tape, layer, x_node, graph, out):
 
 
 def _dgcf_train(tape, layer, x_node, graph, out):
-    """DGCFConv: y = M (x * sigmoid(w)); M is symmetric (sum of symmetric pieces), so dGated = M dY."""
+    """DGCFConv: y = M (x * sigmoid(w)); dGated = M^T dY (M is a sum of symmetric pieces when A is symmetric)."""
     csr = graph.dgcf
     x = x_node.x
     w = layer.locality_adaptive.w
@@ -252,7 +256,7 @@ def _dgcf_train(tape, layer, x_node, graph, out):
         if node.grad is None:
             return
         dg = torch.empty(csr.n_rows, x.shape[1], dtype=torch.float32, device=x.device)
-        ops.spmm(csr, node.grad, dg)
+        ops.spmm(_bwd_csr(graph, "dgcf"), node.grad, dg)
         dx, dw = ops.row_gate_grad(dg, x, w)
         tape.wgrad(w, dw)
         x_node.add_grad(dx)
@@ -286,7 +290,8 @@ def _sage_train(tape, layer, x_node, graph, out):
         dagg = da[:, f:]
         t = ops.scale_rows_inv_degree(dagg, csr.rowptr) if mean else dagg.contiguous()
         dxa = torch.empty(csr.n_rows, f, dtype=torch.float32, device=x.device)
-        ops.spmm(csr, t, dxa, agg=L.AGG_SUM)  # A^T = A: the raw edge list holds both directions of every edge
+        # A^T = A on a symmetric graph (the raw edge list holds both directions of every edge); else the transpose
+        ops.spmm(_bwd_csr(graph, "raw"), t, dxa, agg=L.AGG_SUM)
         x_node.add_grad(ops.axpby(da[:, :f], 1.0, dxa, 1.0))
 
     tape.ops.append(bwd)
@@ -298,6 +303,10 @@ def _gat_train(tape, layer, x_node, graph, out):
     backward = csrc/gat_bwd.cu, then the dense pieces."""
     x = x_node.x
     csr = graph.raw
+    if not graph.symmetric:
+        # gat_bwd.cu reads the edges ENDING in j from row j, which holds them only when the structure is symmetric
+        raise NotImplementedError("GAT training needs a symmetric adjacency (symmetric_adjacency: True, as in every "
+                                  "grid of the reference); the forward pass has no such restriction")
     f = x.shape[1]
     w2 = layer.kernel.reshape(f, layer.channels)
     a_s, a_n = layer.attn_kernel_self.reshape(-1), layer.attn_kernel_neighs.reshape(-1)
@@ -659,4 +668,6 @@ class GraphedTrainStep:
         self.optimizer.iterations += 1
         self.optimizer.lr_t_dev.fill_(self.optimizer.rate(self.optimizer.iterations))
         self.graph.replay()
+        if hasattr(self.model, "invalidate"):
+            self.model.invalidate()  # a propagated table cached by evaluate / predict is stale after this update
         return self.loss.clone(), self.correct.clone()

@@ -188,6 +188,22 @@ int cbrs_dense_tc(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1,
                   const int64_t *idx2, int32_t f2, const void *w_image, const float *b, int64_t m, int32_t n,
                   int act, float *out, int64_t ldo, void *stream);
 
+/* fp32-ACCURATE Dense layer on the tensor cores: the GCN transform Z = X W (src/models/gnn.py:285-295: GCNConv =
+ * transform, then propagate) at scaled-graph size.  out = act(X @ W + b), everything fp32; the product is split
+ * into three kind::tf32 tcgen05 MMAs (Xl Wh + Xh Wl + Xh Wh with xh = tf32(x), xl = x - xh) accumulated in fp32 in
+ * TMEM, which agrees with the fp32 FFMA kernel to ~1e-6 of the output scale (parity test: 1e-5 vs float64).
+ * X tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B); W is handed over as the operand image written by
+ * cbrs_dense_tf32x3_prepare (cbrs_dense_tf32x3_image_bytes(k, n) bytes, 16-byte aligned; rewrite it when W changes).
+ * Shapes: k % 32 == 0, n % 16 == 0, 16 <= n <= 256, both operand images resident in shared memory (k*n <= 16384):
+ * cbrs_dense_tf32x3_eligible.  Rows of x 16-byte aligned.  out_peers_host / n_peers as in cbrs_dense_bcast.
+ * A row's result does not depend on its position in the 128-row tile => identical bits under any row partition.  */
+int cbrs_dense_tf32x3_eligible(int32_t k, int32_t n);
+size_t cbrs_dense_tf32x3_image_bytes(int32_t k, int32_t n);
+int cbrs_dense_tf32x3_prepare(const float *w, int32_t k, int32_t n, void *image, void *stream);
+int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k,
+                      int32_t n, int act, float *out, int64_t ldo, void *const *out_peers_host, int n_peers,
+                      void *stream);
+
 /* General form of cbrs_dense: the output (and its peer copies) can be written as bf16 (out_dtype =
  * CBRS_DTYPE_BF16, round to nearest even, ldo in elements) so that the GCN transform Z = X W feeds the bf16
  * sparse kernel without a conversion pass; out_peers_host / q_peers_host / n_peers as in cbrs_dense_bcast.  */
@@ -257,6 +273,10 @@ int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const float *Q, in
  * 2*n_edges COO entries: (u, U+i) for e < n_edges then (U+i, u).                */
 int cbrs_synth_bipartite(int64_t n_users, int64_t n_items, int64_t n_edges, uint64_t seed,
                          int32_t *coo_row, int32_t *coo_col, void *stream);
+/* scatter_items = 0: item id = popularity rank (no multiplicative scattering), i.e. ids as np.unique would leave a
+ * catalogue that is sorted by popularity - the adversarial case for a row-count partition.  1 = as above. */
+int cbrs_synth_bipartite_ex(int64_t n_users, int64_t n_items, int64_t n_edges, uint64_t seed, int scatter_items,
+                            int32_t *coo_row, int32_t *coo_col, void *stream);
 
 /* ---- peer memory + fused producer -> all-gather kernels (multi-GPU extension) -----
  * One process per GPU.  Every rank allocates the same ("symmetric") buffers with

@@ -12,7 +12,7 @@ def _splitmix(x):
     return x ^ (x >> np.uint64(31))
 
 
-def synth_bipartite(n_users, n_items, n_edges, seed):
+def synth_bipartite(n_users, n_items, n_edges, seed, scatter_items=True):
     """(row, col) int32 [2*n_edges]: (u, U+i) for every edge, then the transposed entries."""
     with np.errstate(over="ignore"):
         e = np.arange(n_edges, dtype=np.uint64)
@@ -26,6 +26,8 @@ def synth_bipartite(n_users, n_items, n_edges, seed):
     mult = 0x9E3779B1 % n_items or 1
     while math.gcd(mult, n_items) != 1:
         mult += 1
+    if not scatter_items:
+        mult = 1
     u = (h0 % np.uint64(n_users)).astype(np.int64)
     lvl = (h1 % np.uint64(levels)).astype(np.int64)
     span = (np.int64(c) << lvl).astype(np.uint64)

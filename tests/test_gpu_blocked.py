@@ -208,3 +208,34 @@ def test_default_policy_leaves_small_graphs_row_major(dev):
     assert blocking_policy(9746) == (0, 0) and blocking_policy(11_000_000)[0] > 0
     g = DeviceGraph.from_scipy(random_bipartite(40, 25, 400, seed=5), dev)
     assert g.norm.blocking == (0, 0) and g.norm.chunks["chunk_len"] is None
+
+
+def test_unscattered_generator_equals_its_numpy_twin_and_concentrates_hot_items(dev):
+    """scatter_items=0 (bench.py --unscattered): item id = popularity rank; same hash as the scattered generator"""
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from oracle import synth as osynth
+    n_users, n_items, n_edges = 5000, 3000, 40000
+    for scatter in (True, False):
+        row, col = ops.synth_bipartite(n_users, n_items, n_edges, 42, dev, scatter_items=scatter)
+        r, c = osynth.synth_bipartite(n_users, n_items, n_edges, 42, scatter_items=scatter)
+        assert np.array_equal(row.cpu().numpy(), r) and np.array_equal(col.cpu().numpy(), c)
+    deg = np.bincount(c[:n_edges] - n_users, minlength=n_items)
+    assert deg[:n_items // 8].sum() > 0.25 * n_edges  # the first eighth of the ids holds far more than an eighth
+
+
+def test_transposed_view_and_symmetry_flag(dev):
+    from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
+    from scipy import sparse
+    adj = random_bipartite(60, 30, 700, seed=1, n_props=10, n_links=50, dup_links=10)
+    g = DeviceGraph.from_scipy(adj, dev)
+    assert g.symmetric
+    half = sparse.coo_matrix((adj.data[:len(adj.data) // 2], (adj.row[:len(adj.data) // 2], adj.col[:len(adj.data) // 2])),
+                             shape=adj.shape)
+    gd = DeviceGraph.from_scipy(half, dev)
+    assert not gd.symmetric
+    t = gd.plain.transposed()
+    want = half.tocsr().T.tocsr()
+    want.sort_indices()
+    got = t.to_scipy()
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.array_equal(got.data, want.data)

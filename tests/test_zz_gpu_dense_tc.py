@@ -132,11 +132,11 @@ def test_hybrid_scorer_on_tensor_cores():
     close(got, want, "bf16 hybrid scores", rtol=2e-3)   # bf16 re-rounding of near-tie activations between layers
 
 
-@pytest.mark.skipif(os.environ.get("CBRS_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental kernel variant (csrc/dense_tc_x.cu), not yet run on a GPU: opt in with CBRS_TEST_EXPERIMENTAL=1")
-def test_experimental_variant():
-    """the same parity cases through CBRS_DENSE_TC_VARIANT=4 (read once per process, hence the child process)"""
-    env = dict(os.environ, CBRS_DENSE_TC_VARIANT="4", CBRS_TEST_EXPERIMENTAL="0")
+@pytest.mark.parametrize("variant", ["3", "4"])
+def test_each_kernel_variant_on_every_shape(variant):
+    """cbrs_dense_tc picks one of two kernels by depth (dense_tc.cu / dense_tc_x.cu); the same parity cases with each
+    kernel forced on every shape (CBRS_DENSE_TC_VARIANT is read once per process, hence the child process)"""
+    env = dict(os.environ, CBRS_DENSE_TC_VARIANT=variant)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k",
                         "single_source or gather_concat or hybrid_scorer"], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -134,10 +134,8 @@ def test_kg_train_steps_reduce_the_loss_and_replay_matches_eager(case, graphs):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("CBRS_TEST_EXPERIMENTAL") != "1",
-                    reason="relational backward written after the round's last GPU session: opt in with CBRS_TEST_EXPERIMENTAL=1")
 def test_rgcn_gradients():
-    """training step of the relational extension (row R): one sparse pass per relation over a stacked operand"""
+    """training step of the relational extension (row R): one product with the transposed stacked operator"""
     from deep_cbrs_amar_renaissance_b200 import training
     from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
     from oracle import graph as og
