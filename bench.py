@@ -237,7 +237,7 @@ def run_b200(args):
         # CBRS_EXCHANGE=nccl|peer; each node type is cut into N blocks of equal EDGE count
         part = RowPartition([n_users, n_items], final_types=[1],
                             balance_rowptr=None if args.row_count_cuts else graph.norm.rowptr).attach(seq)
-        os.environ["CBRS_EXCHANGE"] = part.exchange + ("+fused-transform" if part.exchange == "peer" and part.pipeline == "fused" else "")
+        os.environ["CBRS_EXCHANGE"] = part.exchange + ("+" + part.pipeline if part.exchange == "peer" else "")
         part.csr_slices("norm", graph)
         part.release_full_views(graph)
     else:

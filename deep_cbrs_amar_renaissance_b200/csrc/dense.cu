@@ -29,7 +29,18 @@ struct DenseParams {
     float *q_peer[CBRS_MAX_PEERS - 1];
     int n_peer;
     int out_bf16;  // out / out_peer hold bf16 (round to nearest even), ldo in elements
+    // grouped (relational) output: column c of row m is stored at row (c / group_h) * group_rows + m, column c % group_h,
+    // i.e. X . [W_0 | ... | W_{R-1}] lands directly in the stacked [R * group_rows, group_h] operand of the relational
+    // sparse kernel.  group_h == 0: the ordinary [m, n] output.
+    int32_t group_h;
+    int64_t group_rows;
 };
+
+__device__ __forceinline__ int64_t out_index(const DenseParams &p, int64_t m, int ng) {
+    if (p.group_h == 0) return m * p.ldo + ng;
+    const int r = ng / p.group_h;
+    return ((int64_t)r * p.group_rows + m) * p.ldo + (ng - r * p.group_h);
+}
 
 __device__ __forceinline__ void store_out1(float *base, int64_t idx, float v, int bf16) {
     if (bf16) reinterpret_cast<__nv_bfloat16 *>(base)[idx] = __float2bfloat16_rn(v);
@@ -177,8 +188,8 @@ __global__ void __launch_bounds__(kDenseThreads) dense_kernel(const DenseParams 
             const int ng = n0 + tx * TN + j;
             if (ng < p.n) {
                 const float v = apply_act(acc[i][j] * scale, p.act);
-                store_out1(p.out, m * p.ldo + ng, v, p.out_bf16);
-                for (int q = 0; q < p.n_peer; ++q) store_out1(p.out_peer[q], m * p.ldo + ng, v, p.out_bf16);
+                store_out1(p.out, out_index(p, m, ng), v, p.out_bf16);
+                for (int q = 0; q < p.n_peer; ++q) store_out1(p.out_peer[q], out_index(p, m, ng), v, p.out_bf16);
             }
         }
     }
@@ -325,7 +336,8 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_fast_kernel(const Dens
         if (TN == 8) return n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
         return n0 + tx * TN + j;
     };
-    const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out) % (p.out_bf16 ? 8 : 16) == 0) && TN >= 4;
+    const bool vec_out = (p.ldo % 4 == 0) && (((uintptr_t)p.out) % (p.out_bf16 ? 8 : 16) == 0) && TN >= 4 &&
+                         (p.group_h % 4 == 0);  // a 4-wide group must not straddle two relation blocks
 #pragma unroll
     for (int i = 0; i < kTM; ++i) {
         const int64_t m = m0 + ty + 16 * i;
@@ -372,14 +384,14 @@ __global__ void __launch_bounds__(kDenseThreads, 2) dense_fast_kernel(const Dens
                 for (int j0 = 0; j0 < TN; j0 += 4) {
                     const int ng = col_of(j0);
                     if (ng < p.n)  // n % 4 == 0: a 4-wide group is entirely in or out
-                        store_out4(obase, m * p.ldo + ng, acc[i][j0], acc[i][(j0 + 1) % TN], acc[i][(j0 + 2) % TN],
+                        store_out4(obase, out_index(p, m, ng), acc[i][j0], acc[i][(j0 + 1) % TN], acc[i][(j0 + 2) % TN],
                                    acc[i][(j0 + 3) % TN], p.out_bf16);
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < TN; ++j) {
                     const int ng = col_of(j);
-                    if (ng < p.n) store_out1(obase, m * p.ldo + ng, acc[i][j], p.out_bf16);
+                    if (ng < p.n) store_out1(obase, out_index(p, m, ng), acc[i][j], p.out_bf16);
                 }
             }
         }
@@ -427,8 +439,11 @@ static int dense_impl(const float *x1, int64_t ld1, const int64_t *idx1, int32_t
                       const int64_t *idx2, int32_t f2, const float *w, const float *b, int64_t m, int32_t n, int act,
                       int rowop, const float *a_self, const float *a_neigh, float *p_out, float *q_out, float *out,
                       int64_t ldo, void *const *out_peers_host, void *const *q_peers_host, int n_peers, int out_dtype,
-                      void *stream) {
+                      void *stream, int32_t group_h = 0, int64_t group_rows = 0) {
     CBRS_REQUIRE(x1 && w && out, CBRS_E_INVALID, "dense: null argument");
+    CBRS_REQUIRE(group_h == 0 || (group_h > 0 && n % group_h == 0 && group_rows >= m && rowop == CBRS_ROWOP_NONE &&
+                                  ldo >= group_h),
+                 CBRS_E_INVALID, "dense: grouped output needs n %% group_h == 0, group_rows >= m, no row-op");
     CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || out_dtype == CBRS_DTYPE_BF16, CBRS_E_INVALID, "dense: out_dtype=%d", out_dtype);
     CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || !(rowop == CBRS_ROWOP_L2NORM && n > 128), CBRS_E_UNSUPPORTED,
                  "dense: the two-pass l2-normalise (n > 128) writes float32 only");
@@ -438,7 +453,7 @@ static int dense_impl(const float *x1, int64_t ld1, const int64_t *idx1, int32_t
                  "dense: the attention row-op with peers needs q_peers");
     CBRS_REQUIRE(n_peers == 0 || !(rowop == CBRS_ROWOP_L2NORM && n > 128), CBRS_E_UNSUPPORTED,
                  "dense: the two-pass l2-normalise (n > 128) has no peer form");
-    CBRS_REQUIRE(m >= 0 && n > 0 && f1 > 0 && f2 >= 0 && ld1 >= f1 && ldo >= n, CBRS_E_INVALID,
+    CBRS_REQUIRE(m >= 0 && n > 0 && f1 > 0 && f2 >= 0 && ld1 >= f1 && (ldo >= n || group_h > 0), CBRS_E_INVALID,
                  "dense: m=%lld n=%d f1=%d f2=%d ld1=%lld ldo=%lld", (long long)m, n, f1, f2, (long long)ld1, (long long)ldo);
     CBRS_REQUIRE((x2 == nullptr) == (f2 == 0), CBRS_E_INVALID, "dense: second source and f2 disagree");
     CBRS_REQUIRE(!x2 || ld2 >= f2, CBRS_E_INVALID, "dense: ld2=%lld < f2=%d", (long long)ld2, f2);
@@ -451,6 +466,8 @@ static int dense_impl(const float *x1, int64_t ld1, const int64_t *idx1, int32_t
     DenseParams p{x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out, out, ldo};
     p.n_peer = n_peers;
     p.out_bf16 = out_dtype == CBRS_DTYPE_BF16;
+    p.group_h = group_h;
+    p.group_rows = group_rows;
     for (int q = 0; q < CBRS_MAX_PEERS - 1; ++q) {
         p.out_peer[q] = q < n_peers ? (float *)out_peers_host[q] : nullptr;
         p.q_peer[q] = (q < n_peers && q_peers_host) ? (float *)q_peers_host[q] : nullptr;
@@ -502,4 +519,13 @@ extern "C" int cbrs_dense_ex(const float *x1, int64_t ld1, const int64_t *idx1, 
                              void *stream) {
     return dense_impl(x1, ld1, idx1, f1, x2, ld2, idx2, f2, w, b, m, n, act, rowop, a_self, a_neigh, p_out, q_out,
                       (float *)out, ldo, out_peers_host, q_peers_host, n_peers, out_dtype, stream);
+}
+
+extern "C" int cbrs_dense_grouped(const float *x, int64_t ldx, const float *w_cat, int64_t m, int32_t f, int32_t h,
+                                  int32_t n_groups, void *out, int64_t ldo, int64_t group_rows, int out_dtype,
+                                  void *const *out_peers_host, int n_peers, void *stream) {
+    CBRS_REQUIRE(h > 0 && n_groups > 0, CBRS_E_INVALID, "dense_grouped: h=%d n_groups=%d", h, n_groups);
+    return dense_impl(x, ldx, nullptr, f, nullptr, 0, nullptr, 0, w_cat, nullptr, m, h * n_groups, CBRS_ACT_NONE,
+                      CBRS_ROWOP_NONE, nullptr, nullptr, nullptr, nullptr, (float *)out, ldo, out_peers_host, nullptr, n_peers,
+                      out_dtype, stream, h, group_rows);
 }

@@ -10,7 +10,7 @@ import numpy as np
 import pandas as pd
 
 from .datasets import HybridUserItemEmbeddings, UserItemEmbeddings, UserItemGraph, UserItemGraphEmbeddings
-from .preprocess import build_adjacency_matrix, get_user_properties
+from .preprocess import RelationalAdjacency, build_adjacency_matrix, edge_relations, get_user_properties
 
 
 def _read(path, sep):
@@ -66,7 +66,7 @@ def _lookup(vocab, raw, what, device_ids=None):
 
 def load_train_test_ratings(train_filepath, test_filepath, props_filepath=None, sep='\t',
                             return_adjacency=False, type_adjacency='unary', sparse_adjacency=True,
-                            symmetric_adjacency=True, device_ids=None):
+                            symmetric_adjacency=True, device_ids=None, relations=None):
     """Ratings with sequential ids (items offset by the user count) [+ adjacency].
     device_ids: None = compaction on the GPU for columns of >= 65,536 rows when one is present,
     True / False to force; the result is the same array either way."""
@@ -80,16 +80,22 @@ def load_train_test_ratings(train_filepath, test_filepath, props_filepath=None, 
     if not return_adjacency:
         return (train, test), (users, items)
 
-    props = triples = None
+    props = triples = predicates = None
     if type_adjacency in ('unary-kg', 'unary-uip') and props_filepath is not None:
         raw = _read(props_filepath, sep)
         props, p_of = _unique_inverse(raw[:, 1], device_ids)
-        # the relation column is dropped, every link weighs one (loaders.py:67-68)
+        # the relation column is dropped, every link weighs one (loaders.py:67-68) ...
         triples = np.stack([_lookup(items, raw[:, 0], 'property item', device_ids), p_of + len(items),
                             np.ones(len(raw), dtype=raw.dtype)], axis=1)
+        predicates = raw[:, 2]   # ... unless relations= asks for typed edges (row R, extension; default None = dropped)
     adj = build_adjacency_matrix(train, users, items, props_triples=triples, props=props,
                                  type_adjacency=type_adjacency, sparse_adjacency=sparse_adjacency,
                                  symmetric_adjacency=symmetric_adjacency)
+    if relations is not None:
+        if type_adjacency != 'unary-uip' or predicates is None or not sparse_adjacency:
+            raise ValueError("relations= needs the sparse 'unary-uip' graph and a properties file")
+        rel, n_rel = edge_relations(int((train[:, 2] == 1).sum()), predicates, relations, symmetric_adjacency)
+        adj = RelationalAdjacency(adj, rel, n_rel)
     return (train, test), (users, items), adj
 
 
@@ -146,11 +152,13 @@ def load_hybrid_embeddings(train_ratings_filepath, test_ratings_filepath, graph_
 def load_user_item_graph(train_ratings_filepath, test_ratings_filepath, props_triples_filepath=None,
                          sep='\t', type_adjacency='unary', sparse_adjacency=True,
                          symmetric_adjacency=True, user_properties=False, shuffle=True,
-                         train_batch_size=1024, test_batch_size=2048):
+                         train_batch_size=1024, test_batch_size=2048, relations=None):
+    """relations (extension, row R): None = the reference's untyped graph; 'node-range' / 'predicate' = typed edges
+    for basic.BasicRGCN (preprocess.RelationalAdjacency)."""
     (train, test), (users, items), adj = load_train_test_ratings(
         train_ratings_filepath, test_ratings_filepath, props_triples_filepath, sep=sep,
         return_adjacency=True, type_adjacency=type_adjacency, sparse_adjacency=sparse_adjacency,
-        symmetric_adjacency=symmetric_adjacency)
+        symmetric_adjacency=symmetric_adjacency, relations=relations)
     if user_properties and type_adjacency != 'unary-uip':  # loaders.py:319-322 / :427-430
         ui_adj, ip_adj = adj
         adj = (ui_adj, ip_adj, get_user_properties(ui_adj, ip_adj, len(users), len(items)))

@@ -31,6 +31,50 @@ def get_user_properties(ui_adj, ip_adj, n_users, n_items):
     return up.tocoo()
 
 
+class RelationalAdjacency:
+    """A COO adjacency plus one relation id per stored entry (scope row R, extension).
+
+    The reference reads the predicate column of props2id-*.tsv and drops it (/root/reference/src/data/loaders.py:63-68):
+    its user-item-properties graphs are untyped.  `load_user_item_graph(..., relations=...)` keeps a type per edge
+    instead and hands the models this wrapper; everything that takes the reference's scipy matrix still works on
+    `.coo` (and `tocoo()` / `.shape`), so the non-relational layer families run on the same object unchanged.
+      relations='node-range': 0 = user-item edge, 1 = item-property edge (defined by the node-id ranges of
+                              /root/reference/src/data/preprocess.py:149-159);
+      relations='predicate' : 0 = user-item edge, 1 + p = item-property edge with the p-th distinct predicate.
+    Both directions of a symmetrised edge carry the same relation, so every relation block is symmetric."""
+
+    def __init__(self, coo, rel, n_rel):
+        self.coo, self.rel, self.n_rel = coo, np.ascontiguousarray(rel, dtype=np.int32), int(n_rel)
+        if len(self.rel) != coo.nnz:
+            raise ValueError("one relation id per stored entry: {} ids for {} entries".format(len(self.rel), coo.nnz))
+        self.shape = coo.shape
+
+    def tocoo(self):
+        return self.coo
+
+    def relation_blocks(self):
+        """[scipy COO per relation] (tests, oracle)"""
+        c = self.coo
+        return [sparse.coo_matrix((c.data[self.rel == r], (c.row[self.rel == r], c.col[self.rel == r])), shape=c.shape)
+                for r in range(self.n_rel)]
+
+
+def edge_relations(n_liked, props_triples_rel, relations, symmetric):
+    """relation id of every entry of the 'unary-uip' COO in its entry order: rating edges, property edges, then (when
+    symmetric) the transposed entries in the same order.  props_triples_rel: the predicate column of the triples."""
+    if relations == 'node-range':
+        rel_p = np.ones(len(props_triples_rel), dtype=np.int32)
+        n_rel = 2
+    elif relations == 'predicate':
+        preds, inv = np.unique(props_triples_rel, return_inverse=True)
+        rel_p = (1 + inv).astype(np.int32)
+        n_rel = 1 + len(preds)
+    else:
+        raise ValueError("relations must be None, 'node-range' or 'predicate', got {!r}".format(relations))
+    one = np.concatenate([np.zeros(n_liked, dtype=np.int32), rel_p])
+    return (np.concatenate([one, one]) if symmetric else one), n_rel
+
+
 def _coo(data, rows, cols, n, symmetric, as_sparse):
     m = sparse.coo_matrix((data, (rows, cols)), shape=[n, n], dtype=np.float32)
     if symmetric:

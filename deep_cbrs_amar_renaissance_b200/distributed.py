@@ -267,10 +267,13 @@ class RowPartition:
         # exchange is spread over the whole sparse kernel; other shapes fall back to "off"
         # measured on config 5: the fused sparse kernel is ~10 % slower than the plain one, which pays off once the
         # transform-with-stores kernel it replaces is NVLink-bound: 8 GPUs 84.0 -> 94.2 G edges/s, 2 GPUs 27.1 -> 26.2
-        self.pipeline = pipeline or os.environ.get("CBRS_PIPELINE", "fused" if dist.get_world_size(group) >= 4 else "off")
-        if self.pipeline not in ("off", "kernel", "ce", "fused"):
-            raise ValueError("pipeline must be 'off', 'fused', 'kernel' or 'ce'")
-        self.row_blocks = int(row_blocks or os.environ.get("CBRS_ROW_BLOCKS", "1" if self.pipeline in ("off", "fused") else "2"))
+        # "replicate" (default, round 2): GCN layers compute the whole transform on every rank and exchange the layer
+        # OUTPUT from the sparse kernel's epilogue instead (see _propagate_peer); with the tensor-core transform this
+        # beats every exchange of Z: nothing NVLink-bound is exposed and no software pipeline is needed
+        self.pipeline = pipeline or os.environ.get("CBRS_PIPELINE", "replicate")
+        if self.pipeline not in ("off", "kernel", "ce", "fused", "replicate"):
+            raise ValueError("pipeline must be 'replicate', 'off', 'fused', 'kernel' or 'ce'")
+        self.row_blocks = int(row_blocks or os.environ.get("CBRS_ROW_BLOCKS", "1" if self.pipeline in ("off", "fused", "replicate") else "2"))
         self._side = None
         self._sym = {}
         self.n_rows_by_type = list(n_rows_by_type)
@@ -410,20 +413,40 @@ class RowPartition:
             relu = getattr(layer, "activation", None) == "relu"
             nxt = layers[l + 1] if l + 1 < len(layers) else None
             # the next layer's sparse kernel gathers from this output directly -> every row travels
-            everywhere = isinstance(nxt, (GraphSageConv, LightGCNConv))
+            everywhere = isinstance(nxt, (GraphSageConv, LightGCNConv)) or (self.pipeline == "replicate" and
+                                                                             isinstance(nxt, GCNConv))
 
             def out_peers(view, a):
                 return osb.peer_addrs(view) if (everywhere or is_final(a)) else None
 
-            if isinstance(layer, (GCNConv, RGCNConv)):
+            if isinstance(layer, GCNConv) and self.pipeline == "replicate":
+                # Every rank computes the WHOLE transform Z = X W itself (2.5 ms for 1.1e7 x 128 x 128 on the tensor
+                # cores) from a layer input that is complete on every rank: layer 0 reads the replicated embedding
+                # table, later layers read the previous output, whose rows the sparse kernel's epilogue stored into
+                # every rank's copy while it ran.  So the only inter-GPU traffic of a layer is spread over its sparse
+                # kernel, nothing NVLink-bound is ever exposed, and there is no second exchange for the final rows.
+                if l > 0:
+                    heap.barrier()   # the previous output's remote rows have landed
+                zdt = torch.bfloat16 if getattr(layer, "feature_dtype", "fp32") == "bf16" else torch.float32
+                z = self._buf(("zrep",), n, layer.channels, emb.device, zdt)
+                ops.gcn_transform(x_full, layer.kernel, n, out=z)
+                for sl in self.csr_slices("norm", graph):
+                    a, b = sl.row_offset, sl.row_offset + sl.n_rows
+                    ov = out[a:b]
+                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, peers=out_peers(ov, a))
+                z_ahead = False
+            elif isinstance(layer, (GCNConv, RGCNConv)):
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
                 zdt = torch.bfloat16 if getattr(layer, "feature_dtype", "fp32") == "bf16" else torch.float32
                 zsb, z = self._symbuf(("z", l), len(kernels) * n, layer.channels, zdt)
                 if not z_ahead:
-                    for r, w in enumerate(kernels):
-                        for a, b in self.mine:
-                            zv = z[r * n + a:r * n + b]
-                            ops.gcn_transform(x_full[a:b], w, n, out=zv, peers=zsb.peer_addrs(zv))
+                    for a, b in self.mine:
+                        if len(kernels) > 1:   # relational: every relation's transform of the block in one launch
+                            zv = z[a:(len(kernels) - 1) * n + b]
+                            ops.dense_grouped(x_full[a:b], kernels, zv, n, peers=zsb.peer_addrs(zv))
+                        else:
+                            zv = z[a:b]
+                            ops.gcn_transform(x_full[a:b], kernels[0], n, out=zv, peers=zsb.peer_addrs(zv))
                     heap.barrier()
                 # software pipeline: while the sparse kernel works on row block b+1, the NEXT layer's transform
                 # of block b is computed and stored into every rank's copy on a side stream
@@ -555,9 +578,12 @@ class RowPartition:
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
                 zdt = torch.bfloat16 if getattr(layer, "feature_dtype", "fp32") == "bf16" else torch.float32
                 z = self._buf(("z", l), len(kernels) * n, layer.channels, dev, zdt)
-                for r, w in enumerate(kernels):
-                    for a, b in self.mine:
-                        ops.gcn_transform(x_full[a:b], w, n, out=z[r * n + a:r * n + b])
+                for a, b in self.mine:
+                    if len(kernels) > 1:
+                        ops.dense_grouped(x_full[a:b], kernels, z[a:(len(kernels) - 1) * n + b], n)
+                    else:
+                        ops.gcn_transform(x_full[a:b], kernels[0], n, out=z[a:b])
+                for r in range(len(kernels)):
                     self._exchange(z[r * n:(r + 1) * n])
                 for sl in self.csr_slices("norm", graph):
                     ops.spmm(sl, z, out[sl.row_offset:sl.row_offset + sl.n_rows], bias=layer.bias, relu=relu)

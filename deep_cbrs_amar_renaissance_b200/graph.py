@@ -110,8 +110,9 @@ class DeviceGraph:
         self._views = {}
 
     @classmethod
-    def from_scipy(cls, adj, device=None, chunk_edges=DEFAULT_CHUNK_EDGES):
-        """scipy sparse (any format; COO entry order is preserved) -> device COO."""
+    def from_scipy(cls, adj, device=None, chunk_edges=DEFAULT_CHUNK_EDGES, relational=False):
+        """scipy sparse (any format; COO entry order is preserved) -> device COO.  relational=True keeps the edge types
+        of a data.preprocess.RelationalAdjacency (RGCN); every other layer family sees the untyped graph."""
         if isinstance(adj, DeviceGraph):
             return adj
         device = torch.device(device or "cuda")
@@ -119,6 +120,9 @@ class DeviceGraph:
         row = torch.from_numpy(np.ascontiguousarray(coo.row, dtype=np.int32)).to(device)
         col = torch.from_numpy(np.ascontiguousarray(coo.col, dtype=np.int32)).to(device)
         val = torch.from_numpy(np.ascontiguousarray(coo.data, dtype=np.float32)).to(device)
+        if relational and hasattr(adj, "rel") and hasattr(adj, "n_rel"):   # typed edges (row R)
+            rel = torch.from_numpy(np.ascontiguousarray(adj.rel, dtype=np.int32)).to(device)
+            return cls(row, col, val, coo.shape[0], chunk_edges, rel=rel, n_rel=adj.n_rel)
         return cls(row, col, val, coo.shape[0], chunk_edges)
 
     def _view(self, name, flags, keep_vals, self_rel=0):

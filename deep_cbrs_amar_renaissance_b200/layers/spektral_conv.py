@@ -137,7 +137,6 @@ class RGCNConv(_Conv):
         csr = csr or a.norm
         n = x.shape[0]
         z = torch.empty(self.n_rel * n, self.channels, dtype=torch.float32, device=x.device)
-        for r, w in enumerate(self.kernels):
-            ops.dense(x, w, out=z[r * n:(r + 1) * n])
+        ops.dense_grouped(x, self.kernels, z, n)   # all relations' transforms, one launch, straight into the stack
         return ops.spmm(csr, z, self._out(out, csr.n_rows, x.device), bias=self.bias,
                         relu=self.activation == "relu")

@@ -244,12 +244,13 @@ class DGCF(GNN):
 
 
 class RGCN(GNN):
-    """Relational extension (scope row R): `adj_matrix` is a DeviceGraph carrying relation ids
-    (graph.DeviceGraph(..., rel=, n_rel=)); with one relation it equals GCN."""
+    """Relational extension (scope row R): `adj_matrix` is what `load_user_item_graph(..., relations=...)` returns
+    (data.preprocess.RelationalAdjacency) or a DeviceGraph carrying relation ids (graph.DeviceGraph(..., rel=, n_rel=));
+    with one relation - e.g. a plain scipy matrix - it equals GCN."""
 
     def __init__(self, adj_matrix, n_hiddens=(8, 8, 8), **kwargs):
         if not isinstance(adj_matrix, DeviceGraph):
-            adj_matrix = DeviceGraph.from_scipy(adj_matrix)
+            adj_matrix = DeviceGraph.from_scipy(adj_matrix, relational=True)   # keeps RelationalAdjacency's edge types
         self.n_hiddens = n_hiddens
         self.n_rel = adj_matrix.n_rel
         super().__init__(adj_matrix, len(n_hiddens), **kwargs)

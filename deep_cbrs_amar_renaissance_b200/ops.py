@@ -319,6 +319,32 @@ def gcn_transform(x, w, rows_total, out=None, out_dtype=None, peers=None):
     return dense(x, w, out=out, out_dtype=out_dtype, peers=peers)
 
 
+def dense_grouped(x, kernels, out, group_rows, peers=None):
+    """Relational transform in one launch: out[r * group_rows + m, :] = x[m] @ kernels[r] for every relation r
+    (cbrs_dense_grouped).  `out` is the stacked operand [R * group_rows, h] (or a row-offset view of it)."""
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    m, f = x.shape
+    h = kernels[0].shape[1]
+    w_cat = kernels[0].contiguous() if len(kernels) == 1 else torch.cat(list(kernels), dim=1).contiguous()
+    out, ldo = _rowmajor(out, (torch.float32, torch.bfloat16))
+    if out.shape[1] != h or out.shape[0] < (len(kernels) - 1) * group_rows + m:
+        raise L.CbrsError("dense_grouped: stacked output {} too small for {} x [{}, {}] at stride {}".format(
+            tuple(out.shape), len(kernels), m, h, group_rows))
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(lib.cbrs_dense_grouped(_ptr(x), ldx, _ptr(w_cat, torch.float32), m, f, h, len(kernels), _ptr(out), ldo,
+                                   int(group_rows), L.DTYPE_BF16 if out.dtype == torch.bfloat16 else L.DTYPE_F32,
+                                   _ptr_array(peers) if peers else None, len(peers) if peers else 0, _stream()),
+            "cbrs_dense_grouped")
+    _count(1)
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("dense", e0, e1, m * h * len(kernels)))
+    return out
+
+
 def dense_tc_eligible(f1, f2, n):
     """shapes cbrs_dense_tc takes: source widths multiples of 8, at most 256 outputs"""
     return f1 > 0 and f1 % 8 == 0 and f2 % 8 == 0 and 0 < n <= 256

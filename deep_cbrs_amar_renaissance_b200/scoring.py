@@ -15,6 +15,15 @@ from . import ops
 _PAIR_BUDGET = 1 << 18  # pairs per block: keeps a block's 64-wide activations L2-resident
 
 
+def _blocks(n_users, n_items, user_block=None, budget=_PAIR_BUDGET):
+    """(users per block, items per block): a block never exceeds `budget` pairs.  Catalogs wider than the budget are
+    cut along the ITEM axis too (the per-user top-k is then merged across item blocks), so no path degenerates into
+    one user per Python iteration however large the catalog is."""
+    ib = min(n_items, budget)
+    ub = user_block or max(1, budget // ib)
+    return min(ub, max(n_users, 1)), ib
+
+
 def _block_indices(cache, ub, n_items, device):
     key = (ub, n_items)
     if key not in cache:
@@ -57,31 +66,54 @@ def catalog_scores(model, emb, n_users, n_items, users=None):
     items = torch.arange(n_users, n_users + n_items, device=dev, dtype=torch.int64)
     score = _pair_scorer(model, emb, users, items)
     cache = {}
-    ub = max(1, _PAIR_BUDGET // n_items)
+    ub, ib = _blocks(users.numel(), n_items)
     out = torch.empty(users.numel(), n_items, dtype=torch.float32, device=dev)
     for u0 in range(0, users.numel(), ub):
         nb = min(ub, users.numel() - u0)
-        pu, pi = _block_indices(cache, nb, n_items, dev)
-        out[u0:u0 + nb] = score(pu + u0, pi).reshape(nb, n_items)
+        for i0 in range(0, n_items, ib):
+            ni = min(ib, n_items - i0)
+            pu, pi = _block_indices(cache, nb, ni, dev)
+            out[u0:u0 + nb, i0:i0 + ni] = score(pu + u0, pi + i0).reshape(nb, ni)
     return out
 
 
-def _fused_basic(model, emb, users, items, k, precision="fp32"):
-    """BasicRS with two hidden classifier layers -> the fused kernel (cbrs_score_catalog_topk)."""
+def _hoisted_sources(model, emb, users, items):
+    """(user source, item source, classifier) when the scorer is `clf([f(user) || g(item)])` with f, g depending on one
+    entity each - BasicRS (src/models/basic.py:31-37) and the entity-based HybridCBRS with plain concatenation
+    (src/models/hybrid.py:83-89: dense3a sees the user's two embeddings only, dense3b the item's) - else None."""
     rs = model.rs
-    if not hasattr(rs, "unet") or len(rs.clf.layers) != 3 or k > 128:
+    if hasattr(rs, "unet"):  # BasicRS
+        if rs.unet.layers:
+            return (rs.unet.call_sources([(emb, users)]), None), (rs.inet.call_sources([(emb, items)]), None), rs.clf
+        return (emb, users), (emb, items), rs.clf
+    plain = rs.residual is None and all(f.method == 'concatenate' for f in (rs.fuse1a, rs.fuse1b, rs.fuse2))
+    if rs.feature_based or not plain or model.content_table is None:
         return None
-    l1, l2, l3 = rs.clf.layers
+    table = model.content_table
+    ug = rs.dense1a.call_sources([(emb, users)])
+    ig = rs.dense1b.call_sources([(emb, items)])
+    ub = rs.dense2a.call_sources([(table, users)])
+    ib = rs.dense2b.call_sources([(table, items)])
+    x1 = rs.dense3a.call_sources([(ug, None), (ub, None)])
+    x2 = rs.dense3b.call_sources([(ig, None), (ib, None)])
+    return (x1, None), (x2, None), rs.clf
+
+
+def _fused_basic(model, emb, users, items, k, precision="fp32"):
+    """Scorers of the form clf([f(user) || g(item)]) with two hidden classifier layers -> the fused kernel
+    (cbrs_score_catalog_topk: hoisted first layer, second layer, output, sigmoid and running top-k in one pass)."""
+    clf = model.rs.clf
+    if len(clf.layers) != 3 or k > 128:
+        return None
+    l1, l2, l3 = clf.layers
     if l1.activation != "relu" or l2.activation != "relu" or l3.units != 1:
         return None
     if l1.units % 8 or l1.units > 256 or l2.units > 128:
         return None
-    if rs.unet.layers:
-        ut = rs.unet.call_sources([(emb, users)])
-        it = rs.inet.call_sources([(emb, items)])
-        u_src, i_src = (ut, None), (it, None)
-    else:
-        u_src, i_src = (emb, users), (emb, items)
+    src = _hoisted_sources(model, emb, users, items)
+    if src is None:
+        return None
+    u_src, i_src, _ = src
     du = u_src[0].shape[1]
     l1.build_for(du + i_src[0].shape[1])
     l2.build_for(l1.units)
@@ -101,13 +133,27 @@ def catalog_top_k(model, emb, n_users, n_items, k=10, users=None, user_block=Non
             return out
     score = _pair_scorer(model, emb, users, items)
     cache = {}
-    ub = user_block or max(1, _PAIR_BUDGET // n_items)
+    ub, ib = _blocks(users.numel(), n_items, user_block)
     ids = torch.empty(users.numel(), k, dtype=torch.int32, device=dev)
     vals = torch.empty(users.numel(), k, dtype=torch.float32, device=dev)
     for u0 in range(0, users.numel(), ub):
         nb = min(ub, users.numel() - u0)
-        pu, pi = _block_indices(cache, nb, n_items, dev)
-        s = score(pu + u0, pi).reshape(nb, n_items)
-        bi, bv = ops.topk_rows(s, k)
-        ids[u0:u0 + nb], vals[u0:u0 + nb] = bi, bv
+        best_i = best_v = None
+        for i0 in range(0, n_items, ib):
+            ni = min(ib, n_items - i0)
+            pu, pi = _block_indices(cache, nb, ni, dev)
+            s = score(pu + u0, pi + i0).reshape(nb, ni)
+            bi, bv = ops.topk_rows(s, min(k, ni))
+            bi = bi + i0
+            if best_i is None:
+                best_i, best_v = bi, bv
+                continue
+            # merge with the best of the earlier (lower-id) item blocks: candidates stay ordered by (score desc, id asc)
+            # inside each part and the earlier part comes first, so cbrs_topk_rows' rule "ties go to the lower column"
+            # is still "ties go to the lower item id"
+            cand_v = torch.cat([best_v, bv], dim=1).contiguous()
+            cand_i = torch.cat([best_i, bi], dim=1)
+            sel, best_v = ops.topk_rows(cand_v, min(k, cand_v.shape[1]))
+            best_i = torch.gather(cand_i, 1, sel.long())
+        ids[u0:u0 + nb, :best_i.shape[1]], vals[u0:u0 + nb, :best_v.shape[1]] = best_i, best_v
     return ids, vals

@@ -68,7 +68,8 @@ def partition_parity(group=None, log=None, families=("BasicGCN", "BasicGraphSage
     adj = small_graph(n_users, n_items, 150000, seed=21, n_props=n_props, n_links=4000, dup_links=300)
     u = np.arange(512) % n_users
     i = np.arange(512) % n_items + n_users
-    modes = [("peer", "off"), ("peer", "kernel"), ("peer", "ce"), ("nccl", "off")] if gpu else [("nccl", "off")]
+    modes = ([("peer", "replicate"), ("peer", "off"), ("peer", "kernel"), ("peer", "ce"), ("nccl", "off")] if gpu
+             else [("nccl", "off")])
     for blocking in (None, (257, 40)):          # row-major schedule, then the column-blocked one on the same graph
         G.FORCED_BLOCKING = blocking
         try:
@@ -87,12 +88,12 @@ def partition_parity(group=None, log=None, families=("BasicGCN", "BasicGraphSage
                     model((u, i))
                     full = model.gnn(None).clone()
                     for exchange, pipeline in modes:
-                        if pipeline != "off" and (name != "BasicGCN" or blocking is not None):
-                            continue  # the software pipelines exist for GCN stacks
+                        if pipeline != "off" and (name != "BasicGCN" or (blocking is not None and pipeline != "replicate")):
+                            continue  # the pipelines exist for GCN stacks
                         tag = "%s %s %s/%s%s" % (name, "even" if even else "ragged", exchange, pipeline,
                                                  " blocked" if blocking else "")
                         part = RowPartition(sizes, group=group, final_types=[0, 1, 2], exchange=exchange, pipeline=pipeline,
-                                            row_blocks=3 if pipeline != "off" else 1).attach(seq)
+                                            row_blocks=3 if pipeline in ("kernel", "ce") else 1).attach(seq)
                         for rep in range(3):  # repeated calls reuse the symmetric buffers
                             got = model.gnn(None)
                             if gpu:
@@ -114,24 +115,34 @@ def partition_parity(group=None, log=None, families=("BasicGCN", "BasicGraphSage
                         seq.partition = None
                     say("partition parity: %s %s%s done" % (name, "even" if even else "ragged", " blocked" if blocking else ""))
             if gpu:
-                # 128-wide GCN stack: the sparse kernel of layer l also produces layer l+1's transform and stores it into
-                # every rank's copy (cbrs_spmm_gcn_fused); must still equal the single-GPU, unfused result bit for bit
-                set_seed(11)
-                model = basic.BasicGCN(adj, n_hiddens=[128, 128, 128], embedding_dim=128, dense_units=[48, 48],
-                                       clf_units=[64, 64], final_node="concatenation")
-                seq = model.gnn.gnn_layers
-                model((u, i))
-                full = model.gnn(None).clone()
-                for pipeline in ("fused", "off"):
-                    part = RowPartition([n_users, n_items, n_props], group=group, final_types=[0, 1, 2], exchange="peer",
-                                        pipeline=pipeline).attach(seq)
-                    for rep in range(2):
-                        got = model.gnn(None)
-                        torch.cuda.synchronize()
-                        check(torch.equal(got, full), "128-wide GCN pipeline=%s%s rep %d" % (pipeline, " blocked" if blocking else "", rep))
-                    part.close()
-                    seq.partition = None
-                say("partition parity: 128-wide GCN fused transform%s done" % (" blocked" if blocking else ""))
+                # 128-wide GCN stack, once with each transform kernel.  "ffma": the sparse kernel of layer l may also
+                # produce layer l+1's transform and store it into every rank's copy (cbrs_spmm_gcn_fused); "tf32x3": the
+                # tensor-core transform (forced here: the graph is below its automatic threshold), whole-table on every
+                # rank ("replicate") or own rows + peer stores ("off").  All must equal the single-GPU result bit for bit.
+                from . import ops
+                saved = ops.GCN_TRANSFORM
+                try:
+                    for transform, pipelines in (("ffma", ("fused", "replicate", "off")), ("tf32x3", ("replicate", "off"))):
+                        ops.GCN_TRANSFORM = transform
+                        set_seed(11)
+                        model = basic.BasicGCN(adj, n_hiddens=[128, 128, 128], embedding_dim=128, dense_units=[48, 48],
+                                               clf_units=[64, 64], final_node="concatenation")
+                        seq = model.gnn.gnn_layers
+                        model((u, i))
+                        full = model.gnn(None).clone()
+                        for pipeline in pipelines:
+                            part = RowPartition([n_users, n_items, n_props], group=group, final_types=[0, 1, 2],
+                                                exchange="peer", pipeline=pipeline).attach(seq)
+                            for rep in range(2):
+                                got = model.gnn(None)
+                                torch.cuda.synchronize()
+                                check(torch.equal(got, full), "128-wide GCN %s pipeline=%s%s rep %d" % (
+                                    transform, pipeline, " blocked" if blocking else "", rep))
+                            part.close()
+                            seq.partition = None
+                finally:
+                    ops.GCN_TRANSFORM = saved
+                say("partition parity: 128-wide GCN (fused / replicated / tensor-core transform)%s done" % (" blocked" if blocking else ""))
         finally:
             G.FORCED_BLOCKING = None
     if gpu:

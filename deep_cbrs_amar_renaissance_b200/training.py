@@ -193,8 +193,7 @@ def _gcn_train(tape, layer, x_node, graph, out):
     relational = isinstance(layer, RGCNConv)
     kernels = layer.kernels if relational else [layer.kernel]
     z = torch.empty(len(kernels) * n, layer.channels, dtype=torch.float32, device=x.device)
-    for r, w in enumerate(kernels):
-        ops.dense(x, w, out=z[r * n:(r + 1) * n])
+    ops.dense_grouped(x, kernels, z, n)
     y = ops.spmm(csr, z, out, bias=layer.bias, relu=layer.activation == "relu")
     node = Node(y)
 

@@ -188,6 +188,16 @@ int cbrs_dense_tc(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1,
                   const int64_t *idx2, int32_t f2, const void *w_image, const float *b, int64_t m, int32_t n,
                   int act, float *out, int64_t ldo, void *stream);
 
+/* Grouped transform of the relational layer (row R: "R-GCN per-relation transform plus scatter as a grouped kernel"):
+ * ONE launch computes X[m, f] . [W_0 | ... | W_{R-1}] (w_cat: contiguous [f, n_groups*h], Keras layout) and stores
+ * column block r of row m at row r*group_rows + m of `out` ([n_groups*group_rows, h], leading dimension ldo), i.e.
+ * straight into the stacked operand whose column ids r*N + j the relational CSR (cbrs_graph_build_csr_rel) gathers
+ * from - the sparse kernel that follows is the grouped scatter.  out_dtype / peers as cbrs_dense_ex.  The reference has
+ * no relational layer (it drops the predicate column, src/data/loaders.py:63-68); n_groups = 1 is cbrs_dense.      */
+int cbrs_dense_grouped(const float *x, int64_t ldx, const float *w_cat, int64_t m, int32_t f, int32_t h,
+                       int32_t n_groups, void *out, int64_t ldo, int64_t group_rows, int out_dtype,
+                       void *const *out_peers_host, int n_peers, void *stream);
+
 /* fp32-ACCURATE Dense layer on the tensor cores: the GCN transform Z = X W (src/models/gnn.py:285-295: GCNConv =
  * transform, then propagate) at scaled-graph size.  out = act(X @ W + b), everything fp32; the product is split
  * into three kind::tf32 tcgen05 MMAs (Xl Wh + Xh Wl + Xh Wh with xh = tf32(x), xl = x - xh) accumulated in fp32 in

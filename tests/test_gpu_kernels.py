@@ -504,3 +504,28 @@ def test_spmm_gcn_fused_equals_spmm_then_dense_bit_for_bit(dev, chunk_edges, rel
     assert torch.equal(z1, z2)
     with pytest.raises(RuntimeError):
         ops.spmm_gcn_fused(csr, x[:, :64].contiguous(), y2, b, relu, w, z2)
+
+
+@pytest.mark.parametrize("m,f,h,r", [(300, 16, 16, 2), (1000, 64, 64, 3), (77, 10, 6, 2), (513, 128, 128, 2), (200, 32, 8, 5)])
+def test_dense_grouped_writes_every_relation_block_in_one_launch(dev, m, f, h, r):
+    """cbrs_dense_grouped (row R): X . [W_0 | ... | W_{R-1}] stored straight into the stacked [R*N, H] operand; same
+    bits as R separate cbrs_dense calls, rows outside the written blocks untouched, bf16 output = rounded fp32 output"""
+    from deep_cbrs_amar_renaissance_b200 import ops
+    rng = np.random.RandomState(m + f)
+    x = _t(rng.standard_normal((m, f)).astype(np.float32), dev)
+    ws = [_t(glorot(rng, (f, h)), dev) for _ in range(r)]
+    n_stack = m + 37                                   # the stack is taller than this row block (a rank's slice)
+    z = torch.full((r * n_stack, h), -5.0, device=dev)
+    ops.dense_grouped(x, ws, z[11:], n_stack)          # block written at row offset 11
+    for k, w in enumerate(ws):
+        want = ops.dense(x, w)
+        assert torch.equal(z[k * n_stack + 11:k * n_stack + 11 + m], want), k
+    mask = torch.ones(r * n_stack, dtype=torch.bool, device=dev)
+    for k in range(r):
+        mask[k * n_stack + 11:k * n_stack + 11 + m] = False
+    assert (z[mask] == -5.0).all()
+    assert_close(z[11:11 + m].cpu().numpy(), x.cpu().numpy() @ ws[0].cpu().numpy(), what="relation 0 vs numpy")
+    zb = torch.zeros(r * n_stack, h, device=dev, dtype=torch.bfloat16)
+    ops.dense_grouped(x, ws, zb, n_stack)
+    for k, w in enumerate(ws):
+        assert torch.equal(zb[k * n_stack:k * n_stack + m], ops.dense(x, w).to(torch.bfloat16)), k

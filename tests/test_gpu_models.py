@@ -251,6 +251,63 @@ def test_catalog_top_k_matches_oracle():
     assert torch.equal(ids2, ids[sub])
 
 
+@pytest.mark.parametrize("feature_based", [True, False])
+def test_hybrid_catalog_top_k_matches_oracle(feature_based, monkeypatch):
+    """Full-catalog top-k of the hybrid scorer (src/models/hybrid.py:72-89 applied to every (user, item)): the
+    entity-based form reaches the fused kernel through its hoisted dense3a / dense3b, the feature-based form (what every
+    grid of econfigs/hybrid-gnn.yaml uses) the blocked pair pipeline; both against the oracle's scores, and the fused
+    result against the generic one."""
+    from deep_cbrs_amar_renaissance_b200 import scoring
+    n_users, n_items, dim, k = 90, 260, 768, 10
+    adj = random_bipartite(n_users, n_items, 4000, seed=18)
+    bert = (np.random.RandomState(5).standard_normal((n_users + n_items, dim)) * 0.5).astype(np.float32)
+    grid = (16, [16, 16], [[48, 48], [256, 64], [64, 64]], [64, 64])
+    model = _build("HybridBertGCN", adj, grid, module="hybrid", feature_based=feature_based, fusion_method="concatenate",
+                   residual=False)
+    model.set_content_table(bert)
+    model((np.array([0]), np.array([n_users])))
+    _randomise(model, 9)
+    model.cache_propagation = True
+    w = export_weights(model)
+    emb = ol.propagate("gcn", w["embeddings"], og.gcn_filter(adj), w["layers"])
+    uu = np.repeat(np.arange(n_users), n_items)
+    ii = np.tile(np.arange(n_items), n_users) + n_users
+    oracle_scores = ol.hybrid_cbrs(emb, uu, ii, bert[uu], bert[ii], w, feature_based=feature_based).reshape(n_users, n_items)
+    monkeypatch.setattr(scoring._blocks, "__defaults__", (None, 100))   # 100 pairs per block < n_items: item blocks too
+    ids_g, vals_g = model.recommend_top_k(n_users, n_items, k, fused=False)
+    dense_scores = scoring.catalog_scores(model, model.propagate(), n_users, n_items).cpu().numpy()
+    assert_close(dense_scores, oracle_scores, rtol=2e-5, what="hybrid catalog scores")
+    want_ids, want_vals = ol.top_k_catalog(dense_scores, k)   # bit-exact with a stable sort of its own scores
+    assert np.array_equal(ids_g.cpu().numpy(), want_ids) and np.array_equal(vals_g.cpu().numpy(), want_vals)
+    # hybrid scores carry 2e-5 (768-term fp32 dot products): ids are compared where the oracle's gaps exceed that
+    assert assert_topk_equivalent(ids_g.cpu().numpy(), vals_g.cpu().numpy(), oracle_scores, k, tol=2e-5) > 0.5
+    ids_f, vals_f = model.recommend_top_k(n_users, n_items, k)   # fused where the scorer allows it
+    assert assert_topk_equivalent(ids_f.cpu().numpy(), vals_f.cpu().numpy(), oracle_scores, k, tol=2e-5) > 0.5
+    if not feature_based:
+        assert scoring._hoisted_sources(model, model.propagate(), torch.arange(n_users, device="cuda"),
+                                        torch.arange(n_users, n_users + n_items, device="cuda")) is not None
+
+
+def test_item_blocked_catalog_top_k_keeps_the_tie_rule(monkeypatch):
+    """catalogs wider than the pair budget are cut along the item axis and merged: exact ties must still go to the
+    lower item id across block borders, and the result must equal the unblocked one"""
+    from deep_cbrs_amar_renaissance_b200 import scoring
+    n_users, n_items = 30, 50
+    adj = random_bipartite(n_users, n_items, 300, seed=2)
+    model = _build("BasicGCN", adj, GRIDS[0])
+    model((np.array([0]), np.array([n_users])))
+    saved = model.get_weights()
+    model.cache_propagation = True
+    full_ids, full_vals = model.recommend_top_k(n_users, n_items, 7, fused=False)
+    monkeypatch.setattr(scoring._blocks, "__defaults__", (None, 16))   # 16 pairs per block: 4 item blocks per user
+    ids, vals = model.recommend_top_k(n_users, n_items, 7, fused=False)
+    assert torch.equal(ids, full_ids) and torch.equal(vals, full_vals)
+    model.set_weights([np.zeros_like(w) for w in saved])  # every score is sigmoid(0) = 0.5
+    model.invalidate()
+    ids, vals = model.recommend_top_k(n_users, n_items, 7, fused=False)
+    assert (ids.cpu().numpy() == np.arange(7)[None, :]).all() and (vals == 0.5).all()
+
+
 def test_exact_ties_go_to_the_lower_item_index():
     n_users, n_items = 30, 50
     adj = random_bipartite(n_users, n_items, 300, seed=2)

@@ -128,3 +128,41 @@ def test_two_step_two_way_constructor_errors(shape_only_graphs):
     # experiment.py:139-146 dispatches on these parents
     assert issubclass(basic.BasicTSGAT, basic.BasicTSGNN) and issubclass(basic.BasicTWDGCF, basic.BasicTWGNN)
     assert issubclass(basic.BasicTSGNN, basic.BasicGNN)
+
+
+def test_typed_edges_from_the_loader_follow_the_entry_order_of_the_reference_graph():
+    """relations= (row R, extension): the COO entries are exactly the reference's untyped 'unary-uip' graph (golden
+    fixture written by the reference's own loader), each with a relation id; both directions of an edge agree."""
+    import os
+    from deep_cbrs_amar_renaissance_b200.data import loaders
+    from deep_cbrs_amar_renaissance_b200.data.preprocess import edge_relations
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "uip_small")
+    files = [os.path.join(root, f) for f in ("train2id.tsv", "test2id.tsv", "props2id.tsv")]
+    gold = np.load(os.path.join(root, "golden.npz"))
+    plain, _ = loaders.load_user_item_graph(*files, type_adjacency="unary-uip")
+    assert np.array_equal(plain.adj_matrix.row, gold["adj_row"]) and np.array_equal(plain.adj_matrix.col, gold["adj_col"])
+    raw = np.loadtxt(files[2], dtype=np.int64, delimiter="\t")
+    n_users, n_items = len(plain.users), len(plain.items)
+    for mode in ("node-range", "predicate"):
+        typed, _ = loaders.load_user_item_graph(*files, type_adjacency="unary-uip", relations=mode)
+        adj = typed.adj_matrix
+        assert np.array_equal(adj.coo.row, gold["adj_row"]) and np.array_equal(adj.coo.col, gold["adj_col"])
+        assert np.array_equal(adj.coo.data, gold["adj_data"]) and adj.shape == tuple(gold["adj_shape"])
+        is_prop_edge = (adj.coo.row >= n_users + n_items) | (adj.coo.col >= n_users + n_items)
+        assert np.array_equal(adj.rel > 0, is_prop_edge)
+        half = adj.coo.nnz // 2
+        assert np.array_equal(adj.rel[:half], adj.rel[half:])
+        if mode == "node-range":
+            assert adj.n_rel == 2 and set(np.unique(adj.rel)) == {0, 1}
+        else:
+            preds = np.unique(raw[:, 2])
+            assert adj.n_rel == 1 + len(preds)
+            n_liked = int((typed.ratings[:, 2] == 1).sum())
+            assert np.array_equal(adj.rel[n_liked:half], 1 + np.searchsorted(preds, raw[:, 2]))
+        blocks = adj.relation_blocks()
+        assert sum(b.nnz for b in blocks) == adj.coo.nnz
+        assert abs(sum(b.tocsr() for b in blocks) - adj.coo.tocsr()).nnz == 0
+    with pytest.raises(ValueError):
+        loaders.load_user_item_graph(*files[:2], type_adjacency="unary", relations="node-range")
+    with pytest.raises(ValueError):
+        edge_relations(3, raw[:, 2], "by-colour", True)

@@ -95,3 +95,39 @@ def test_driver_runs_linear_and_grid_experiments(tmp_path):
             same = np.diff(pred[:, 0]) == 0
             assert (np.diff(pred[:, 2])[same] <= 0).all()                # scores descending within a user
             assert (art / "predictions" / ("top_%d" % k) / "results.tsv").exists()
+
+
+def test_relational_grid_runs_from_the_packaged_econfig(tmp_path):
+    """row R end to end: deep_cbrs_amar_renaissance_b200/econfigs/basic-rgcn-uip-2relconf.yaml (basic.BasicRGCN +
+    `relations:` in the dataset section) through the driver - loader keeps the edge types, the model trains, evaluates
+    and writes its predictions; 'predicate' relations give one kernel per distinct predicate + the rating relation."""
+    import deep_cbrs_amar_renaissance_b200 as pkg
+    from deep_cbrs_amar_renaissance_b200 import experiment as ex
+    from deep_cbrs_amar_renaissance_b200.data import loaders
+    cfg, _, paths = write_inputs(tmp_path / "data")
+    grids = ex.load_yaml(os.path.join(os.path.dirname(pkg.__file__), "econfigs", "basic-rgcn-uip-2relconf.yaml"))
+    g2 = grids["grid"]["grid2"]
+    assert g2["model"]["name"] == ["basic.BasicRGCN"] and g2["dataset"]["relations"] == ["node-range", "predicate"]
+    g2["dataset"]["props_triples_filepath"] = [paths["props_triples_filepath"]]
+    g2["model"]["l2_regularizer"] = [1e-4]
+    exps = os.path.join(str(tmp_path), "rgcn.yaml")
+    with open(exps, "w") as fp:
+        yaml.safe_dump({"grid": {"grid2": g2}}, fp)
+    results = ex.main(["-c", cfg, "-e", exps, "--out", str(tmp_path / "runs"), "--exp_name", "rgcn"])
+    assert len(results) == 2 and all(m is not None for m in results.values())
+    for m in results.values():
+        hist = m["history"]["loss"]
+        assert len(hist) == 3 and hist[-1] < hist[0] and 0.0 <= m["test_accuracy"] <= 1.0
+    # the loader's typed graph: both directions of an edge carry the same relation; predicates are compacted
+    train, _ = loaders.load_user_item_graph(paths["train_ratings_filepath"], paths["test_ratings_filepath"],
+                                            paths["props_triples_filepath"], type_adjacency="unary-uip", relations="predicate")
+    adj = train.adj_matrix
+    raw = np.loadtxt(paths["props_triples_filepath"], dtype=np.int64, delimiter="\t")
+    assert adj.n_rel == 1 + len(np.unique(raw[:, 2])) and len(adj.rel) == adj.coo.nnz
+    half = adj.coo.nnz // 2
+    assert np.array_equal(adj.rel[:half], adj.rel[half:]) and (adj.rel[:half] == 0).sum() == (train.ratings[:, 2] == 1).sum()
+    plain, _ = loaders.load_user_item_graph(paths["train_ratings_filepath"], paths["test_ratings_filepath"],
+                                            paths["props_triples_filepath"], type_adjacency="unary-uip")
+    assert np.array_equal(plain.adj_matrix.row, adj.coo.row) and np.array_equal(plain.adj_matrix.col, adj.coo.col)
+    params = sorted(m["trainable_params"] for m in results.values())
+    assert params[0] < params[1]    # more relations, more kernels
