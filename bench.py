@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-scale", default="c5-hundredth", choices=sorted(SCALES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the bf16-operand variant of the step")
+    ap.add_argument("--no-small-configs", action="store_true", help="skip the MovieLens-1M-shaped configs 1-4 block")
     ap.add_argument("--unscattered", action="store_true",
                     help="item id = popularity rank (no scattering of hot items over the id space): the adversarial case for "
                          "the row partition; cuts are balanced by edge count either way")
@@ -174,6 +175,85 @@ class ClockSampler:
                     "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
         except Exception as e:  # pragma: no cover
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["parse error: %s" % e]}
+
+
+# ----------------------------------------------------------------------------- configs 1-4 (MovieLens-1M shape)
+def small_configs(dev):
+    """BASELINE configs 1-4 on one GPU: the per-batch model call (batch 2048, econfigs grid2 shapes) eager and as a
+    CUDA-graph replay, and full-catalog top-10 for every user with HOST ids in and HOST (ids, scores) out.  These
+    graphs are L2-resident (~67 MB of algorithmic traffic per layer) and launch-latency-bound: the numbers are times
+    against the launch count, never an HBM fraction.  Published context (other
+    hardware, whole training loop): BasicRS-GCN 16/2 trains in 211 s / 25 epochs on an RTX 3060 = ~11.4 ms per step."""
+    import torch
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from deep_cbrs_amar_renaissance_b200.data.preprocess import RelationalAdjacency
+    from deep_cbrs_amar_renaissance_b200.graphed import GraphedForward
+    from deep_cbrs_amar_renaissance_b200.keras_like import set_seed
+    from deep_cbrs_amar_renaissance_b200.models import basic, hybrid
+    from deep_cbrs_amar_renaissance_b200.selfcheck import small_graph
+
+    def timeit(fn, n=30, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    n_users, n_items, batch, k = 6040, 3706, 2048, 10
+    n_props, n_links = 17554, 70341                      # doc.pdf Table 3
+    adj = small_graph(n_users, n_items, 572000, seed=42)
+    uip = small_graph(n_users, n_items, 572000, seed=42, n_props=n_props, n_links=n_links, dup_links=400)
+    is_prop = (uip.row >= n_users + n_items) | (uip.col >= n_users + n_items)
+    uip_rel = RelationalAdjacency(uip, is_prop.astype(np.int32), 2)
+    rng = np.random.RandomState(0)
+    u = rng.randint(0, n_users, size=batch)
+    i = rng.randint(0, n_items, size=batch) + n_users
+    bert = (rng.standard_normal((n_users + n_items, 768)) * 0.5).astype(np.float32)
+    all_users = torch.arange(n_users, dtype=torch.int64).pin_memory()
+    hyb = dict(dense_units=[[48, 48], [256, 64], [64, 64]], feature_based=True)
+    cases = [("config 1: BasicGCN", basic.BasicGCN, adj, {}, "fp32"),
+             ("config 2: BasicGraphSage", basic.BasicGraphSage, adj, {}, "fp32"),
+             ("config 2: BasicGAT", basic.BasicGAT, adj, {}, "fp32"),
+             ("config 3: BasicGCN on the user-item-properties graph (untyped, as the reference)", basic.BasicGCN, uip, {}, "fp32"),
+             ("config 3: BasicRGCN, 2 relation types (node-range)", basic.BasicRGCN, uip_rel, {}, "fp32"),
+             ("config 4: HybridBertGCN feature-based, fp32 scorer", hybrid.HybridBertGCN, adj, hyb, "fp32"),
+             ("config 4: HybridBertGCN feature-based, bf16 tensor-core scorer", hybrid.HybridBertGCN, adj, hyb, "bf16")]
+    out = []
+    for name, cls, a, extra, precision in cases:
+        set_seed(42)
+        kw = dict(n_hiddens=[16, 16], n_layers=2, embedding_dim=16, dense_units=[48, 48], clf_units=[64, 64])
+        kw.update(extra)
+        model = cls(a, **kw)
+        if cls is hybrid.HybridBertGCN:
+            model.set_content_table(bert)
+            model.set_scorer_precision(precision)
+        model((u, i))
+        before = ops.LAUNCHES
+        model((u, i))
+        kernels = ops.LAUNCHES - before
+        eager = timeit(lambda: model((u, i)))
+        g = GraphedForward(model, batch)
+        graphed = timeit(lambda: g((u, i)))
+        gph = model.gnn.gnn_layers.adj_matrix
+        nnz = (gph.raw if ("Sage" in name or "GAT" in name) else gph.norm).nnz
+
+        def catalog():
+            users = all_users.to(dev, non_blocking=True)              # H2D: the ids to rank for
+            ids, vals = model.recommend_top_k(n_users, n_items, k, users=users, precision=precision)
+            return ids.cpu(), vals.cpu()                              # D2H: the lists
+        cat = timeit(catalog, n=3, warm=1)                            # propagation recomputed inside: end to end
+        out.append({"case": name, "nnz": nnz, "layers": 2, "batch": batch, "kernels_per_call": kernels,
+                    "eager_ms": eager, "graph_replay_ms": graphed, "us_per_kernel_in_graph": graphed * 1e3 / max(kernels, 1),
+                    "edges_per_s_graph_replay": 2 * nnz / (graphed * 1e-3),
+                    "catalog_top10_e2e_ms": cat, "catalog_pairs_per_s_e2e": n_users * n_items / (cat * 1e-3),
+                    "catalog_h2d_bytes": n_users * 8, "catalog_d2h_bytes": n_users * k * 8, "scorer_precision": precision})
+        del model, g
+    return out
 
 
 # ----------------------------------------------------------------------------- B200 arm
@@ -408,6 +488,18 @@ def run_b200(args):
             line["hybrid_towers"] = towers.run(1 << 20)
         except Exception as e:  # noqa: BLE001  (never let the side measurement take the headline line down)
             line["hybrid_towers"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    if world == 1 and not args.no_small_configs:
+        try:
+            sc = small_configs(dev)
+            line["small_configs"] = sc
+            hyb = [c for c in sc if c["case"].startswith("config 4")]
+            line["pairs"]["hybrid"] = [{"value": c["catalog_pairs_per_s_e2e"], "unit": "pairs/s", "ms": c["catalog_top10_e2e_ms"],
+                                        "what": c["case"] + ": propagation + 6040 x 3706 full-catalog top-10, host ids in, host "
+                                        "lists out (MovieLens-1M shape, BASELINE config 4)",
+                                        "tolerance": "fp32: 2e-5 vs the oracle; bf16: 2e-3 vs an oracle rounding the same operands "
+                                                     "(tests/test_zz_gpu_dense_tc.py, tests/test_gpu_models.py)"} for c in hyb]
+        except Exception as e:  # noqa: BLE001
+            line["small_configs"] = {"error": "%s: %s" % (type(e).__name__, e)}
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         r = cpu_reference_run(args.cpu_scale, 2, 1, threads)

@@ -487,6 +487,25 @@ def score_catalog_topk(P, Q, w2, b2, w3, b3, k, precision="fp32"):
 
 
 # ------------------------------------------------------------------ misc
+def score_hybrid_topk_bf16(P1, Q1, P2, Q2, w3a2, b3a2, w3b2, b3b2, wc1, bc1, wc2, bc2, wc3, bc3, k):
+    """Feature-based hybrid scorer over the whole catalog + per-user top-k, chained tcgen05 kernel
+    (cbrs_score_hybrid_topk_bf16).  Returns (item index int32 [U, k], score float32 [U, k])."""
+    lib = L.load()
+    ts = [t.contiguous() for t in (P1, Q1, P2, Q2, w3a2, b3a2, w3b2, b3b2, wc1, bc1, wc2, bc2, wc3, bc3)]
+    n_users, c = ts[0].shape
+    n_items = ts[1].shape[0]
+    dev = ts[0].device
+    ids = torch.empty(n_users, k, dtype=torch.int32, device=dev)
+    vals = torch.empty(n_users, k, dtype=torch.float32, device=dev)
+    ws = _ws(lib.cbrs_score_hybrid_topk_bf16_workspace_bytes(), dev)
+    L.check(lib.cbrs_score_hybrid_topk_bf16(_ptr(ts[0], torch.float32), _ptr(ts[1], torch.float32), _ptr(ts[2], torch.float32),
+                                            _ptr(ts[3], torch.float32), n_users, n_items, c,
+                                            *[_ptr(t, torch.float32) for t in ts[4:]], k, _ptr(ids), _ptr(vals), _ptr(ws),
+                                            ws.numel(), _stream()), "cbrs_score_hybrid_topk_bf16")
+    _count(2)
+    return ids, vals
+
+
 def synth_bipartite(n_users, n_items, n_edges, seed, device, scatter_items=True):
     lib = L.load()
     row = torch.empty(2 * n_edges, dtype=torch.int32, device=device)

@@ -123,12 +123,46 @@ def _fused_basic(model, emb, users, items, k, precision="fp32"):
     return ops.score_catalog_topk(P, Q, l2.kernel, l2.bias, l3.kernel.reshape(-1), l3.bias, k, precision)
 
 
+def _fused_hybrid_feature(model, emb, users, items, k):
+    """Feature-based HybridCBRS with the shapes of every hybrid grid of the reference (dense3a / dense3b = two 64-wide
+    layers, classifier 64 -> 64 -> 1, relu, plain concatenation) -> the chained tensor-core kernel
+    (cbrs_score_hybrid_topk_bf16).  None when the scorer has another shape."""
+    rs = model.rs
+    if hasattr(rs, "unet") or not rs.feature_based or rs.residual is not None or model.content_table is None or k > 128:
+        return None
+    if any(f.method != 'concatenate' for f in (rs.fuse1a, rs.fuse1b, rs.fuse2)):
+        return None
+    d3a, d3b, clf = rs.dense3a.layers, rs.dense3b.layers, rs.clf.layers
+    if len(d3a) != 2 or len(d3b) != 2 or len(clf) != 3 or clf[2].units != 1:
+        return None
+    if any(ly.units != 64 or ly.activation != "relu" for ly in (*d3a, *d3b, clf[0], clf[1])):
+        return None
+    table = model.content_table
+    ug = rs.dense1a.call_sources([(emb, users)])
+    ig = rs.dense1b.call_sources([(emb, items)])
+    ub = rs.dense2a.call_sources([(table, users)])
+    ib = rs.dense2b.call_sources([(table, items)])
+    g, c = ug.shape[1], ub.shape[1]
+    d3a[0].build_for(g + ig.shape[1]); d3a[1].build_for(64)
+    d3b[0].build_for(c + ib.shape[1]); d3b[1].build_for(64)
+    clf[0].build_for(128); clf[1].build_for(64); clf[2].build_for(64)
+    P1 = ops.dense(ug, d3a[0].kernel[:g], d3a[0].bias, None)     # bias folded into the user half
+    Q1 = ops.dense(ig, d3a[0].kernel[g:], None, None)
+    P2 = ops.dense(ub, d3b[0].kernel[:c], d3b[0].bias, None)
+    Q2 = ops.dense(ib, d3b[0].kernel[c:], None, None)
+    return ops.score_hybrid_topk_bf16(P1, Q1, P2, Q2, d3a[1].kernel, d3a[1].bias, d3b[1].kernel, d3b[1].bias,
+                                      clf[0].kernel, clf[0].bias, clf[1].kernel, clf[1].bias, clf[2].kernel.reshape(-1),
+                                      clf[2].bias, k)
+
+
 def catalog_top_k(model, emb, n_users, n_items, k=10, users=None, user_block=None, fused=True, precision="fp32"):
     dev = emb.device
     users = torch.arange(n_users, device=dev, dtype=torch.int64) if users is None else users.to(dev, torch.int64)
     items = torch.arange(n_users, n_users + n_items, device=dev, dtype=torch.int64)
     if fused:
         out = _fused_basic(model, emb, users, items, k, precision)
+        if out is None and precision == "bf16":
+            out = _fused_hybrid_feature(model, emb, users, items, k)
         if out is not None:
             return out
     score = _pair_scorer(model, emb, users, items)

@@ -188,6 +188,22 @@ int cbrs_dense_tc(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1,
                   const int64_t *idx2, int32_t f2, const void *w_image, const float *b, int64_t m, int32_t n,
                   int act, float *out, int64_t ldo, void *stream);
 
+/* Full-catalog scoring of the FEATURE-BASED hybrid scorer with a fused per-user top-k, chained on the tensor cores
+ * (src/models/hybrid.py:72-89 for every (user, item) pair; the form all of econfigs/hybrid-gnn*.yaml use).  The caller
+ * hoists what depends on one entity: the four towers and the first layer of dense3a / dense3b, split into a user half
+ * (bias folded in) and an item half: P1 [U, c], Q1 [I, c] (collaborative branch), P2, Q2 (content branch), rows
+ * contiguous.  Per pair the kernel computes, bf16 operands / fp32 accumulation, activations never leaving the SM:
+ *   x1 = relu(relu(P1[u]+Q1[i]) w3a2 + b3a2),  x2 = relu(relu(P2[u]+Q2[i]) w3b2 + b3b2),
+ *   g = relu([x1 || x2] wc1 + bc1),  score = sigmoid(relu(g wc2 + bc2) . wc3 + bc3)
+ * w3a2, w3b2, wc2: [c, c]; wc1: [2c, c] (Keras [in, out], contiguous); c = 64.  ids_out [U, k] int32 item indices,
+ * scores_out [U, k], descending, ties to the lower index; k <= 128.                                               */
+size_t cbrs_score_hybrid_topk_bf16_workspace_bytes(void);
+int cbrs_score_hybrid_topk_bf16(const float *P1, const float *Q1, const float *P2, const float *Q2, int64_t n_users,
+                                int32_t n_items, int32_t c, const float *w3a2, const float *b3a2, const float *w3b2,
+                                const float *b3b2, const float *wc1, const float *bc1, const float *wc2,
+                                const float *bc2, const float *wc3, const float *bc3, int32_t k, int32_t *ids_out,
+                                float *scores_out, void *workspace, size_t workspace_bytes, void *stream);
+
 /* Grouped transform of the relational layer (row R: "R-GCN per-relation transform plus scatter as a grouped kernel"):
  * ONE launch computes X[m, f] . [W_0 | ... | W_{R-1}] (w_cat: contiguous [f, n_groups*h], Keras layout) and stores
  * column block r of row m at row r*group_rows + m of `out` ([n_groups*group_rows, h], leading dimension ldo), i.e.
