@@ -53,6 +53,8 @@ def parse():
                     help="item id = popularity rank (no scattering of hot items over the id space): the adversarial case for "
                          "the row partition; cuts are balanced by edge count either way")
     ap.add_argument("--row-count-cuts", action="store_true", help="N > 1: cut node types at equal ROW counts (round-1 behaviour)")
+    ap.add_argument("--edge-count-cuts", action="store_true", help="N > 1: cut at equal EDGE counts (default: equal edge COST, "
+                                                                   "edges of rows that stream from HBM weigh 2.4)")
     ap.add_argument("--no-parity-check", action="store_true", help="N > 1: skip the bit-identity self-check that precedes timing")
     ap.add_argument("--catalog-users", type=int, default=4736,
                     help="users per rank scored against the whole catalog (4736 = 148 SMs x 2 CTAs x 16 users: one full wave of "
@@ -316,7 +318,8 @@ def run_b200(args):
     if world > 1:
         # CBRS_EXCHANGE=nccl|peer; each node type is cut into N blocks of equal EDGE count
         part = RowPartition([n_users, n_items], final_types=[1],
-                            balance_rowptr=None if args.row_count_cuts else graph.norm.rowptr).attach(seq)
+                            balance_rowptr=None if args.row_count_cuts else graph.norm.rowptr,
+                            balance_min_len=0 if args.edge_count_cuts else graph.norm.blocking[1]).attach(seq)
         os.environ["CBRS_EXCHANGE"] = part.exchange + ("+" + part.pipeline if part.exchange == "peer" else "")
         part.csr_slices("norm", graph)
         part.release_full_views(graph)
@@ -389,7 +392,7 @@ def run_b200(args):
         per = [float(t.item()) for t in every]
         rank_sparse = {"ms_per_step": per, "min": min(per), "max": max(per), "max_over_min": max(per) / max(min(per), 1e-9),
                        "local_edges": part.local_edges("norm"),
-                       "cuts": "equal row counts" if args.row_count_cuts else "equal edge counts per node type"}
+                       "cuts": "equal row counts" if args.row_count_cuts else ("equal edge counts per node type" if args.edge_count_cuts else "equal edge cost per node type (edges of rows that stream from HBM weigh 2.4)")}
 
     # ---- end to end through the public model call with HOST buffers (e2e) --------------------
     def e2e_step():

@@ -42,12 +42,37 @@ def block_ranges(n_rows_by_type, world_size):
     return out
 
 
+# Relative cost of one edge of a row that is NOT column-blocked (graph.blocking_policy) on a graph whose operand table
+# exceeds L2: its gathers stream from HBM, a blocked row's come out of the L2 window.  Calibrated on the unscattered
+# config-5 graph over 4 GPUs (profiles/r02_bench_c5_n4_unscattered*.json): with 1.4 the rank holding the hottest items
+# finished its item rows in 26.7 ms against 48-54 ms for the ranks holding the cold tail, i.e. a streamed edge costs
+# about 2.5 blocked ones.  CBRS_COLD_EDGE_COST overrides.
+COLD_EDGE_COST = float(os.environ.get("CBRS_COLD_EDGE_COST", "2.4"))
+
+
+def edge_cost_prefix(rowptr, n_rows_by_type, block_min_len=0, cold_cost=COLD_EDGE_COST):
+    """[N+1] prefix sums of a per-row cost for balanced_ranges: the row's edge count, times `cold_cost` for rows of
+    node types that contain column-blocked rows (>= block_min_len edges) but are themselves below the threshold.
+    block_min_len == 0 (row-major schedule): plain edge counts, i.e. rowptr itself."""
+    if not block_min_len:
+        return rowptr
+    lens = (rowptr[1:] - rowptr[:-1]).to(torch.float64)
+    cost = lens.clone()
+    base = 0
+    for n in n_rows_by_type:
+        seg = lens[base:base + n]
+        if n and bool((seg >= block_min_len).any()):
+            cost[base:base + n] = torch.where(seg >= block_min_len, seg, seg * cold_cost)
+        base += n
+    return torch.cat([torch.zeros(1, dtype=torch.float64, device=rowptr.device), torch.cumsum(cost, 0)])
+
+
 def balanced_ranges(n_rows_by_type, world_size, rowptr):
-    """block_ranges with each node type cut at (about) equal EDGE count instead of equal row count: block r of a type
-    ends at the first row whose prefix edge count reaches r/world of the type's edges.  `rowptr` is the
-    [N+1] row pointer of the CSR view the sparse kernel runs on (host or device tensor); every rank computes the
-    same cuts from it.  Real ids come out of np.unique in id order, so popular items may sit next to each other;
-    equal row counts would then give one rank most of the edges."""
+    """block_ranges with each node type cut at (about) equal EDGE count (or edge COST, when `rowptr` is an
+    edge_cost_prefix) instead of equal row count: block r of a type ends at the first row whose prefix reaches r/world
+    of the type's total.  `rowptr` is the [N+1] row pointer of the CSR view the sparse kernel runs on (host
+    or device tensor); every rank computes the same cuts from it.  Real ids come out of np.unique in id order, so
+    popular items may sit next to each other; equal row counts would then give one rank most of the edges."""
     out = [[] for _ in range(world_size)]
     base = 0
     for n in n_rows_by_type:
@@ -55,9 +80,8 @@ def balanced_ranges(n_rows_by_type, world_size, rowptr):
         cuts = [0] * (world_size + 1)
         cuts[world_size] = n
         if n > 0:
-            lo, hi = int(rp[0].item()), int(rp[-1].item())
-            targets = torch.tensor([lo + (hi - lo) * k // world_size for k in range(1, world_size)], dtype=rp.dtype,
-                                   device=rp.device)
+            lo, hi = rp[0].item(), rp[-1].item()
+            targets = torch.tensor([lo + (hi - lo) * k / world_size for k in range(1, world_size)], device=rp.device).to(rp.dtype)
             mids = torch.searchsorted(rp.contiguous(), targets).tolist() if world_size > 1 else []
             for k, m in enumerate(mids):
                 cuts[k + 1] = min(max(int(m), cuts[k]), n)
@@ -234,7 +258,7 @@ class RowPartition:
     are exchanged, because scoring is sharded by user."""
 
     def __init__(self, n_rows_by_type, group=None, final_types=None, exchange=None, pipeline=None,
-                 row_blocks=None, balance_rowptr=None):
+                 row_blocks=None, balance_rowptr=None, balance_min_len=0):
         self.group = group
         exchange = exchange or os.environ.get("CBRS_EXCHANGE") or ("peer" if torch.cuda.is_available() else "nccl")
         if exchange not in ("peer", "nccl"):
@@ -274,14 +298,18 @@ class RowPartition:
         if self.pipeline not in ("off", "kernel", "ce", "fused", "replicate"):
             raise ValueError("pipeline must be 'replicate', 'off', 'fused', 'kernel' or 'ce'")
         self.row_blocks = int(row_blocks or os.environ.get("CBRS_ROW_BLOCKS", "1" if self.pipeline in ("off", "fused", "replicate") else "2"))
+        self.replicate_l0 = os.environ.get("CBRS_REPLICATE_L0", "1") != "0"
         self._side = None
         self._sym = {}
         self.n_rows_by_type = list(n_rows_by_type)
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        # balance_rowptr: the CSR row pointer to balance EDGES by (balanced_ranges); None = equal row counts
+        # balance_rowptr: the CSR row pointer to balance EDGES by (balanced_ranges); None = equal row counts.
+        # balance_min_len: the graph's column-blocking threshold (CsrSlice.blocking[1]) - rows below it in a node type
+        # that has blocked rows cost COLD_EDGE_COST per edge (edge_cost_prefix)
         self.ranges = (block_ranges(n_rows_by_type, self.world) if balance_rowptr is None
-                       else balanced_ranges(n_rows_by_type, self.world, balance_rowptr))
+                       else balanced_ranges(n_rows_by_type, self.world,
+                                            edge_cost_prefix(balance_rowptr, n_rows_by_type, balance_min_len)))
         self.mine = [rg for rg in self.ranges[self.rank] if rg[1] > rg[0]]
         self.final_types = list(range(1, len(n_rows_by_type))) if final_types is None else list(final_types)
         self._slices = {}
@@ -439,7 +467,11 @@ class RowPartition:
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
                 zdt = torch.bfloat16 if getattr(layer, "feature_dtype", "fp32") == "bf16" else torch.float32
                 zsb, z = self._symbuf(("z", l), len(kernels) * n, layer.channels, zdt)
-                if not z_ahead:
+                if not z_ahead and l == 0 and len(kernels) == 1 and self.replicate_l0 and x_full is emb and zdt == torch.float32:
+                    # layer 0 reads the REPLICATED embedding table: every rank transforms all rows itself (2.5 ms on the
+                    # tensor cores at config 5) instead of its own rows + an exposed, NVLink-bound exchange (6.5 ms)
+                    ops.gcn_transform(emb, kernels[0], n, out=z[0:n])
+                elif not z_ahead:
                     for a, b in self.mine:
                         if len(kernels) > 1:   # relational: every relation's transform of the block in one launch
                             zv = z[a:(len(kernels) - 1) * n + b]

@@ -118,3 +118,15 @@ def test_exchange_rows_gloo_world2(sizes):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, sizes, 3, out), nprocs=world, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def test_edge_cost_prefix_weighs_streamed_rows_only_where_blocked_rows_exist():
+    from deep_cbrs_amar_renaissance_b200.distributed import COLD_EDGE_COST, edge_cost_prefix
+    lens = torch.tensor([3, 4, 5, 100, 2, 50, 1], dtype=torch.int64)      # users: 3 short rows; items: 100, 2, 50, 1
+    rp = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(lens, 0)])
+    assert edge_cost_prefix(rp, [3, 4], 0) is rp                          # row-major schedule: plain edge counts
+    cp = edge_cost_prefix(rp, [3, 4], block_min_len=40)
+    want = [3, 4, 5, 100, 2 * COLD_EDGE_COST, 50, 1 * COLD_EDGE_COST]    # users have no blocked row: unweighted
+    assert torch.allclose(cp[1:] - cp[:-1], torch.tensor(want, dtype=torch.float64))
+    r = balanced_ranges([3, 4], 2, cp)
+    assert r[0][0][0] == 0 and r[1][0][1] == 3 and r[0][1][0] == 3 and r[1][1][1] == 7
