@@ -132,7 +132,7 @@ def workload_config(scale, gpus):
     return {"workload": "%s scaled synthetic bipartite graph, BasicGCN %d layers dim %d fp32, concatenation, "
                         "BasicRS %s/%s, %d scored pairs per step" % (scale, LAYERS, DIM, DENSE_UNITS, CLF_UNITS, PAIR_BATCH),
             "users": n_users, "items": n_items, "undirected_edges": n_edges, "dim": DIM, "layers": LAYERS,
-            "parallelism": ("rows x%d, %s exchange" % (gpus, os.environ.get("CBRS_EXCHANGE", "peer"))) if gpus > 1 else "single",
+            "parallelism": ("rows x%d" % gpus) if gpus > 1 else "single",
             "l2": "inputs larger than L2 (no flush needed)"}
 
 
@@ -320,7 +320,9 @@ def run_b200(args):
         part = RowPartition([n_users, n_items], final_types=[1],
                             balance_rowptr=None if args.row_count_cuts else graph.norm.rowptr,
                             balance_min_len=0 if args.edge_count_cuts else graph.norm.blocking[1]).attach(seq)
-        os.environ["CBRS_EXCHANGE"] = part.exchange + ("+" + part.pipeline if part.exchange == "peer" else "")
+        exchange_label = part.exchange + ("+" + part.pipeline if part.exchange == "peer" else "")
+        if part.heap is not None:
+            exchange_label += ", %s buffers" % part.heap.backend + (", NVSwitch multicast stores" if part.heap.flags.mc_ptr else "")
         part.csr_slices("norm", graph)
         part.release_full_views(graph)
     else:
@@ -474,6 +476,7 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": 2 * PAIR_BATCH * 8,
                 "d2h_bytes_per_step": PAIR_BATCH * 4, "ms_per_step": ms_e2e / args.steps},
         "roofline": roofline, "partition_parity": parity, "rank_sparse_ms": rank_sparse,
+        "exchange": exchange_label if world > 1 else None,
         "pairs": {"value": pairs_per_s, "unit": "pairs/s", "what": "full-catalog BasicRS scoring + top-10, %d users x %d items per rank" % (cu, n_items),
                   "ms": cat_ms,
                   "bf16_tcgen05": {"value": pairs_tc, "unit": "pairs/s", "users_per_rank": cu_tc, "ms": tc_ms,

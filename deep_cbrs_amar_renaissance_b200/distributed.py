@@ -118,8 +118,10 @@ def exchange_rows(x, ranges, group=None):
 class SymmetricBuffer:
     """One allocation of a PeerHeap: the same number of bytes on every rank, all copies mapped here."""
 
-    def __init__(self, heap, nbytes, ptrs):
+    def __init__(self, heap, nbytes, ptrs, mc_ptr=0, keep=None):
         self.heap, self.nbytes, self.ptrs = heap, nbytes, ptrs  # ptrs[r] = address of rank r's copy
+        self.mc_ptr = int(mc_ptr or 0)   # NVSwitch multicast mapping of all copies (0: none); a store there lands in every copy
+        self._keep = keep                # the torch symmetric-memory tensor + handle that own the mapping ("symm" backend)
         self.local = ptrs[heap.rank]
         self._iface = type("_Raw", (), {})()
         self._iface.__cuda_array_interface__ = {"shape": (nbytes // 4,), "typestr": "<f4",
@@ -141,16 +143,44 @@ class SymmetricBuffer:
             raise ValueError("view does not live in this symmetric buffer")
         return [p + off for r, p in enumerate(self.ptrs) if r != self.heap.rank]
 
+    def mc_addr(self, view):
+        """address of `view` in the multicast mapping, or None when the buffer has none"""
+        if not self.mc_ptr:
+            return None
+        off = view.data_ptr() - self.local
+        if off < 0 or off >= self.nbytes:
+            raise ValueError("view does not live in this symmetric buffer")
+        return self.mc_ptr + off
+
 
 class PeerHeap:
     """Symmetric peer-mapped allocations for the ranks of one box + the flag barrier.
     alloc() is collective: every rank calls it in the same order with the same size."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, backend=None):
+        """backend: "ipc" = cudaMalloc + CUDA IPC handles (cbrs_peer_*); "symm" = torch.distributed symmetric memory
+        (plumbing only: allocation + rendezvous), which also maps the buffers through an NVSwitch MULTICAST object when
+        the fabric supports it (NCCL calls the same facility NVLS) - SymmetricBuffer.mc_ptr.  Default: CBRS_PEER_BACKEND
+        or "symm", falling back to "ipc" together on every rank if symmetric memory cannot be set up."""
         from . import _lib as L
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self.backend = backend or os.environ.get("CBRS_PEER_BACKEND", "symm")
+        if self.backend not in ("ipc", "symm"):
+            raise ValueError("peer backend must be 'ipc' or 'symm'")
+        if self.backend == "symm":
+            ok = 1
+            try:
+                import torch.distributed._symmetric_memory as symm_mem   # noqa: F401
+                probe = self._alloc_symm(256)
+                del probe
+            except Exception as e:  # noqa: BLE001
+                ok, self._symm_error = 0, e
+            flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) != 1:
+                self.backend = "ipc"
         if self.world > L.MAX_PEERS:
             raise L.CbrsError("peer exchange supports up to {} ranks (one NVSwitch box)".format(L.MAX_PEERS))
         self._lib = L.load()
@@ -166,9 +196,26 @@ class PeerHeap:
         self.barrier()
         self.check()
 
+    def _alloc_symm(self, nbytes):
+        import torch.distributed._symmetric_memory as symm_mem
+        t = symm_mem.empty(nbytes // 4, dtype=torch.float32, device=torch.device("cuda", torch.cuda.current_device()))
+        hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+        t.zero_()
+        torch.cuda.synchronize()
+        ptrs = [int(a) for a in hdl.buffer_ptrs]
+        ptrs[self.rank] = t.data_ptr()
+        mc = int(hdl.multicast_ptr) if getattr(hdl, "has_multicast_support", lambda *_: True) and hdl.multicast_ptr else 0
+        if os.environ.get("CBRS_MULTICAST", "1") == "0":
+            mc = 0
+        return SymmetricBuffer(self, nbytes, ptrs, mc_ptr=mc, keep=(t, hdl))
+
     def alloc(self, nbytes):
         from . import _lib as L
         nbytes = (int(nbytes) + 255) // 256 * 256
+        if self.backend == "symm":
+            sb = self._alloc_symm(nbytes)
+            dist.barrier(group=self.group)   # every rank zeroed its copy before anybody stores into it
+            return sb
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_ubyte * L.IPC_HANDLE_BYTES)()
         # a local failure (cudaMalloc out of memory, export error) must not skip the collective below: the other
@@ -236,6 +283,7 @@ class PeerHeap:
         torch.cuda.synchronize()
         self.check()
         dist.barrier(group=self.group)
+        self.flags = None   # "symm" backend: the mappings go with the tensors
         for q in self._opened:
             self._lib.cbrs_peer_close(ctypes.c_void_p(q))
         self._opened = []
@@ -447,6 +495,14 @@ class RowPartition:
             def out_peers(view, a):
                 return osb.peer_addrs(view) if (everywhere or is_final(a)) else None
 
+            def out_targets(view, a):
+                """keyword arguments for the sparse kernels: one store to the multicast mapping when the buffer has
+                one, else a store per peer copy"""
+                if not (everywhere or is_final(a)):
+                    return {}
+                mc = osb.mc_addr(view)
+                return {"mc": mc} if mc else {"peers": osb.peer_addrs(view)}
+
             if isinstance(layer, GCNConv) and self.pipeline == "replicate":
                 # Every rank computes the WHOLE transform Z = X W itself (2.5 ms for 1.1e7 x 128 x 128 on the tensor
                 # cores) from a layer input that is complete on every rank: layer 0 reads the replicated embedding
@@ -461,7 +517,7 @@ class RowPartition:
                 for sl in self.csr_slices("norm", graph):
                     a, b = sl.row_offset, sl.row_offset + sl.n_rows
                     ov = out[a:b]
-                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, peers=out_peers(ov, a))
+                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, **out_targets(ov, a))
                 z_ahead = False
             elif isinstance(layer, (GCNConv, RGCNConv)):
                 kernels = layer.kernels if isinstance(layer, RGCNConv) else [layer.kernel]
@@ -516,7 +572,7 @@ class RowPartition:
                 for sl in self.csr_slices("norm", graph):
                     a, b = sl.row_offset, sl.row_offset + sl.n_rows
                     ov = out[a:b]
-                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, peers=out_peers(ov, a))
+                    ops.spmm(sl, z, ov, bias=layer.bias, relu=relu, **out_targets(ov, a))
                     if z_ahead:
                         done = torch.cuda.Event()
                         done.record(main)
@@ -555,7 +611,7 @@ class RowPartition:
                     heap.barrier()  # x_full = previous output, pushed everywhere by its producer
                 for sl in self.csr_slices("norm", graph):
                     ov = out[sl.row_offset:sl.row_offset + sl.n_rows]
-                    ops.spmm(sl, x_full, ov, peers=out_peers(ov, sl.row_offset))
+                    ops.spmm(sl, x_full, ov, **out_targets(ov, sl.row_offset))
             elif isinstance(layer, GraphSageConv):
                 if l > 0:
                     heap.barrier()

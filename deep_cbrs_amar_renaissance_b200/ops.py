@@ -125,10 +125,13 @@ def _ptr_array(addresses):
     return (ctypes.c_void_p * max(len(addresses), 1))(*addresses)
 
 
-def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None, peers=None):
+def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None, peers=None, mc=None):
     """out[:, :] = epilogue(A @ x) for the rows held by `csr` (a graph.CsrSlice).
     peers: device addresses of the same `out` view in the other ranks' symmetric buffers; every
-    finished row is stored there too (cbrs_spmm_csr_bcast)."""
+    finished row is stored there too (cbrs_spmm_csr_bcast).
+    mc: address of the same `out` view in the NVSwitch MULTICAST mapping of the symmetric buffer: the kernel then
+    stores every finished row ONCE, to that address, and the switch delivers it to all ranks' copies (this rank's
+    included) - one store per row instead of 1 + n_peers (multimem.st is a plain store on a multicast address)."""
     lib = L.load()
     x, ldx = _rowmajor(x, (torch.float32, torch.bfloat16))
     xdt = L.DTYPE_BF16 if x.dtype == torch.bfloat16 else L.DTYPE_F32
@@ -141,7 +144,11 @@ def spmm(csr, x, out, agg=L.AGG_WEIGHTED, bias=None, relu=False, workspace=None,
     if PROFILE_ON:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    if peers:
+    if mc:
+        L.check(lib.cbrs_spmm_csr(ctypes.byref(csr.desc), _ptr(x), ldx, ctypes.c_void_p(int(mc)), ldy, d, agg,
+                                  _ptr(bias, torch.float32), 1 if relu else 0, xdt, _ptr(ws), ws.numel(),
+                                  _stream()), "cbrs_spmm_csr")
+    elif peers:
         L.check(lib.cbrs_spmm_csr_bcast(ctypes.byref(csr.desc), _ptr(x), ldx, _ptr(out), ldy, d, agg,
                                         _ptr(bias, torch.float32), 1 if relu else 0, xdt, _ptr_array(peers),
                                         len(peers), _ptr(ws), ws.numel(), _stream()), "cbrs_spmm_csr_bcast")
