@@ -99,7 +99,12 @@ template <>
 struct Vec<8> {
     float4 a, b;
     __device__ __forceinline__ void zero() { a = make_float4(0.f, 0.f, 0.f, 0.f); b = a; }
-    __device__ __forceinline__ void load(const float *p) { a = ldg4(p); b = ldg4(p + 4); }
+    // one 256-bit load (LDG.E.256, sm_100): a 128-wide fp32 row is 16 lanes, two chunks share a warp
+    __device__ __forceinline__ void load(const float *p) {
+        asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                     : "l"(p));
+    }
     __device__ __forceinline__ void load_plain(const float *p) {
         a = *reinterpret_cast<const float4 *>(p); b = *reinterpret_cast<const float4 *>(p + 4);
     }
@@ -485,6 +490,13 @@ static int launch(const SpmmParams &p, cudaStream_t s) {
                 case 5: spmm_chunk_kernel<32, 4, 2, 6><<<grid, kSpmmThreads, 0, s>>>(p); break;
                 default: spmm_chunk_kernel<32, 4, 4, 4><<<grid, kSpmmThreads, 0, s>>>(p); break;
             }
+        } else if (G == 16 && VEC == 8) {
+            switch (spmm_variant()) {   // fp32, 256-bit loads: loads in flight x occupancy
+                case 7: spmm_chunk_kernel<16, 8, 4, 3><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 8: spmm_chunk_kernel<16, 8, 2, 4><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                case 9: spmm_chunk_kernel<16, 8, 8, 2><<<grid, kSpmmThreads, 0, s>>>(p); break;
+                default: spmm_chunk_kernel<16, 8, 4, 4><<<grid, kSpmmThreads, 0, s>>>(p); break;
+            }
         } else {
             spmm_chunk_kernel<G, VEC><<<grid, kSpmmThreads, 0, s>>>(p);
         }
@@ -562,6 +574,9 @@ static int spmm_impl(const cbrs_csr_t *g, const void *x, int64_t ldx, void *y, i
         if (v8) return dispatch_g<8, __nv_bfloat16>(d / 8, p, s);  // 16-byte loads, half the lanes per row
         return v4 ? dispatch_g<4, __nv_bfloat16>(d / 4, p, s) : dispatch_g<1, __nv_bfloat16>(d, p, s);
     }
+    // CBRS_SPMM_VARIANT=6: 256-bit row loads (fp32 rows 32-byte aligned, d % 8 == 0) - tuning knob
+    const bool vec8 = vec4 && (d % 8 == 0) && (ldx % 8 == 0) && ((uintptr_t)x % 32 == 0) && spmm_variant() >= 6;
+    if (vec8) return dispatch_g<8>(d / 8, p, s);
     return vec4 ? dispatch_g<4>(d / 4, p, s) : dispatch_g<1>(d, p, s);
 }
 
