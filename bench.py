@@ -117,14 +117,22 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+NCU_SPMM = os.path.join("profiles", "r02_ncu_spmm_blocked_tf32x3_c5.json")
+
+
 def ncu_traffic(scale, world):
-    """dram bytes per SpMM launch from the committed ncu --set full capture (same workload, 1 GPU only)."""
+    """dram bytes per sparse-kernel launch from the committed `ncu --set full` capture of this same workload (one GPU,
+    config 5): a CITATION of profiles/r02_ncu_spmm_blocked_tf32x3_c5.json, not something measured in this run (ncu
+    cannot run inside a timed bench); the line says so in roofline.traffic_source."""
     if scale != "c5" or world != 1:
         return None
     try:
-        return json.load(open(os.path.join(REPO, "profiles", "r01_spmm_ncu.json")))["traffic_bytes_per_launch"]
+        for k in json.load(open(os.path.join(REPO, NCU_SPMM))):
+            if "spmm_chunk_kernel" in k["kernel"]:
+                return (float(k["dram__bytes_read.sum [Gbyte]"]) + float(k["dram__bytes_write.sum [Gbyte]"])) * 1e9
     except Exception:
-        return None
+        pass
+    return None
 
 
 def workload_config(scale, gpus):
@@ -409,13 +417,17 @@ def run_b200(args):
     avg_ms = float(np.mean(spmm_ms)) if spmm_ms else float("nan")
     alg_bytes = float(np.mean([m["bytes"] for m in spmm_meta])) if spmm_meta else float("nan")
     achieved = (sum(m["bytes"] for m in spmm_meta) / (sum(spmm_ms) * 1e-3) / 1e9) if spmm_ms else float("nan")
-    roofline = {"bound": "hbm", "kernel": "spmm_chunk_kernel<32,4,4,4> (+heavy-row merge)", "achieved": achieved,
-                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": ncu_traffic(args.scale, world),
+    traffic = ncu_traffic(args.scale, world)
+    roofline = {"bound": "hbm", "kernel": "spmm_chunk_kernel<32,4,4,4> on the column-blocked schedule (+heavy-row merge)",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                "traffic_source": (NCU_SPMM + " (ncu --set full of this workload, committed; not measured in this run)") if traffic else None,
                 "peak_source": peak_src, "launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_edge": 8 + DIM * 4, "launches_timed": len(spmm_ms),
                 "share_of_step": (sum(spmm_ms) / args.steps) / ms_per_step if spmm_ms else None,
-                "note": "achieved = algorithmic bytes (no-reuse gather model) / measured launch time; it can exceed the "
-                        "DRAM peak because hot item rows hit in L2 - `traffic` is what ncu saw cross the HBM pins"}
+                "note": "achieved = algorithmic bytes (no-reuse gather model, SURVEY 8d) / measured launch time; it exceeds the "
+                        "DRAM peak because the blocked schedule serves heavy rows from an L2-resident window and hot item "
+                        "rows hit in L2 - `traffic` is what ncu saw cross the HBM pins (the kernel is bound by the L2 -> SM "
+                        "path, DESIGN.md section 4)"}
 
     # ---- the same step with bf16 STORAGE of the gathered operand (config 5's "bf16 feature variant") -------
     # Z = X W is written as bf16 by the dense kernel (and travels as bf16 between GPUs); products and sums stay
