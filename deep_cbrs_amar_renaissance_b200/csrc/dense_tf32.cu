@@ -53,6 +53,7 @@ struct T3Params {
     int64_t ldo;
     float *out_peer[CBRS_MAX_PEERS - 1];
     int32_t n_peer;
+    int32_t out_bf16;   // out / out_peer hold bf16 (round to nearest even), ldo in elements
     int64_t n_tiles;
 };
 
@@ -99,6 +100,15 @@ __device__ __forceinline__ void t3_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// 16 fp32 -> 16 bf16 = one 32-byte sector
+__device__ __forceinline__ void t3_store16_bf16(float *base, int64_t elem, const float (&o)[2][8]) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = tc::pack_bf16x2(o[j >> 2][(2 * j) & 7], o[j >> 2][(2 * j + 1) & 7]);
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(reinterpret_cast<__nv_bfloat16 *>(base) + elem),
+                 "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
 }
 __device__ __forceinline__ void t3_store8(float *p, const float (&o)[8]) {
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
@@ -274,7 +284,10 @@ __global__ void __launch_bounds__(kT3Threads, 1)
                     for (int j = 0; j < 16; ++j)
                         o[j >> 3][j & 7] = kPlain ? __uint_as_float(v[j]) : t3_act(__uint_as_float(v[j]) + bias_s[cb + j], p.act);
                     const int64_t off = row * p.ldo + cb;
-                    if (v8_ok) {
+                    if (p.out_bf16) {   // host checked: ldo % 16 == 0 and 32-byte aligned bases
+                        t3_store16_bf16(p.out, off, o);
+                        for (int q = 0; q < p.n_peer; ++q) t3_store16_bf16(p.out_peer[q], off, o);
+                    } else if (v8_ok) {
                         t3_store8(p.out + off, o[0]);
                         t3_store8(p.out + off + 8, o[1]);
                         for (int q = 0; q < p.n_peer; ++q) {
@@ -350,8 +363,12 @@ extern "C" int cbrs_dense_tf32x3_prepare(const float *w, int32_t k, int32_t n, v
 }
 
 extern "C" int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k,
-                                 int32_t n, int act, float *out, int64_t ldo, void *const *out_peers_host, int n_peers,
-                                 void *stream) {
+                                 int32_t n, int act, void *out_v, int64_t ldo, int out_dtype, void *const *out_peers_host,
+                                 int n_peers, void *stream) {
+    float *out = (float *)out_v;
+    CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || out_dtype == CBRS_DTYPE_BF16, CBRS_E_INVALID, "cbrs_dense_tf32x3: out_dtype=%d", out_dtype);
+    CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || (ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(out_v) & 31u) == 0), CBRS_E_INVALID,
+                 "cbrs_dense_tf32x3: a bf16 output needs 32-byte aligned rows (ldo %% 16 == 0)");
     CBRS_REQUIRE(x && w_image && out, CBRS_E_INVALID, "cbrs_dense_tf32x3: null pointer");
     CBRS_REQUIRE(cbrs_dense_tf32x3_eligible(k, n), CBRS_E_INVALID, "cbrs_dense_tf32x3: k = %d, n = %d not supported (see "
                  "cbrs_dense_tf32x3_eligible); use cbrs_dense", k, n);
@@ -377,6 +394,7 @@ extern "C" int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_imag
     T3Params p;
     p.w_image = (const uint8_t *)w_image; p.bias = b; p.act = act; p.m = m; p.n = n; p.k = k; p.out = out; p.ldo = ldo;
     p.n_peer = n_peers;
+    p.out_bf16 = out_dtype == CBRS_DTYPE_BF16;
     for (int q = 0; q < CBRS_MAX_PEERS - 1; ++q) {
         p.out_peer[q] = q < n_peers ? (float *)out_peers_host[q] : nullptr;
         CBRS_REQUIRE(q >= n_peers || (p.out_peer[q] && ((reinterpret_cast<uintptr_t>(p.out_peer[q]) & 31u) ==

@@ -286,14 +286,20 @@ def tf32x3_chosen(rows_total, k, n, x=None, out=None):
         return False
     if not L.load().cbrs_dense_tf32x3_eligible(int(k), int(n)):
         return False
-    for t in (x, out):
-        if t is not None and (t.dtype != torch.float32 or t.stride(1) != 1 or t.stride(0) % 4 or t.data_ptr() % 16):
+    if x is not None and (x.dtype != torch.float32 or x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16):
+        return False
+    if out is not None:
+        if out.dtype == torch.bfloat16:
+            if out.stride(1) != 1 or out.stride(0) % 16 or out.data_ptr() % 32:
+                return False
+        elif out.dtype != torch.float32 or out.stride(1) != 1 or out.stride(0) % 4 or out.data_ptr() % 16:
             return False
     return True
 
 
-def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None):
-    """act(x @ w + b) with the product as three TF32 tcgen05 MMAs (fp32-accurate, cbrs_dense_tf32x3)."""
+def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None, out_dtype=None):
+    """act(x @ w + b) with the product as three TF32 tcgen05 MMAs (fp32-accurate, cbrs_dense_tf32x3); the result can be
+    stored rounded to bf16 (out_dtype=torch.bfloat16 / a bf16 `out`), as cbrs_dense_ex does for the FFMA kernel."""
     lib = L.load()
     x, ldx = _rowmajor(x)
     m, k = x.shape
@@ -301,8 +307,8 @@ def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None):
         raise L.CbrsError("dense_tf32x3: kernel must be contiguous [{}, n], got {}".format(k, tuple(w.shape)))
     n = w.shape[1]
     if out is None:
-        out = torch.empty(m, n, dtype=torch.float32, device=x.device)
-    out, ldo = _rowmajor(out)
+        out = torch.empty(m, n, dtype=out_dtype or torch.float32, device=x.device)
+    out, ldo = _rowmajor(out, (torch.float32, torch.bfloat16))
     image = torch.empty(lib.cbrs_dense_tf32x3_image_bytes(k, n), dtype=torch.uint8, device=x.device)
     if PROFILE_ON:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -310,6 +316,7 @@ def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None):
     L.check(lib.cbrs_dense_tf32x3_prepare(_ptr(w, torch.float32), k, n, _ptr(image), _stream()), "cbrs_dense_tf32x3_prepare")
     code = act if isinstance(act, int) else L.ACTS[act]
     L.check(lib.cbrs_dense_tf32x3(_ptr(x), ldx, _ptr(image), _ptr(b, torch.float32), m, k, n, code, _ptr(out), ldo,
+                                  L.DTYPE_BF16 if out.dtype == torch.bfloat16 else L.DTYPE_F32,
                                   _ptr_array(peers) if peers else None, len(peers) if peers else 0, _stream()),
             "cbrs_dense_tf32x3")
     _count(2)
@@ -321,7 +328,9 @@ def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None):
 
 def gcn_transform(x, w, rows_total, out=None, out_dtype=None, peers=None):
     """Z = x @ w for a GCN layer; rows_total = node count of the whole graph (decides the kernel, see above)."""
-    if out_dtype is None and (out is None or out.dtype == torch.float32) and tf32x3_chosen(rows_total, x.shape[1], w.shape[1], x, out):
+    if out is None and out_dtype is not None:
+        out = torch.empty(x.shape[0], w.shape[1], dtype=out_dtype, device=x.device)
+    if tf32x3_chosen(rows_total, x.shape[1], w.shape[1], x, out):
         return dense_tf32x3(x, w, out=out, peers=peers)
     return dense(x, w, out=out, out_dtype=out_dtype, peers=peers)
 

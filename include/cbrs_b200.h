@@ -221,14 +221,15 @@ int cbrs_dense_grouped(const float *x, int64_t ldx, const float *w_cat, int64_t 
  * X tiles arrive by TMA (cp.async.bulk.tensor, SWIZZLE_128B); W is handed over as the operand image written by
  * cbrs_dense_tf32x3_prepare (cbrs_dense_tf32x3_image_bytes(k, n) bytes, 16-byte aligned; rewrite it when W changes).
  * Shapes: k % 32 == 0, n % 16 == 0, 16 <= n <= 256, both operand images resident in shared memory (k*n <= 16384):
- * cbrs_dense_tf32x3_eligible.  Rows of x 16-byte aligned.  out_peers_host / n_peers as in cbrs_dense_bcast.
+ * cbrs_dense_tf32x3_eligible.  Rows of x 16-byte aligned.  out_peers_host / n_peers as in cbrs_dense_bcast;
+ * out_dtype = CBRS_DTYPE_BF16 stores the fp32 result rounded to bf16 (ldo in elements, % 16 == 0), as cbrs_dense_ex.
  * A row's result does not depend on its position in the 128-row tile => identical bits under any row partition.  */
 int cbrs_dense_tf32x3_eligible(int32_t k, int32_t n);
 size_t cbrs_dense_tf32x3_image_bytes(int32_t k, int32_t n);
 int cbrs_dense_tf32x3_prepare(const float *w, int32_t k, int32_t n, void *image, void *stream);
 int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k,
-                      int32_t n, int act, float *out, int64_t ldo, void *const *out_peers_host, int n_peers,
-                      void *stream);
+                      int32_t n, int act, void *out, int64_t ldo, int out_dtype, void *const *out_peers_host,
+                      int n_peers, void *stream);
 
 /* General form of cbrs_dense: the output (and its peer copies) can be written as bf16 (out_dtype =
  * CBRS_DTYPE_BF16, round to nearest even, ldo in elements) so that the GCN transform Z = X W feeds the bf16

@@ -103,3 +103,16 @@ def test_gcn_layer_with_the_tensor_core_transform_matches_oracle(dev, monkeypatc
     z = ops.gcn_transform(xd, wd, n)
     ops.spmm(g.norm, z, out, bias=bd, relu=True)
     assert_close(out.cpu().numpy(), want, rtol=1e-5, what="GCN layer, tf32x3 transform")
+
+
+def test_tf32x3_bf16_output_is_the_rounded_fp32_output(dev):
+    """out_dtype = bf16 (the bf16-operand variant of the propagation stores Z = X W as bf16): exactly the fp32 result
+    rounded to nearest even, also into a strided buffer"""
+    from deep_cbrs_amar_renaissance_b200 import ops
+    x, w, b, xd, wd, bd = _case(1000, 128, 128, 12, dev)
+    full = ops.dense_tf32x3(xd, wd)
+    assert torch.equal(ops.dense_tf32x3(xd, wd, out_dtype=torch.bfloat16), full.to(torch.bfloat16))
+    buf = torch.zeros(1000, 256, device=dev, dtype=torch.bfloat16)
+    ops.dense_tf32x3(xd, wd, bd, "relu", out=buf[:, 128:])
+    assert torch.equal(buf[:, 128:], ops.dense_tf32x3(xd, wd, bd, "relu").to(torch.bfloat16)) and (buf[:, :128] == 0).all()
+    assert ops.tf32x3_chosen(1 << 20, 128, 128, xd, buf[:, 128:]) and not ops.tf32x3_chosen(1 << 20, 128, 128, xd, buf[:, 8:136])
