@@ -55,6 +55,10 @@ struct T3Params {
     int32_t n_peer;
     int32_t out_bf16;   // out / out_peer hold bf16 (round to nearest even), ldo in elements
     int64_t n_tiles;
+    // GAT row-op (cbrs_dense_tf32x3_attn): p[m] = out[m,:] . a_self, q[m] = out[m,:] . a_neigh (GATConv's attention logits)
+    const float *a_self, *a_neigh;
+    float *p_out, *q_out;
+    float *q_peer[CBRS_MAX_PEERS - 1];
 };
 
 __device__ __forceinline__ float t3_act(float v, int act) {
@@ -132,7 +136,9 @@ __global__ void t3_prep_kernel(const float *__restrict__ w, int k, int n, uint8_
     }
 }
 
-template <bool kPlain>   // kPlain: no bias, no activation (the GCN transform): the epilogue is a straight copy
+// kPlain: no bias, no activation (the GCN / GAT transform): the epilogue is a straight copy.  kAttn (implies kPlain):
+// also the two attention logits of the row.
+template <bool kPlain, bool kAttn = false>
 __global__ void __launch_bounds__(kT3Threads, 1)
     dense_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ T3Params p) {
     extern __shared__ __align__(1024) unsigned char t3_smem[];
@@ -170,6 +176,11 @@ __global__ void __launch_bounds__(kT3Threads, 1)
     }
     if (!kPlain)
         for (int e = tid; e < p.n; e += kT3Threads) bias_s[e] = p.bias ? __ldg(p.bias + e) : 0.f;
+    if (kAttn)
+        for (int e = tid; e < p.n; e += kT3Threads) {
+            bias_s[e] = __ldg(p.a_self + e);
+            bias_s[p.n + e] = __ldg(p.a_neigh + e);
+        }
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
@@ -274,6 +285,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
             tc::tc_fence_after_sync();
             const int64_t row = tile * kT3Rows + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n);
+            float ps = 0.f, qs = 0.f;
             for (int cb = 0; cb < p.n; cb += 16) {
                 uint32_t v[16];
                 tc::tmem_ld16(taddr + (uint32_t)cb, v);   // warp-collective
@@ -283,6 +295,13 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         o[j >> 3][j & 7] = kPlain ? __uint_as_float(v[j]) : t3_act(__uint_as_float(v[j]) + bias_s[cb + j], p.act);
+                    if (kAttn) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            ps = fmaf(o[j >> 3][j & 7], bias_s[cb + j], ps);
+                            qs = fmaf(o[j >> 3][j & 7], bias_s[p.n + cb + j], qs);
+                        }
+                    }
                     const int64_t off = row * p.ldo + cb;
                     if (p.out_bf16) {   // host checked: ldo % 16 == 0 and 32-byte aligned bases
                         t3_store16_bf16(p.out, off, o);
@@ -303,6 +322,11 @@ __global__ void __launch_bounds__(kT3Threads, 1)
                     }
                 }
             }
+            if (kAttn && row < p.m) {
+                p.p_out[row] = ps;
+                p.q_out[row] = qs;
+                for (int q = 0; q < p.n_peer; ++q) p.q_peer[q][row] = qs;
+            }
             tc::tc_fence_before_sync();
             t3_arrive(acc_empty + acc);
         }
@@ -317,7 +341,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 
 static size_t t3_smem_bytes(int k, int n) {
     return 2 * (size_t)(k / kT3Atom) * n * 128 + (size_t)(4 + kT3Raw) * kT3AtomBytes + (2 * kT3Raw + 9) * sizeof(uint64_t) + 8 +
-           (size_t)n * 4 + 64;
+           2 * (size_t)n * 4 + 64;
 }
 
 typedef CUresult (*t3_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -362,10 +386,14 @@ extern "C" int cbrs_dense_tf32x3_prepare(const float *w, int32_t k, int32_t n, v
     return CBRS_OK;
 }
 
-extern "C" int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k,
-                                 int32_t n, int act, void *out_v, int64_t ldo, int out_dtype, void *const *out_peers_host,
-                                 int n_peers, void *stream) {
+static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k, int32_t n, int act,
+                   void *out_v, int64_t ldo, int out_dtype, void *const *out_peers_host, int n_peers, const float *a_self,
+                   const float *a_neigh, float *p_out, float *q_out, void *const *q_peers_host, void *stream) {
     float *out = (float *)out_v;
+    const bool attn = a_self != nullptr;
+    CBRS_REQUIRE(!attn || (a_neigh && p_out && q_out && !b && act == CBRS_ACT_NONE && out_dtype == CBRS_DTYPE_F32 &&
+                           (n_peers == 0 || q_peers_host)),
+                 CBRS_E_INVALID, "cbrs_dense_tf32x3_attn: needs a_self, a_neigh, p_out, q_out (and q_peers with peers), fp32 output");
     CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || out_dtype == CBRS_DTYPE_BF16, CBRS_E_INVALID, "cbrs_dense_tf32x3: out_dtype=%d", out_dtype);
     CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || (ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(out_v) & 31u) == 0), CBRS_E_INVALID,
                  "cbrs_dense_tf32x3: a bf16 output needs 32-byte aligned rows (ldo %% 16 == 0)");
@@ -401,6 +429,11 @@ extern "C" int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_imag
                                                          (reinterpret_cast<uintptr_t>(out) & 31u))),
                      CBRS_E_INVALID, "cbrs_dense_tf32x3: peer copy %d is null or aligned differently from out", q);
     }
+    p.a_self = a_self; p.a_neigh = a_neigh; p.p_out = p_out; p.q_out = q_out;
+    for (int q = 0; q < CBRS_MAX_PEERS - 1; ++q) {
+        p.q_peer[q] = (attn && q < n_peers) ? (float *)q_peers_host[q] : nullptr;
+        CBRS_REQUIRE(!attn || q >= n_peers || p.q_peer[q], CBRS_E_INVALID, "cbrs_dense_tf32x3_attn: q peer copy %d is null", q);
+    }
     p.n_tiles = cdiv(m, kT3Rows);
     const size_t smem = t3_smem_bytes(k, n);
     static bool attr_set = false;
@@ -408,14 +441,34 @@ extern "C" int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_imag
         cudaError_t e = cudaFuncSetAttribute(dense_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(dense_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(dense_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "cbrs_dense_tf32x3: %s", cudaGetErrorString(e));
         attr_set = true;
     }
     const unsigned grid = (unsigned)(p.n_tiles < kSMs ? p.n_tiles : kSMs);
-    if (!b && act == CBRS_ACT_NONE)
+    if (attn)
+        dense_tf32x3_kernel<true, true><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(map, p);
+    else if (!b && act == CBRS_ACT_NONE)
         dense_tf32x3_kernel<true><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(map, p);
     else
         dense_tf32x3_kernel<false><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(map, p);
     CBRS_CHECK_LAUNCH("cbrs_dense_tf32x3");
     return CBRS_OK;
+}
+
+extern "C" int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k,
+                                 int32_t n, int act, void *out, int64_t ldo, int out_dtype, void *const *out_peers_host,
+                                 int n_peers, void *stream) {
+    return t3_impl(x, ldx, w_image, b, m, k, n, act, out, ldo, out_dtype, out_peers_host, n_peers, nullptr, nullptr, nullptr,
+                   nullptr, nullptr, stream);
+}
+
+extern "C" int cbrs_dense_tf32x3_attn(const float *x, int64_t ldx, const void *w_image, int64_t m, int32_t k, int32_t n,
+                                      const float *a_self, const float *a_neigh, float *p_out, float *q_out, float *out,
+                                      int64_t ldo, void *const *out_peers_host, void *const *q_peers_host, int n_peers,
+                                      void *stream) {
+    CBRS_REQUIRE(a_self && a_neigh && p_out && q_out, CBRS_E_INVALID, "cbrs_dense_tf32x3_attn: null attention argument");
+    return t3_impl(x, ldx, w_image, nullptr, m, k, n, CBRS_ACT_NONE, out, ldo, CBRS_DTYPE_F32, out_peers_host, n_peers, a_self,
+                   a_neigh, p_out, q_out, q_peers_host, stream);
 }

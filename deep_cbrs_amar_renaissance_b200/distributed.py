@@ -596,10 +596,9 @@ class RowPartition:
                 p = self._buf(("p", l), n, 1, emb.device)
                 for a, b in self.mine:
                     zv, qv = z[a:b], q[a:b, 0]
-                    _, pp, _ = ops.dense(x_full[a:b], layer.kernel.reshape(widths[l], layer.channels),
-                                         rowop=L.ROWOP_ATTN, a_self=layer.attn_kernel_self.reshape(-1),
-                                         a_neigh=layer.attn_kernel_neighs.reshape(-1), out=zv, q_out=qv,
-                                         peers=zsb.peer_addrs(zv), q_peers=qsb.peer_addrs(qv))
+                    _, pp, _ = ops.gat_transform(x_full[a:b], layer.kernel.reshape(widths[l], layer.channels),
+                                                 layer.attn_kernel_self.reshape(-1), layer.attn_kernel_neighs.reshape(-1), n,
+                                                 out=zv, q_out=qv, peers=zsb.peer_addrs(zv), q_peers=qsb.peer_addrs(qv))
                     p[a:b, 0].copy_(pp)
                 heap.barrier()
                 for sl in self.csr_slices("raw", graph):
@@ -680,9 +679,9 @@ class RowPartition:
                 p = self._buf(("p", l), n, 1, dev)
                 q = self._buf(("q", l), n, 1, dev)
                 for a, b in self.mine:
-                    _, pp, qq = ops.dense(x_full[a:b], layer.kernel.reshape(widths[l], layer.channels),
-                                          rowop=L.ROWOP_ATTN, a_self=layer.attn_kernel_self.reshape(-1),
-                                          a_neigh=layer.attn_kernel_neighs.reshape(-1), out=z[a:b])
+                    _, pp, qq = ops.gat_transform(x_full[a:b], layer.kernel.reshape(widths[l], layer.channels),
+                                                  layer.attn_kernel_self.reshape(-1), layer.attn_kernel_neighs.reshape(-1), n,
+                                                  out=z[a:b])
                     p[a:b, 0].copy_(pp)
                     q[a:b, 0].copy_(qq)
                 self._exchange(z)

@@ -109,8 +109,8 @@ class GATConv(_Conv):
     def call(self, inputs, out=None, csr=None, **kwargs):
         x, a = inputs
         csr = csr or a.raw
-        z, p, q = ops.dense(x, self.kernel.reshape(x.shape[1], self.channels), rowop=L.ROWOP_ATTN,
-                            a_self=self.attn_kernel_self.reshape(-1), a_neigh=self.attn_kernel_neighs.reshape(-1))
+        z, p, q = ops.gat_transform(x, self.kernel.reshape(x.shape[1], self.channels), self.attn_kernel_self.reshape(-1),
+                                    self.attn_kernel_neighs.reshape(-1), x.shape[0])
         return ops.gat(csr, z, p, q, self._out(out, csr.n_rows, x.device), bias=self.bias,
                        relu=self.activation == "relu", row_offset=csr.row_offset)
 

@@ -326,6 +326,37 @@ def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None, out_dtype=None):
     return out
 
 
+def gat_transform(x, w, a_self, a_neigh, rows_total, out=None, q_out=None, peers=None, q_peers=None):
+    """(z, p, q) = (x @ w, z . a_self, z . a_neigh) for a GAT layer: the tensor-core kernel with the attention row-op from
+    TF32X3_MIN_ROWS graph nodes up (cbrs_dense_tf32x3_attn), else cbrs_dense with CBRS_ROWOP_ATTN."""
+    k, n = x.shape[1], w.shape[1]
+    if not tf32x3_chosen(rows_total, k, n, x, out):
+        return dense(x, w, rowop=L.ROWOP_ATTN, a_self=a_self, a_neigh=a_neigh, out=out, q_out=q_out, peers=peers, q_peers=q_peers)
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    m = x.shape[0]
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    out, ldo = _rowmajor(out)
+    p_out = torch.empty(m, dtype=torch.float32, device=x.device)
+    if q_out is None:
+        q_out = torch.empty(m, dtype=torch.float32, device=x.device)
+    image = torch.empty(lib.cbrs_dense_tf32x3_image_bytes(k, n), dtype=torch.uint8, device=x.device)
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(lib.cbrs_dense_tf32x3_prepare(_ptr(w.contiguous(), torch.float32), k, n, _ptr(image), _stream()), "cbrs_dense_tf32x3_prepare")
+    L.check(lib.cbrs_dense_tf32x3_attn(_ptr(x), ldx, _ptr(image), m, k, n, _ptr(a_self, torch.float32), _ptr(a_neigh, torch.float32),
+                                       _ptr(p_out), _ptr(q_out), _ptr(out), ldo, _ptr_array(peers) if peers else None,
+                                       _ptr_array(q_peers) if q_peers else None, len(peers) if peers else 0, _stream()),
+            "cbrs_dense_tf32x3_attn")
+    _count(2)
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("dense", e0, e1, m * n))
+    return out, p_out, q_out
+
+
 def gcn_transform(x, w, rows_total, out=None, out_dtype=None, peers=None):
     """Z = x @ w for a GCN layer; rows_total = node count of the whole graph (decides the kernel, see above)."""
     if out is None and out_dtype is not None:

@@ -140,6 +140,20 @@ def partition_parity(group=None, log=None, families=("BasicGCN", "BasicGraphSage
                                     transform, pipeline, " blocked" if blocking else "", rep))
                             part.close()
                             seq.partition = None
+                        if transform == "tf32x3":   # the GAT transform (z, p, q) on the tensor-core kernel, partitioned
+                            set_seed(13)
+                            model = basic.BasicGAT(adj, n_hiddens=[64, 64], embedding_dim=64, dense_units=[48, 48],
+                                                   clf_units=[64, 64])
+                            seq = model.gnn.gnn_layers
+                            model((u, i))
+                            full = model.gnn(None).clone()
+                            part = RowPartition([n_users, n_items, n_props], group=group, final_types=[0, 1, 2],
+                                                exchange="peer").attach(seq)
+                            got = model.gnn(None)
+                            torch.cuda.synchronize()
+                            check(torch.equal(got, full), "64-wide GAT tf32x3%s" % (" blocked" if blocking else ""))
+                            part.close()
+                            seq.partition = None
                 finally:
                     ops.GCN_TRANSFORM = saved
                 say("partition parity: 128-wide GCN (fused / replicated / tensor-core transform)%s done" % (" blocked" if blocking else ""))

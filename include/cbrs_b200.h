@@ -231,6 +231,14 @@ int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const fl
                       int32_t n, int act, void *out, int64_t ldo, int out_dtype, void *const *out_peers_host,
                       int n_peers, void *stream);
 
+/* The GAT transform on the same kernel (spektral GATConv built at src/models/gnn.py:321-328: z = x W, then the two
+ * attention logits per node): out = X W (fp32) plus p[m] = out[m,:] . a_self and q[m] = out[m,:] . a_neigh, i.e.
+ * cbrs_dense with CBRS_ROWOP_ATTN on the tensor cores.  q_peers_host as in cbrs_dense_bcast.                          */
+int cbrs_dense_tf32x3_attn(const float *x, int64_t ldx, const void *w_image, int64_t m, int32_t k, int32_t n,
+                           const float *a_self, const float *a_neigh, float *p_out, float *q_out, float *out,
+                           int64_t ldo, void *const *out_peers_host, void *const *q_peers_host, int n_peers,
+                           void *stream);
+
 /* General form of cbrs_dense: the output (and its peer copies) can be written as bf16 (out_dtype =
  * CBRS_DTYPE_BF16, round to nearest even, ldo in elements) so that the GCN transform Z = X W feeds the bf16
  * sparse kernel without a conversion pass; out_peers_host / q_peers_host / n_peers as in cbrs_dense_bcast.  */

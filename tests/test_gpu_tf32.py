@@ -116,3 +116,35 @@ def test_tf32x3_bf16_output_is_the_rounded_fp32_output(dev):
     ops.dense_tf32x3(xd, wd, bd, "relu", out=buf[:, 128:])
     assert torch.equal(buf[:, 128:], ops.dense_tf32x3(xd, wd, bd, "relu").to(torch.bfloat16)) and (buf[:, :128] == 0).all()
     assert ops.tf32x3_chosen(1 << 20, 128, 128, xd, buf[:, 128:]) and not ops.tf32x3_chosen(1 << 20, 128, 128, xd, buf[:, 8:136])
+
+
+def test_gat_transform_on_the_tensor_cores(dev, monkeypatch):
+    """z = x W with the two attention logits per row (cbrs_dense_tf32x3_attn) against float64, and a whole GAT layer
+    with it against the oracle"""
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
+    from oracle import layers as ol
+    x, w, b, xd, wd, bd = _case(2000, 64, 32, 21, dev)
+    rng = np.random.RandomState(2)
+    a_s, a_n = rng.standard_normal(32).astype(np.float32), rng.standard_normal(32).astype(np.float32)
+    monkeypatch.setattr(ops, "GCN_TRANSFORM", "tf32x3")
+    z, p, q = ops.gat_transform(xd, wd, torch.from_numpy(a_s).to(dev), torch.from_numpy(a_n).to(dev), 2000)
+    z64 = x.astype(np.float64) @ w.astype(np.float64)
+    assert_close(z.cpu().numpy(), z64.astype(np.float32), rtol=1e-5, what="z")
+    assert_close(p.cpu().numpy(), (z64 @ a_s).astype(np.float32), rtol=1e-5, what="p = z . a_self")
+    assert_close(q.cpu().numpy(), (z64 @ a_n).astype(np.float32), rtol=1e-5, what="q = z . a_neigh")
+    zf, pf, qf = ops.dense(xd, wd, rowop=2, a_self=torch.from_numpy(a_s).to(dev), a_neigh=torch.from_numpy(a_n).to(dev))
+    assert float((p - pf).abs().max()) <= 5e-6 * float(pf.abs().max())
+    # row slices give the same bits (row partition)
+    z2, p2, q2 = ops.gat_transform(xd[100:777], wd, torch.from_numpy(a_s).to(dev), torch.from_numpy(a_n).to(dev), 2000)
+    assert torch.equal(z2, z[100:777]) and torch.equal(p2, p[100:777]) and torch.equal(q2, q[100:777])
+    adj = random_bipartite(300, 80, 6000, seed=8)
+    n = adj.shape[0]
+    xx = rng.standard_normal((n, 64)).astype(np.float32)
+    g = DeviceGraph.from_scipy(adj, dev)
+    zz, pp, qq = ops.gat_transform(torch.from_numpy(xx).to(dev), wd, torch.from_numpy(a_s).to(dev), torch.from_numpy(a_n).to(dev), n)
+    out = torch.empty(n, 32, device=dev)
+    ops.gat(g.raw, zz, pp, qq, out, bias=bd, relu=True)
+    ptr, idx, _ = og.reorder_raw(adj)
+    want = ol.gat_conv(xx, ptr, idx, w, a_s, a_n, b, "relu")
+    assert_close(out.cpu().numpy(), want, rtol=1e-5, what="GAT layer, tensor-core transform")

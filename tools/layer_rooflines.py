@@ -85,6 +85,13 @@ def main():
     # GCN transform
     ms = timeit(lambda: ops.dense(x, w, out=out2))
     report("GCN transform X W (dense, fp32 FFMA)", ms, 0, n * 2 * d * s, {"tflops": 2 * n * d * d / (ms * 1e-3) / 1e12})
+    ms = timeit(lambda: ops.dense_tf32x3(x, w, out=out2))
+    report("GCN transform X W (tcgen05, 3xTF32, TMA: the kernel the layers use at this scale)", ms, 0, n * 2 * d * s,
+           {"tflops_fp32_equivalent": 2 * n * d * d / (ms * 1e-3) / 1e12})
+    ms = timeit(lambda: ops.gat_transform(x, w, a_s, a_n, n, out=out2))
+    report("GAT transform X W + attention logits (tcgen05, 3xTF32)", ms, 0, n * 2 * d * s + 8 * n)
+    ms = timeit(lambda: ops.dense(x, w, rowop=L.ROWOP_ATTN, a_self=a_s, a_neigh=a_n, out=out2))
+    report("GAT transform X W + attention logits (dense, fp32 FFMA)", ms, 0, n * 2 * d * s + 8 * n)
     # GAT: transform + logits, then fused edge softmax + aggregate: nnz*(4+4+H*s) + N*(H*s+16)
     z, p, q = ops.dense(x, w, rowop=L.ROWOP_ATTN, a_self=a_s, a_neigh=a_n)
     ms = timeit(lambda: ops.gat(raw, z, p, q, out, bias=bias, relu=True))
