@@ -240,7 +240,8 @@ def small_configs(dev):
         kw.update(extra)
         model = cls(a, **kw)
         if cls is hybrid.HybridBertGCN:
-            model.set_content_table(bert)
+            # the bf16 case keeps the static content table as bf16: its towers are fed by TMA (cbrs_dense_tc_bf16)
+            model.set_content_table(bert, dtype="bf16" if precision == "bf16" else "fp32")
             model.set_scorer_precision(precision)
         model((u, i))
         before = ops.LAUNCHES

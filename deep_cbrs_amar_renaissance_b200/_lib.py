@@ -53,6 +53,10 @@ _SIGS = {
     "cbrs_dense_tc_image_bytes": (c_size_t, [c_int32, c_int32]),
     "cbrs_dense_tc_prepare": (c_int, [P, c_int32, c_int32, P, P]),
     "cbrs_dense_tc": (c_int, [P, c_int64, P, c_int32, P, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int, P, c_int64, P]),
+    "cbrs_convert_f32_bf16": (c_int, [P, c_int64, c_int64, c_int32, P, c_int64, P]),
+    "cbrs_dense_tc_bf16_eligible": (c_int, [c_int32, c_int32, c_int32]),
+    "cbrs_dense_tc_bf16": (c_int, [P, c_int64, c_int64, P, c_int32, P, c_int64, c_int64, P, c_int32, P, P, c_int64, c_int32, c_int,
+                                   P, c_int64, c_int, P]),
     "cbrs_score_hybrid_topk_bf16_workspace_bytes": (c_size_t, []),
     "cbrs_score_hybrid_topk_bf16": (c_int, [P, P, P, P, c_int64, c_int32, c_int32, P, P, P, P, P, P, P, P, P, P, c_int32, P, P, P,
                                             c_size_t, P]),

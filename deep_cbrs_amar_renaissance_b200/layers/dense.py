@@ -35,6 +35,15 @@ class Dense(Layer):
         x2, i2 = (sources[1] if len(sources) > 1 else (None, None))
         f1, f2 = x1.shape[1], (x2.shape[1] if x2 is not None else 0)
         self.build_for(f1 + f2)
+        if x1.dtype == torch.bfloat16 or (x2 is not None and x2.dtype == torch.bfloat16):
+            # bf16-STORED sources (a content table kept as bf16, set_content_table(dtype="bf16")): TMA-fed tensor-core
+            # kernel; there is no fp32 kernel that reads bf16 rows, so the layer must be in bf16 precision
+            if self.precision != "bf16" or not ops.dense_tc_bf16_eligible(f1, f2, self.units) or \
+                    (x2 is not None and x2.dtype != x1.dtype):
+                raise ValueError("a source stored as bf16 needs set_scorer_precision('bf16'), source widths that are "
+                                 "multiples of 64 and at most 256 units (got {} + {} -> {}, precision {})".format(
+                                     f1, f2, self.units, self.precision))
+            return ops.dense_tc_bf16(x1, self.kernel, self.bias, self.activation, x2=x2, idx1=i1, idx2=i2)
         if self.precision == "bf16" and ops.dense_tc_eligible(f1, f2, self.units) and _aligned(x1) and _aligned(x2):
             return ops.dense_tc(x1, self.kernel, self.bias, self.activation, x2=x2, idx1=i1, idx2=i2)
         return ops.dense(x1, self.kernel, self.bias, self.activation, x2=x2, idx1=i1, idx2=i2)

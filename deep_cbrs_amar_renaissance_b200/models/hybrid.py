@@ -113,9 +113,17 @@ class HybridBertGNN(Model, abc.ABC):
         self.rs.build_for(self.gnn.out_dim, content_dim)
         return self
 
-    def set_content_table(self, table):
-        """Upload the [N, 768] content embeddings once (rows ordered like node ids)."""
-        self.content_table = _rows(table).contiguous()
+    def set_content_table(self, table, dtype="fp32"):
+        """Upload the [N, 768] content embeddings once (rows ordered like node ids).  dtype='bf16' keeps the table
+        rounded to bf16 (round to nearest even - what the tensor-core scorer does to every row it reads anyway) and
+        feeds the towers by TMA (cbrs_dense_tc_bf16); needs set_scorer_precision('bf16')."""
+        if dtype not in ("fp32", "bf16"):
+            raise ValueError("dtype must be 'fp32' or 'bf16'")
+        table = _rows(table).contiguous()
+        if dtype == "bf16":
+            from .. import ops
+            table = ops.to_bf16(table)
+        self.content_table = table
 
     def propagate(self):
         if self.cache_propagation and self._cached is not None:

@@ -422,6 +422,66 @@ def dense_tc(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, out=None, i
     return out
 
 
+def to_bf16(x, out=None):
+    """row-major fp32 matrix -> bf16 copy, round to nearest even (cbrs_convert_f32_bf16): how a static table (the
+    content embeddings) is stored once for cbrs_dense_tc_bf16"""
+    lib = L.load()
+    x, ldx = _rowmajor(x)
+    m, k = x.shape
+    if k % 8 != 0:
+        raise L.CbrsError("to_bf16: width must be a multiple of 8 (16-byte bf16 rows), got {}".format(k))
+    if out is None:
+        out = torch.empty(m, k, dtype=torch.bfloat16, device=x.device)
+    if out.dtype != torch.bfloat16 or out.stride(1) != 1 or tuple(out.shape) != (m, k):
+        raise L.CbrsError("to_bf16: out must be a row-major bf16 [{}, {}]".format(m, k))
+    L.check(lib.cbrs_convert_f32_bf16(_ptr(x), ldx, m, k, _ptr(out, torch.bfloat16), out.stride(0) if m > 1 else k, _stream()),
+            "cbrs_convert_f32_bf16")
+    _count(1)
+    return out
+
+
+def dense_tc_bf16_eligible(f1, f2, n):
+    """shapes cbrs_dense_tc_bf16 takes: source widths multiples of 64 (one 128-byte swizzle row of bf16), n <= 256"""
+    return f1 > 0 and f1 % 64 == 0 and f2 % 64 == 0 and 0 < n <= 256
+
+
+def dense_tc_bf16(x1, w, b=None, act=None, x2=None, idx1=None, idx2=None, out=None, image=None, out_dtype=torch.float32):
+    """cbrs_dense_tc over bf16-STORED sources, fed by TMA (tile::gather4 for indexed rows):
+    act([x1[idx1] || x2[idx2]] @ bf16(w) + b), fp32 accumulate; the output is fp32 or bf16 (`out_dtype` / `out`)."""
+    lib = L.load()
+    if x1.dtype != torch.bfloat16 or (x2 is not None and x2.dtype != torch.bfloat16):
+        raise L.CbrsError("dense_tc_bf16: sources must be stored as bf16 (ops.to_bf16)")
+
+    def _bf16_rows(x):
+        if x.dim() != 2 or x.stride(1) != 1 or not x.is_cuda:
+            raise L.CbrsError("dense_tc_bf16: sources must be row-major CUDA matrices")
+        return x, (x.stride(0) if x.shape[0] > 1 else x.shape[1])
+
+    x1, ld1 = _bf16_rows(x1)
+    f1, f2, ld2, rows2 = x1.shape[1], 0, 0, 0
+    if x2 is not None:
+        x2, ld2 = _bf16_rows(x2)
+        f2, rows2 = x2.shape[1], x2.shape[0]
+    m = idx1.numel() if idx1 is not None else x1.shape[0]
+    if w.dim() != 2 or w.shape[0] != f1 + f2 or not w.is_contiguous():
+        raise L.CbrsError("dense_tc_bf16: kernel must be contiguous [{}, n], got {}".format(f1 + f2, tuple(w.shape)))
+    n = w.shape[1]
+    if image is None:
+        image = dense_tc_image(w)
+    if out is None:
+        out = torch.empty(m, n, dtype=out_dtype, device=x1.device)
+    if out.dtype not in (torch.float32, torch.bfloat16) or out.dim() != 2 or out.stride(1) != 1 or tuple(out.shape) != (m, n):
+        raise L.CbrsError("dense_tc_bf16: out must be a row-major fp32 or bf16 [{}, {}]".format(m, n))
+    ldo = out.stride(0) if m > 1 else n
+    code = act if isinstance(act, int) else L.ACTS[act]
+    L.check(lib.cbrs_dense_tc_bf16(_ptr(x1, torch.bfloat16), ld1, x1.shape[0], _ptr(idx1, torch.int64), f1,
+                                   _ptr(x2, torch.bfloat16), ld2, rows2, _ptr(idx2, torch.int64), f2, _ptr(image),
+                                   _ptr(b, torch.float32), m, n, code, _ptr(out, out.dtype), ldo,
+                                   L.DTYPE_BF16 if out.dtype == torch.bfloat16 else L.DTYPE_F32, _stream()), "cbrs_dense_tc_bf16")
+    _count(1)
+    return out
+
+
 def dense_tc_image(w):
     """bf16 tensor-core operand image of a Keras kernel [k, n] (cbrs_dense_tc_prepare)"""
     lib = L.load()

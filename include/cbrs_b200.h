@@ -188,6 +188,22 @@ int cbrs_dense_tc(const float *x1, int64_t ld1, const int64_t *idx1, int32_t f1,
                   const int64_t *idx2, int32_t f2, const void *w_image, const float *b, int64_t m, int32_t n,
                   int act, float *out, int64_t ldo, void *stream);
 
+/* The same layer over bf16-STORED sources, fed by TMA (the static content table of the hybrid models:
+ * src/models/hybrid.py:136-140 gathers its rows by the batch's ids, hybrid.py:74-77 runs the towers on them).
+ * cbrs_convert_f32_bf16 rounds a row-major fp32 matrix to bf16 once (round to nearest even: the rounding cbrs_dense_tc
+ * applies to every row on every call, so both kernels multiply identical operands); k, ldx, ldo multiples of 4.
+ * cbrs_dense_tc_bf16: X1 [rows1, ld1] and X2 [rows2, ld2] hold bf16 (ld in elements, % 8 == 0, 16-byte aligned bases);
+ * rows of an indexed source arrive by cp.async.bulk.tensor tile::gather4, consecutive rows as one tiled box, W as
+ * the image of cbrs_dense_tc_prepare; out_dtype = CBRS_DTYPE_F32 (float *out) or CBRS_DTYPE_BF16 (ldo in elements),
+ * so a tower's layers chain without an fp32 round trip.  Requirements: f1, f2 multiples of 64, n <= 256, every index
+ * in [0, rows), m <= rows when a source has no index.                                                               */
+int cbrs_convert_f32_bf16(const float *x, int64_t ldx, int64_t m, int32_t k, void *out, int64_t ldo, void *stream);
+int cbrs_dense_tc_bf16_eligible(int32_t f1, int32_t f2, int32_t n);
+int cbrs_dense_tc_bf16(const void *x1, int64_t ld1, int64_t rows1, const int64_t *idx1, int32_t f1, const void *x2,
+                       int64_t ld2, int64_t rows2, const int64_t *idx2, int32_t f2, const void *w_image,
+                       const float *b, int64_t m, int32_t n, int act, void *out, int64_t ldo, int out_dtype,
+                       void *stream);
+
 /* Full-catalog scoring of the FEATURE-BASED hybrid scorer with a fused per-user top-k, chained on the tensor cores
  * (src/models/hybrid.py:72-89 for every (user, item) pair; the form all of econfigs/hybrid-gnn*.yaml use).  The caller
  * hoists what depends on one entity: the four towers and the first layer of dense3a / dense3b, split into a user half

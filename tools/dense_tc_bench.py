@@ -54,10 +54,24 @@ def run(rows=1 << 20, shapes=((768, 256), (256, 64)), gather=False):
         ms_fp = time_ms(lambda: ops.dense(x, w, b, "relu", idx1=idx, out=y), iters=3, warmup=1)
         flop = 2.0 * rows * k * n
         byt = rows * (k + n) * 4.0 + image.numel()
+        tma = None
+        if ops.dense_tc_bf16_eligible(k, 0, n):
+            # the same layer over the table stored as bf16 once, rows fed by TMA (cbrs_dense_tc_bf16): fp32 and bf16 output
+            xb = ops.to_bf16(x)
+            yb = torch.empty(rows, n, device=dev, dtype=torch.bfloat16)
+            ms_f = time_ms(lambda: ops.dense_tc_bf16(xb, w, b, "relu", idx1=idx, out=y, image=image))
+            ms_b = time_ms(lambda: ops.dense_tc_bf16(xb, w, b, "relu", idx1=idx, out=yb, image=image))
+            byt_f, byt_b = rows * (k * 2.0 + n * 4.0) + image.numel(), rows * (k + n) * 2.0 + image.numel()
+            tma = {"out_f32": {"ms": ms_f, "tflops": flop / ms_f / 1e9, "frac_of_bf16_peak": flop / ms_f / 1e9 / tflops,
+                               "hbm_gbps": byt_f / ms_f / 1e6, "frac_of_hbm_peak": byt_f / ms_f / 1e6 / hbm},
+                   "out_bf16": {"ms": ms_b, "tflops": flop / ms_b / 1e9, "frac_of_bf16_peak": flop / ms_b / 1e9 / tflops,
+                                "hbm_gbps": byt_b / ms_b / 1e6, "frac_of_hbm_peak": byt_b / ms_b / 1e6 / hbm},
+                   "bytes": "rows as bf16 (k * 2 B) read once + output once + the image once"}
+            del xb, yb
         out.append({"op": "dense %d->%d relu" % (k, n), "rows": rows, "gathered": bool(gather),
                     "tc_bf16": {"ms": ms_tc, "tflops": flop / ms_tc / 1e9, "frac_of_bf16_peak": flop / ms_tc / 1e9 / tflops,
                                 "hbm_gbps": byt / ms_tc / 1e6, "frac_of_hbm_peak": byt / ms_tc / 1e6 / hbm},
-                    "fp32_ffma": {"ms": ms_fp, "tflops": flop / ms_fp / 1e9},
+                    "fp32_ffma": {"ms": ms_fp, "tflops": flop / ms_fp / 1e9}, "tc_bf16_table_tma": tma,
                     "speedup": ms_fp / ms_tc, "peaks": {"hbm_gbps": hbm, "bf16_tflops": tflops}})
         del x, y
     return out
