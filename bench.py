@@ -188,6 +188,33 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- configs 1-4 (MovieLens-1M shape)
+def nvlink_counters(local):
+    """Cumulative NVLink payload bytes (tx, rx) of this rank's GPU summed over its links, read from NVML field values
+    (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / RX, KiB, scope = all links); None when NVML does not expose them."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(local).uuid)).encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local)
+        vals = pynvml.nvmlDeviceGetFieldValues(handle, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                        (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            kib = {pynvml.NVML_VALUE_TYPE_UNSIGNED_LONG_LONG: v.value.ullVal, pynvml.NVML_VALUE_TYPE_UNSIGNED_LONG: v.value.ulVal,
+                   pynvml.NVML_VALUE_TYPE_UNSIGNED_INT: v.value.uiVal}.get(v.valueType)
+            if kib is None:
+                return None
+            out.append(int(kib) * 1024)
+        return tuple(out)
+    except Exception:
+        return None
+
+
 def small_configs(dev):
     """BASELINE configs 1-4 on one GPU: the per-batch model call (batch 2048, econfigs grid2 shapes) eager and as a
     CUDA-graph replay, and full-catalog top-10 for every user with HOST ids in and HOST (ids, scores) out.  These
@@ -382,7 +409,9 @@ def run_b200(args):
     barrier()
     ops.PROFILE_ON = True
     ops.LAUNCHES = 0
+    nvl0 = nvlink_counters(local) if world > 1 else None
     ms, t0, t1 = timed(lambda: model((u_dev, i_dev)), args.steps, 0)
+    nvl1 = nvlink_counters(local) if world > 1 else None
     launches = ops.LAUNCHES
     ops.PROFILE_ON = False
     clocks = sampler.stop(t0, t1) if sampler else None
@@ -404,6 +433,24 @@ def run_b200(args):
         rank_sparse = {"ms_per_step": per, "min": min(per), "max": max(per), "max_over_min": max(per) / max(min(per), 1e-9),
                        "local_edges": part.local_edges("norm"),
                        "cuts": "equal row counts" if args.row_count_cuts else ("equal edge counts per node type" if args.edge_count_cuts else "equal edge cost per node type (edges of rows that stream from HBM weigh 2.4)")}
+
+    # NVLink payload bytes this rank's GPU sent / received during the timed steps (NVML counters), next to what the
+    # exchange must move: every layer's output rows reach the other G-1 ranks ((G-1)/G * N * H * 4 bytes received per
+    # layer and rank); sent = own rows once when the stores go through the NVSwitch multicast mapping, G-1 times otherwise
+    nvlink = None
+    if world > 1:
+        mine = torch.tensor([(nvl1[0] - nvl0[0]) / args.steps, (nvl1[1] - nvl0[1]) / args.steps] if nvl0 and nvl1 else [-1.0, -1.0],
+                            device=dev, dtype=torch.float64)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        if all(float(t[0]) >= 0 for t in every):
+            own_rows = sum(hi - lo for lo, hi in part.ranges[rank])
+            rows_out = [(n if l < LAYERS - 1 else n_items) for l in range(LAYERS)]   # last layer: items only (scoring is user-sharded)
+            nvlink = {"tx_bytes_per_step": [float(t[0]) for t in every], "rx_bytes_per_step": [float(t[1]) for t in every],
+                      "expected_rx_bytes_per_step_per_rank": sum(r * (world - 1) / world for r in rows_out) * DIM * 4,
+                      "expected_tx_multicast": sum(r / world for r in rows_out) * DIM * 4,
+                      "expected_tx_unicast": sum(r * (world - 1) / world for r in rows_out) * DIM * 4,
+                      "rank0_own_rows": own_rows, "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX, all links, around the timed steps"}
 
     # ---- end to end through the public model call with HOST buffers (e2e) --------------------
     def e2e_step():
@@ -462,11 +509,15 @@ def run_b200(args):
     model.propagate()
     cu = min(args.catalog_users, u_hi - u_lo)
     users = torch.arange(u_lo, u_lo + cu, device=dev)
-    cat_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users), 1, 1)
-    pairs_per_s = world * cu * n_items / (cat_ms * 1e-3)
-    # bf16 tensor-core scorer (tcgen05): more users per launch so the grid fills the chip
+    # fp32 FFMA kernel (round 1's parity path), for reference next to the headline
+    ffma_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users, precision="fp32-ffma"), 1, 1)
+    pairs_ffma = world * cu * n_items / (ffma_ms * 1e-3)
+    # tensor-core scorers (tcgen05): more users per launch so the grid fills the chip.  fp32 = the 3xTF32 kernel
+    # (fp32-accurate, the default of recommend_top_k: same parity tests as the FFMA kernel); bf16 = bf16 operands
     cu_tc = min(args.catalog_users * 4, u_hi - u_lo)
     users_tc = torch.arange(u_lo, u_lo + cu_tc, device=dev)
+    cat_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users_tc), 1, 1)
+    pairs_per_s = world * cu_tc * n_items / (cat_ms * 1e-3)
     tc_ms, _, _ = timed(lambda: model.recommend_top_k(n_users, n_items, 10, users=users_tc, precision="bf16"), 1, 1)
     pairs_tc = world * cu_tc * n_items / (tc_ms * 1e-3)
     model.cache_propagation = False
@@ -489,9 +540,13 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": 2 * PAIR_BATCH * 8,
                 "d2h_bytes_per_step": PAIR_BATCH * 4, "ms_per_step": ms_e2e / args.steps},
         "roofline": roofline, "partition_parity": parity, "rank_sparse_ms": rank_sparse,
-        "exchange": exchange_label if world > 1 else None,
-        "pairs": {"value": pairs_per_s, "unit": "pairs/s", "what": "full-catalog BasicRS scoring + top-10, %d users x %d items per rank" % (cu, n_items),
-                  "ms": cat_ms,
+        "exchange": exchange_label if world > 1 else None, "nvlink": nvlink,
+        "pairs": {"value": pairs_per_s, "unit": "pairs/s",
+                  "what": "full-catalog BasicRS scoring + top-10, %d users x %d items per rank, fp32-accurate 3xTF32 tcgen05 "
+                          "kernel (cbrs_score_catalog_topk_tf32x3; 1e-5 parity vs the oracle in tests/test_gpu_kernels.py)" % (cu_tc, n_items),
+                  "ms": cat_ms, "tensor_flops_per_pair": 3 * 2 * CLF_UNITS[0] * CLF_UNITS[1],
+                  "fp32_ffma": {"value": pairs_ffma, "unit": "pairs/s", "users_per_rank": cu, "ms": ffma_ms,
+                                "what": "cbrs_score_catalog_topk (CUDA-core FFMA kernel, round 1's parity path)"},
                   "bf16_tcgen05": {"value": pairs_tc, "unit": "pairs/s", "users_per_rank": cu_tc, "ms": tc_ms,
                                    "tensor_flops_per_pair": 2 * CLF_UNITS[0] * CLF_UNITS[1],
                                    "frac_of_bf16_peak": pairs_tc / world * 2 * CLF_UNITS[0] * CLF_UNITS[1] / 1e12 / (peaks.get("bf16_tflops_sustained") or 1398.0)}},

@@ -76,6 +76,10 @@ _SIGS = {
     "cbrs_topk_pairs": (c_int, [P, P, c_int64, c_int64, P, P, P, c_size_t, P]),
     "cbrs_score_catalog_topk": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, c_int32, P, P, c_int32,
                                         P, P, P]),
+    "cbrs_score_catalog_topk_tf32x3_eligible": (c_int, [c_int32, c_int32]),
+    "cbrs_score_catalog_topk_tf32x3_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "cbrs_score_catalog_topk_tf32x3": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, c_int32, P, P, c_int32,
+                                               P, P, P, c_size_t, P]),
     "cbrs_score_catalog_topk_bf16_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "cbrs_score_catalog_topk_bf16": (c_int, [P, c_int64, P, c_int64, c_int64, c_int32, c_int32, P, P, c_int32, P, P,
                                              c_int32, P, P, P, c_size_t, P]),

@@ -357,11 +357,13 @@ static tm_encode_fn tm_encoder() {
     }
     return fn;
 }
-// L2 promotion of the loads: gathered rows are read in 128-byte slices, one K block at a time; promoting each miss to 256 B
-// brings the next K block's slice of the same row along (CBRS_TMA_L2_PROMOTION=128|256 overrides, for measurements)
+// L2 promotion of the loads: a row is read in 128-byte slices, one K block at a time; promoting each miss to 256 B brings the
+// next K block's slice of the same row along (measured, 768 -> 256 at 2^20 rows: 0.543 vs 0.558 ms consecutive, 0.609 vs
+// 0.623 ms gathered, profiles/r02_dense_tc_tma_bench_l2p{128,256}.jsonl).  CBRS_TMA_L2_PROMOTION=64|128|256 overrides.
 static CUtensorMapL2promotion tm_l2_promotion(bool gather) {
     static const int forced = getenv("CBRS_TMA_L2_PROMOTION") ? atoi(getenv("CBRS_TMA_L2_PROMOTION")) : 0;
-    const int v = forced ? forced : (gather ? 256 : 128);
+    (void)gather;
+    const int v = forced ? forced : 256;
     return v == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
 }
 // rows of `f` bf16 out of a [rows, ld] table; box = 64 columns x (1 row for tile::gather4 | 64 rows tiled)

@@ -562,8 +562,28 @@ def topk_pairs(users, scores, n_users, k):
 
 def score_catalog_topk(P, Q, w2, b2, w3, b3, k, precision="fp32"):
     """Fused BasicRS catalog scorer: P [U,c1] (bias folded in), Q [I,c1] -> (ids int32 [U,k], scores [U,k]).
-    precision 'fp32' = FFMA kernel (1e-5 parity); 'bf16' = tcgen05 tensor-core kernel."""
+    precision 'fp32' = fp32-accurate (1e-5 parity): the 3xTF32 tensor-core kernel for the shapes it takes (c1 in {32, 64},
+    c2 <= 64: the reference's grids), the FFMA kernel otherwise; 'fp32-ffma' forces the FFMA kernel (CBRS_SCORE_FP32=ffma
+    does the same for a whole process); 'bf16' = bf16 operands on the tensor cores."""
     lib = L.load()
+    if precision == "fp32" and os.environ.get("CBRS_SCORE_FP32", "") != "ffma" and \
+            lib.cbrs_score_catalog_topk_tf32x3_eligible(P.shape[1], w2.shape[1]):
+        P, ldp = _rowmajor(P)
+        Q, ldq = _rowmajor(Q)
+        n_users, c1 = P.shape
+        c2 = w2.shape[1]
+        ids = torch.empty(n_users, k, dtype=torch.int32, device=P.device)
+        vals = torch.empty(n_users, k, dtype=torch.float32, device=P.device)
+        ws = _ws(lib.cbrs_score_catalog_topk_tf32x3_workspace_bytes(c1, c2), P.device)
+        L.check(lib.cbrs_score_catalog_topk_tf32x3(_ptr(P), ldp, _ptr(Q), ldq, n_users, Q.shape[0], c1,
+                                                   _ptr(w2, torch.float32), _ptr(b2, torch.float32), c2,
+                                                   _ptr(w3, torch.float32), _ptr(b3, torch.float32), k, _ptr(ids),
+                                                   _ptr(vals), _ptr(ws), ws.numel(), _stream()),
+                "cbrs_score_catalog_topk_tf32x3")
+        _count(2)
+        return ids, vals
+    if precision not in ("fp32", "fp32-ffma", "bf16"):
+        raise L.CbrsError("score_catalog_topk: precision must be 'fp32', 'fp32-ffma' or 'bf16'")
     if precision == "bf16":
         P, ldp = _rowmajor(P)
         Q, ldq = _rowmajor(Q)

@@ -303,6 +303,18 @@ int cbrs_score_catalog_topk(const float *P, int64_t ldp, const float *Q, int64_t
                             const float *w3, const float *b3, int32_t k, int32_t *ids_out,
                             float *scores_out, void *stream);
 
+/* The same scorer with the 64 x 64 product on the tensor cores at fp32 accuracy (3xTF32: h = relu(P[u]+Q[i]) and W2 are
+ * split into a tf32 part and an exact remainder, three kind::tf32 MMAs per K step accumulate in fp32; the A operand is
+ * written by its threads straight into tensor memory).  Same contract, outputs and tie rule as cbrs_score_catalog_topk;
+ * scores agree with it to ~1e-6 (1e-5 stated in the tests).  Shapes: c1 in {32, 64}, c2 <= 64 (the reference's grids:
+ * clf_units [64, 64]); anything else: cbrs_score_catalog_topk.  Workspace: the operand images of W2.            */
+int cbrs_score_catalog_topk_tf32x3_eligible(int32_t c1, int32_t c2);
+size_t cbrs_score_catalog_topk_tf32x3_workspace_bytes(int32_t c1, int32_t c2);
+int cbrs_score_catalog_topk_tf32x3(const float *P, int64_t ldp, const float *Q, int64_t ldq, int64_t n_users,
+                                   int32_t n_items, int32_t c1, const float *w2, const float *b2, int32_t c2,
+                                   const float *w3, const float *b3, int32_t k, int32_t *ids_out,
+                                   float *scores_out, void *workspace, size_t workspace_bytes, void *stream);
+
 /* bf16 tensor-core variant (tcgen05.mma, TMEM accumulator): same contract and arguments; the
  * per-pair activations relu(P[u]+Q[i]) and W2 are rounded to bf16, accumulation is fp32, so
  * scores differ from the fp32 kernel by O(1e-3) (tolerance stated in tests).  c1 % 8 == 0,

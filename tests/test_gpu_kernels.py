@@ -335,9 +335,17 @@ def test_top_k_predictions_frame(dev):
 
 @pytest.mark.parametrize("n_users,n_items,c1,c2,k", [(1, 1, 4, 1, 1), (37, 3706, 64, 64, 10), (50, 1000, 48, 48, 5),
                                                       (16, 333, 64, 128, 128), (70, 2049, 128, 96, 10),
-                                                      (5, 7, 64, 64, 10), (33, 40000, 64, 64, 10)])
-def test_fused_catalog_scorer_matches_oracle(dev, n_users, n_items, c1, c2, k):
-    from deep_cbrs_amar_renaissance_b200 import ops
+                                                      (5, 7, 64, 64, 10), (33, 40000, 64, 64, 10),
+                                                      (45, 1500, 32, 64, 10), (21, 777, 64, 48, 7), (18, 600, 32, 24, 5)])
+@pytest.mark.parametrize("precision", ["fp32", "fp32-ffma"])
+def test_fused_catalog_scorer_matches_oracle(dev, n_users, n_items, c1, c2, k, precision):
+    """'fp32' takes the 3xTF32 tensor-core kernel for c1 in {32, 64}, c2 <= 64 (fp32-accurate: same oracle, same
+    tolerance, same tie rule) and the FFMA kernel otherwise; 'fp32-ffma' forces the FFMA kernel on every shape."""
+    from deep_cbrs_amar_renaissance_b200 import _lib, ops
+    if precision == "fp32":
+        launches = ops.LAUNCHES
+        tensor = bool(_lib.load().cbrs_score_catalog_topk_tf32x3_eligible(c1, c2))
+        assert tensor == (c1 in (32, 64) and c2 <= 64)
     from tests.helpers import assert_topk_equivalent
     rng = np.random.RandomState(n_items + c2)
     P = rng.standard_normal((n_users, c1)).astype(np.float32)
@@ -346,7 +354,10 @@ def test_fused_catalog_scorer_matches_oracle(dev, n_users, n_items, c1, c2, k):
         Q[50:60] = Q[40:50]  # exact duplicates: exact score ties, lower index must win
     w2, b2 = glorot(rng, (c1, c2)), rng.standard_normal(c2).astype(np.float32) * 0.1
     w3, b3 = glorot(rng, (c2, 1)).reshape(-1), np.array([0.05], np.float32)
-    ids, vals = ops.score_catalog_topk(_t(P, dev), _t(Q, dev), _t(w2, dev), _t(b2, dev), _t(w3, dev), _t(b3, dev), k)
+    ids, vals = ops.score_catalog_topk(_t(P, dev), _t(Q, dev), _t(w2, dev), _t(b2, dev), _t(w3, dev), _t(b3, dev), k,
+                                       precision=precision)
+    if precision == "fp32":
+        assert ops.LAUNCHES - launches == (2 if tensor else 1)   # operand-image prep + scorer | the FFMA scorer
     h1 = np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1)
     h2 = np.maximum(h1 @ w2 + b2, 0)
     scores = ol.sigmoid(h2 @ w3 + b3).reshape(n_users, n_items)
