@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kDtThreads, 2) dense_tc_kernel(const __grid_co
             tc::mbar_wait(mma_done + buf, (uint32_t)(use - 1) & 1u);
             tc::tc_fence_after_sync();
         }
-        if (tid == 0) {   // block kb of the image (already in operand layout); lands while A is being built
+        if (warp == 0 && tc::elect_one()) {   // block kb of the image (already in operand layout); lands while A is being built
             dt_expect_tx(b_full + buf, (uint32_t)b_bytes);
             const unsigned char *src = p.w_image + (size_t)kb * b_bytes;
             unsigned char *dst = Bs + buf * b_bytes;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kDtThreads, 2) dense_tc_kernel(const __grid_co
         tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core
         tc::tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && tc::elect_one()) {   // elected: UTCHMMA issues once, not in a per-lane loop
             tc::mbar_wait(b_full + buf, (uint32_t)use & 1u);
             tc::tc_fence_after_sync();
 #pragma unroll

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kTmThreads, 1)
         }
     } else if (warp == kTmProducers) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        if (tc::elect_one()) {   // one lane, and ptxas knows it: UTCHMMA issues once, not in a per-lane loop
             const uint32_t idesc = tc::idesc_bf16_f32(128, p.n_pad);
             const uint32_t ring_addr = tc::smem_u32(ring);
             int64_t it = 0;

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kXThreads, 2) dense_tc_x_kernel(const __grid_c
             tc::mbar_wait(mma_done + buf, (uint32_t)(use - 1) & 1u);
             tc::tc_fence_after_sync();
         }
-        if (tid == 0) {
+        if (warp == 0 && tc::elect_one()) {
             dt_expect_tx(b_full + buf, (uint32_t)b_bytes);
             const unsigned char *src = p.w_image + (size_t)kb * b_bytes;
             unsigned char *dst = Bs + buf * b_bytes;
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kXThreads, 2) dense_tc_x_kernel(const __grid_c
         tc::fence_proxy_async_smem();
         tc::tc_fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && tc::elect_one()) {
             tc::mbar_wait(b_full + buf, (uint32_t)use & 1u);
             tc::tc_fence_after_sync();
 #pragma unroll

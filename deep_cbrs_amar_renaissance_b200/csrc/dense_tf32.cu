@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
 
     if (warp == 8) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
+        if (tc::elect_one()) {   // one lane, and ptxas knows it: TMA / MMA instructions issue once, not in a per-lane loop
             t3_expect_tx(w_full, 2u * (uint32_t)w_bytes);
             for (int off = 0; off < 2 * w_bytes; off += 16384) {
                 const int nb = (2 * w_bytes - off < 16384) ? 2 * w_bytes - off : 16384;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         }
     } else if (warp == 9) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        if (tc::elect_one()) {
             const uint32_t idesc = t3_idesc(kT3Rows, p.n);
             const uint32_t wh_addr = tc::smem_u32(Wh), wl_addr = tc::smem_u32(Wl), op_addr = tc::smem_u32(ops_s);
             tc::mbar_wait(w_full, 0);

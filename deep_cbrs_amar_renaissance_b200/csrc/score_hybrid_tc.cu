@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const Hy
         tc::fence_proxy_async_smem();   // my generic-proxy stores -> visible to the tensor core
         tc::tc_fence_before_sync();     // my previous tcgen05.ld -> ordered before the next MMA
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && tc::elect_one()) {   // elected: UTCHMMA issues once, not in a per-lane loop
             tc::tc_fence_after_sync();
             issue();
             tc::mma_commit(mbar);

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kTcThreads, QREG ? 4 : 3) score_tc_kernel(cons
             tc::tc_fence_before_sync();     // my previous tcgen05.ld -> ordered before the next MMA
             __syncthreads();
             // ---- MMA: one thread ---------------------------------------------------------------
-            if (tid == 0) {
+            if (warp == 0 && tc::elect_one()) {
                 tc::tc_fence_after_sync();
                 for (int s = 0; s < k_steps; ++s) {
                     const uint32_t koff = (uint32_t)(s & 3) * 32;  // 16 bf16 = 32 bytes inside the swizzle atom
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kTcThreads, 4) score_tc2_kernel(const __grid_c
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && tc::elect_one()) {   // elected: UTCHMMA issues once, not in a per-lane loop
         tc::tc_fence_after_sync();
         issue(0);
     }
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(kTcThreads, 4) score_tc2_kernel(const __grid_c
         tc::fence_proxy_async_smem();
         tc::tc_fence_before_sync();   // my tcgen05.ld of step-1 precede the MMA that will overwrite that TMEM buffer
         __syncthreads();
-        if (tid == 0 && nxt < n_steps) {
+        if (warp == 0 && nxt < n_steps && tc::elect_one()) {
             tc::tc_fence_after_sync();
             issue(nxt);
         }

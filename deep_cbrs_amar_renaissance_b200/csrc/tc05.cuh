@@ -71,6 +71,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// one lane of a fully converged warp; ptxas knows a region predicated on elect.sync has a single active lane, so
+// uniform-datapath instructions inside it (UTCHMMA, UTCBAR, UTMALDG) are issued once instead of in a per-lane loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- descriptors --------------------------------------------------------------------------
 // K-major operand tile in the canonical SWIZZLE_128B layout: rows of 128 bytes (64 bf16), groups of
 // 8 rows 1024 bytes apart (SBO), 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).
