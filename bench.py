@@ -443,7 +443,12 @@ def run_b200(args):
                             device=dev, dtype=torch.float64)
         every = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(every, mine)
-        if all(float(t[0]) >= 0 for t in every):
+        if not all(float(t[0]) >= 0 for t in every):
+            nvlink = {"unavailable": "NVML reports NVLINK_THROUGHPUT_DATA_TX/RX as NOT_SUPPORTED on this (virtualised) pool and "
+                                     "`nvidia-smi nvlink -gt d` prints N/A (profiles/r02_nvlink_counters_unavailable.txt)",
+                      "expected_rx_bytes_per_step_per_rank":
+                          sum((n if l < LAYERS - 1 else n_items) * (world - 1) / world for l in range(LAYERS)) * DIM * 4}
+        else:
             own_rows = sum(hi - lo for lo, hi in part.ranges[rank])
             rows_out = [(n if l < LAYERS - 1 else n_items) for l in range(LAYERS)]   # last layer: items only (scoring is user-sharded)
             nvlink = {"tx_bytes_per_step": [float(t[0]) for t in every], "rx_bytes_per_step": [float(t[1]) for t in every],
