@@ -14,19 +14,22 @@
 //
 // One persistent CTA per SM, 128 output rows per tile, warp-specialised:
 //   warp 8    TMA producer: cp.async.bulk.tensor.2d brings the tile's A operand one K atom (32 fp32 = one 128-byte
-//             swizzle row) at a time, 128 rows x 128 B, already in the canonical K-major SWIZZLE_128B layout
-//             (the tensor map carries the swizzle), into one of two landing slots;
-//   warps 0-3 split: read the landed atom into registers, hand the slot straight back to the producer (a slot is
-//             held for one HBM round trip only - v1 held it through the MMAs and spent 78 % of the split warps'
-//             time waiting for data, profiles/r02_ncu_tf32x3_v1.txt), write tf32(x) and x - tf32(x) into a
-//             double-buffered operand pair (the swizzle is a permutation of 16-byte chunks, so an elementwise pass
-//             needs no address math), fence.proxy.async, arrive;
-//   warp 9    one thread issues 4 x 3 tcgen05.mma (M=128, N=n, K=8) per atom and commits: the commit frees the
-//             operand pair; the last commit of a tile hands the accumulator to the epilogue.  Wh and Wl (operand
-//             images prepared once per call by cbrs_dense_tf32x3_prepare) stay in shared memory for the CTA's life;
-//   warps 4-7 epilogue: tcgen05.ld of the accumulator (double buffered in TMEM, so tile t+1's MMAs run under tile
-//             t's epilogue), bias, activation, 256-bit global stores (a full 32-byte sector per lane), optionally
-//             also into the peer-mapped copies of the other GPUs (multi-GPU all-gather from the producing kernel).
+//             swizzle row) at a time, 128 rows x 128 B (SWIZZLE_128B, so that a thread reading ITS row hits 8 different
+//             bank groups), into a ring of landing slots - as many 16 KB slots as fit beside the resident W images
+//             (6 at k = n = 128): the bytes in flight per SM are what keeps HBM busy;
+//   warps 0-3 split: thread t reads row t of the landed atom into registers, hands the slot straight back to the
+//             producer, and writes tf32(x) and x - tf32(x) into TENSOR MEMORY (tcgen05.st, lane = row, column = k;
+//             double buffered): the A operand never goes back to shared memory.  v2 of this kernel wrote the two operand
+//             tiles to shared memory; with them the kernel moved 160 KB through shared memory per atom (TMA write 16,
+//             split read 16 + write 32, MMA reads 12 x (4 + 4)) - 2.8 us per tile at 128 B/clk, as long as the tile's
+//             HBM time - now 80 KB;
+//   warp 9    one elected thread issues 4 x 3 tcgen05.mma (M=128, N=n, K=8, A from TMEM) per atom and commits: the commit
+//             frees the operand buffer; the last commit of a tile hands the accumulator to the epilogue.  Wh and Wl
+//             (operand images prepared once per call by cbrs_dense_tf32x3_prepare) stay in shared memory for the CTA's life;
+//   warps 4-7 epilogue: tcgen05.ld of the accumulator (double buffered in TMEM when 2 n + 128 <= 512 columns, so tile
+//             t+1's MMAs run under tile t's epilogue), bias, activation, 256-bit global stores (a full 32-byte sector per
+//             lane), optionally also into the peer-mapped copies of the other GPUs (multi-GPU all-gather from the
+//             producing kernel).
 // HBM traffic = X once + out once: the kernel's roofline is the copy bandwidth (1.7 ms at config 5).
 // Row results do not depend on the row's position in its tile (each accumulator element is an independent dot
 // product over K), so a row partition produces the same bits as the full run.
@@ -40,7 +43,7 @@ namespace cbrs {
 constexpr int kT3Rows = 128;     // output rows per tile = MMA M
 constexpr int kT3Atom = 32;      // fp32 elements per 128-byte swizzle row
 constexpr int kT3AtomBytes = kT3Rows * 128;   // one operand atom tile: 128 rows x 128 B
-constexpr int kT3Raw = 2;        // landing slots for the TMA loads (16 KB each)
+constexpr int kT3MaxRaw = 8;     // at most this many landing slots for the TMA loads (16 KB each)
 constexpr int kT3Threads = 320;  // 4 split warps, 4 epilogue warps, producer warp, MMA warp
 
 struct T3Params {
@@ -55,6 +58,8 @@ struct T3Params {
     int32_t n_peer;
     int32_t out_bf16;   // out / out_peer hold bf16 (round to nearest even), ldo in elements
     int64_t n_tiles;
+    int32_t n_raw;      // landing slots (2 .. kT3MaxRaw)
+    int32_t acc_bufs;   // accumulators in TMEM (2 when 2 n + 128 <= 512 columns, else 1)
     // GAT row-op (cbrs_dense_tf32x3_attn): p[m] = out[m,:] . a_self, q[m] = out[m,:] . a_neigh (GATConv's attention logits)
     const float *a_self, *a_neigh;
     float *p_out, *q_out;
@@ -105,6 +110,28 @@ __device__ __forceinline__ void t3_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A from tensor memory (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void t3_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread t of the warp writes lane (base_lane + t), columns c..c+31
+__device__ __forceinline__ void t3_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void t3_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 16 fp32 -> 16 bf16 = one 32-byte sector
 __device__ __forceinline__ void t3_store16_bf16(float *base, int64_t elem, const float (&o)[2][8]) {
     uint32_t w[8];
@@ -146,22 +173,23 @@ __global__ void __launch_bounds__(kT3Threads, 1)
     const int w_bytes = k_atoms * p.n * 128;           // one image (hi or lo)
     unsigned char *Wh = t3_smem;                       // [k_atoms][n][128 B]
     unsigned char *Wl = Wh + w_bytes;
-    unsigned char *ops_s = Wl + w_bytes;               // [2][hi 16 KB | lo 16 KB]: what the tensor core reads
-    unsigned char *raw_s = ops_s + 2 * 2 * kT3AtomBytes;   // [kT3Raw][16 KB]: where TMA lands the fp32 atoms
-    uint64_t *bars = reinterpret_cast<uint64_t *>(raw_s + kT3Raw * kT3AtomBytes);
-    uint64_t *raw_full = bars, *raw_empty = bars + kT3Raw, *op_ready = bars + 2 * kT3Raw, *op_empty = op_ready + 2;
+    unsigned char *raw_s = Wl + w_bytes;               // [n_raw][16 KB]: where TMA lands the fp32 atoms
+    uint64_t *bars = reinterpret_cast<uint64_t *>(raw_s + (size_t)p.n_raw * kT3AtomBytes);
+    uint64_t *raw_full = bars, *raw_empty = bars + kT3MaxRaw, *op_ready = bars + 2 * kT3MaxRaw, *op_empty = op_ready + 2;
     uint64_t *acc_full = op_empty + 2, *acc_empty = acc_full + 2, *w_full = acc_empty + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(w_full + 1);
     float *bias_s = reinterpret_cast<float *>(tmem_slot + 2);
+    // TMEM columns: accumulators [0, acc_bufs n), then the split operand, double buffered: (hi 32 | lo 32) x 2
+    const uint32_t col_a = (uint32_t)(p.acc_bufs * p.n);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < 2 * p.n) tmem_cols <<= 1;
+    while ((int)tmem_cols < p.acc_bufs * p.n + 128) tmem_cols <<= 1;
     if ((tc::smem_u32(t3_smem) & 1023u) != 0u) __trap();  // SWIZZLE_128B tiles need the declared alignment
 
     if (warp == 0) tc::tmem_alloc(tmem_slot, tmem_cols);
     if (tid == 32) {
-        for (int s = 0; s < kT3Raw; ++s) {
+        for (int s = 0; s < p.n_raw; ++s) {
             tc::mbar_init(raw_full + s, 1);
             tc::mbar_init(raw_empty + s, 128);
         }
@@ -200,8 +228,8 @@ __global__ void __launch_bounds__(kT3Threads, 1)
             for (int64_t lt = 0; lt < my_tiles; ++lt) {
                 const int64_t tile = blockIdx.x + lt * gridDim.x;
                 for (int a = 0; a < k_atoms; ++a, ++it) {
-                    const int s = (int)(it % kT3Raw);
-                    const int64_t use = it / kT3Raw;
+                    const int s = (int)(it % p.n_raw);
+                    const int64_t use = it / p.n_raw;
                     if (use > 0) tc::mbar_wait(raw_empty + s, (uint32_t)(use - 1) & 1u);
                     t3_expect_tx(raw_full + s, kT3AtomBytes);
                     t3_tma_load(raw_s + s * kT3AtomBytes, &map_x, a * kT3Atom, (int32_t)(tile * kT3Rows), raw_full + s);
@@ -212,12 +240,12 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         // ---------------- MMA issuer ----------------
         if (tc::elect_one()) {
             const uint32_t idesc = t3_idesc(kT3Rows, p.n);
-            const uint32_t wh_addr = tc::smem_u32(Wh), wl_addr = tc::smem_u32(Wl), op_addr = tc::smem_u32(ops_s);
+            const uint32_t wh_addr = tc::smem_u32(Wh), wl_addr = tc::smem_u32(Wl);
             tc::mbar_wait(w_full, 0);
             int64_t it = 0;
             for (int64_t lt = 0; lt < my_tiles; ++lt) {
-                const int acc = (int)(lt & 1);
-                const int64_t acc_use = lt >> 1;
+                const int acc = (int)(lt % p.acc_bufs);
+                const int64_t acc_use = lt / p.acc_bufs;
                 if (acc_use > 0) tc::mbar_wait(acc_empty + acc, (uint32_t)(acc_use - 1) & 1u);
                 tc::tc_fence_after_sync();
                 const uint32_t d = tmem_base + (uint32_t)(acc * p.n);
@@ -225,52 +253,59 @@ __global__ void __launch_bounds__(kT3Threads, 1)
                     const int o = (int)(it & 1);
                     tc::mbar_wait(op_ready + o, (uint32_t)(it >> 1) & 1u);
                     tc::tc_fence_after_sync();
-                    const uint32_t ah = op_addr + (uint32_t)o * 2 * kT3AtomBytes, al = ah + kT3AtomBytes;
+                    const uint32_t ah = tmem_base + col_a + (uint32_t)o * 64, al = ah + 32;
                     const uint32_t bh = wh_addr + (uint32_t)a * p.n * 128, bl = wl_addr + (uint32_t)a * p.n * 128;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {   // 4 x K=8 inside the 32-wide atom; small terms first
                         const uint32_t koff = (uint32_t)ks * 32;
-                        t3_mma(d, tc::smem_desc_sw128(al + koff), tc::smem_desc_sw128(bh + koff), idesc, (a > 0 || ks > 0) ? 1u : 0u);
-                        t3_mma(d, tc::smem_desc_sw128(ah + koff), tc::smem_desc_sw128(bl + koff), idesc, 1u);
-                        t3_mma(d, tc::smem_desc_sw128(ah + koff), tc::smem_desc_sw128(bh + koff), idesc, 1u);
+                        t3_mma_ts(d, al + (uint32_t)ks * 8, tc::smem_desc_sw128(bh + koff), idesc, (a > 0 || ks > 0) ? 1u : 0u);
+                        t3_mma_ts(d, ah + (uint32_t)ks * 8, tc::smem_desc_sw128(bl + koff), idesc, 1u);
+                        t3_mma_ts(d, ah + (uint32_t)ks * 8, tc::smem_desc_sw128(bh + koff), idesc, 1u);
                     }
-                    tc::mma_commit(op_empty + o);       // operand pair reusable once these MMAs have read it
+                    tc::mma_commit(op_empty + o);       // operand buffer reusable once these MMAs have read it
                 }
                 tc::mma_commit(acc_full + acc);         // accumulator complete
             }
         }
     } else if (warp < 4) {
-        // ---------------- split: x -> (tf32(x), x - tf32(x)) ----------------
-        // The landing slot is given back to the producer as soon as its 16 KB sit in registers, so the next TMA load
-        // is in flight during the conversion, the operand stores and the MMAs: a slot is held for one HBM round trip.
+        // ---------------- split: x -> (tf32(x), x - tf32(x)), thread t = row t of the tile ----------------
+        // The landing slot is given back to the producer as soon as the thread's row sits in registers, so a slot is
+        // held for one HBM round trip only; the split operand goes straight into tensor memory.
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + col_a;
         int64_t it = 0;
         for (int64_t lt = 0; lt < my_tiles; ++lt) {
             for (int a = 0; a < k_atoms; ++a, ++it) {
-                const int s = (int)(it % kT3Raw), o = (int)(it & 1);
-                tc::mbar_wait(raw_full + s, (uint32_t)(it / kT3Raw) & 1u);
-                const float4 *raw = reinterpret_cast<const float4 *>(raw_s + s * kT3AtomBytes);
-                float4 v[8], h[8];
+                const int s = (int)(it % p.n_raw), o = (int)(it & 1);
+                tc::mbar_wait(raw_full + s, (uint32_t)(it / p.n_raw) & 1u);
+                const unsigned char *raw = raw_s + s * kT3AtomBytes + tid * 128;   // my row; chunk c sits at c ^ (row & 7)
+                float4 v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = raw[j * 128 + tid];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) h[j] = make_float4(t3_hi(v[j].x), t3_hi(v[j].y), t3_hi(v[j].z), t3_hi(v[j].w));
+                for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4 *>(raw + ((c ^ (tid & 7)) << 4));
                 // the slot may be refilled only after every load of it has RETURNED: the barrier address carries a data
                 // dependence on all 32 loaded words (a run-time zero the compiler cannot fold), so the arrive cannot
                 // issue - let alone be reordered by ptxas - before the loads have landed in registers
                 uint32_t dep = 0u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dep ^= __float_as_uint(v[j].x) ^ __float_as_uint(v[j].y) ^ __float_as_uint(v[j].z) ^ __float_as_uint(v[j].w);
+                for (int c = 0; c < 8; ++c)
+                    dep ^= __float_as_uint(v[c].x) ^ __float_as_uint(v[c].y) ^ __float_as_uint(v[c].z) ^ __float_as_uint(v[c].w);
                 t3_arrive(reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(raw_empty + s) + (dep & zero_rt)));
-                if (it >= 2) tc::mbar_wait(op_empty + o, (uint32_t)((it >> 1) - 1) & 1u);
-                float4 *hi = reinterpret_cast<float4 *>(ops_s + o * 2 * kT3AtomBytes);
-                float4 *lo = reinterpret_cast<float4 *>(ops_s + o * 2 * kT3AtomBytes + kT3AtomBytes);
+                uint32_t hi[32], lo[32];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    hi[j * 128 + tid] = h[j];
-                    lo[j * 128 + tid] = make_float4(v[j].x - h[j].x, v[j].y - h[j].y, v[j].z - h[j].z, v[j].w - h[j].w);
+                for (int c = 0; c < 8; ++c) {
+                    const float h0 = t3_hi(v[c].x), h1 = t3_hi(v[c].y), h2 = t3_hi(v[c].z), h3 = t3_hi(v[c].w);
+                    hi[4 * c] = __float_as_uint(h0); hi[4 * c + 1] = __float_as_uint(h1);
+                    hi[4 * c + 2] = __float_as_uint(h2); hi[4 * c + 3] = __float_as_uint(h3);
+                    lo[4 * c] = __float_as_uint(v[c].x - h0); lo[4 * c + 1] = __float_as_uint(v[c].y - h1);
+                    lo[4 * c + 2] = __float_as_uint(v[c].z - h2); lo[4 * c + 3] = __float_as_uint(v[c].w - h3);
                 }
-                tc::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's operand reads
+                if (it >= 2) {   // the MMAs that read this operand buffer two atoms ago must have completed
+                    tc::mbar_wait(op_empty + o, (uint32_t)((it >> 1) - 1) & 1u);
+                    tc::tc_fence_after_sync();
+                }
+                t3_tmem_st32(trow + (uint32_t)o * 64, hi);
+                t3_tmem_st32(trow + (uint32_t)o * 64 + 32, lo);
+                t3_tmem_st_wait();
+                tc::tc_fence_before_sync();     // my tcgen05.st -> ordered before the MMAs the issuer launches after the arrive
                 t3_arrive(op_ready + o);
             }
         }
@@ -280,8 +315,8 @@ __global__ void __launch_bounds__(kT3Threads, 1)
         const bool v8_ok = (p.ldo % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 31u) == 0);
         for (int64_t lt = 0; lt < my_tiles; ++lt) {
             const int64_t tile = blockIdx.x + lt * gridDim.x;
-            const int acc = (int)(lt & 1);
-            tc::mbar_wait(acc_full + acc, (uint32_t)(lt >> 1) & 1u);
+            const int acc = (int)(lt % p.acc_bufs);
+            tc::mbar_wait(acc_full + acc, (uint32_t)(lt / p.acc_bufs) & 1u);
             tc::tc_fence_after_sync();
             const int64_t row = tile * kT3Rows + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n);
@@ -339,9 +374,16 @@ __global__ void __launch_bounds__(kT3Threads, 1)
     }
 }
 
+static size_t t3_tail_bytes(int n) { return (2 * kT3MaxRaw + 9) * sizeof(uint64_t) + 8 + 2 * (size_t)n * 4 + 64; }
+// landing slots that fit beside the resident W images (0: the shape does not fit at all)
+static int t3_raw_slots(int k, int n) {
+    const size_t fixed = 2 * (size_t)(k / kT3Atom) * n * 128 + t3_tail_bytes(n);
+    if (fixed + 2 * (size_t)kT3AtomBytes > 227 * 1024) return 0;
+    const size_t slots = (227 * 1024 - fixed) / kT3AtomBytes;
+    return slots > (size_t)kT3MaxRaw ? kT3MaxRaw : (int)slots;
+}
 static size_t t3_smem_bytes(int k, int n) {
-    return 2 * (size_t)(k / kT3Atom) * n * 128 + (size_t)(4 + kT3Raw) * kT3AtomBytes + (2 * kT3Raw + 9) * sizeof(uint64_t) + 8 +
-           2 * (size_t)n * 4 + 64;
+    return 2 * (size_t)(k / kT3Atom) * n * 128 + (size_t)t3_raw_slots(k, n) * kT3AtomBytes + t3_tail_bytes(n);
 }
 
 typedef CUresult (*t3_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -365,7 +407,7 @@ static t3_encode_fn t3_encoder() {
 using namespace cbrs;
 
 extern "C" int cbrs_dense_tf32x3_eligible(int32_t k, int32_t n) {
-    return k > 0 && k % kT3Atom == 0 && n >= 16 && n <= 256 && n % 16 == 0 && t3_smem_bytes(k, n) <= 227 * 1024;
+    return k > 0 && k % kT3Atom == 0 && n >= 16 && n <= 256 && n % 16 == 0 && t3_raw_slots(k, n) >= 2;
 }
 
 extern "C" size_t cbrs_dense_tf32x3_image_bytes(int32_t k, int32_t n) {
@@ -435,6 +477,8 @@ static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float
         CBRS_REQUIRE(!attn || q >= n_peers || p.q_peer[q], CBRS_E_INVALID, "cbrs_dense_tf32x3_attn: q peer copy %d is null", q);
     }
     p.n_tiles = cdiv(m, kT3Rows);
+    p.n_raw = t3_raw_slots(k, n);
+    p.acc_bufs = (2 * n + 128 <= 512) ? 2 : 1;
     const size_t smem = t3_smem_bytes(k, n);
     static bool attr_set = false;
     if (!attr_set) {
