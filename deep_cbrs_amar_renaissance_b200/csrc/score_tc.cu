@@ -561,6 +561,326 @@ __global__ void __launch_bounds__(kTcThreads, 4) score_tc2_kernel(const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// v3 (c1 <= 64, c2 <= 64: the reference's grids): every per-pair product on the tensor core, warp-specialised.
+// v2 spends ~290 CUDA-core instructions per pair around an 8 kFLOP MMA (0.26 of the bf16 peak): 72 to build the operand
+// row in shared memory and 192 for bias + relu + the output dot in fp32.  Here
+//  * producers (warps 0-3) form h1 = relu(bf16(P) + bf16(Q)) with one fma.rn.relu.bf16x2 per two elements and write the
+//    row straight into TENSOR MEMORY (tcgen05.st; the MMAs read A from there): no operand stores, no swizzle math;
+//  * the bias joins the product: the operand has 16 more K columns holding a constant 1 (written once), the image of W2
+//    a row holding bf16(b2);
+//  * relu + the output layer are a SECOND product: mid warps (4-7) read the accumulator, apply relu, round to bf16
+//    (one cvt.rn.relu.bf16x2.f32 per two elements) and store the row as the A operand of an M128 x N16 x K64 MMA
+//    against a 16-row image whose row 0 is bf16(w3): the logit arrives in one accumulator column;
+//  * final warps (8-11) read that column and feed the per-user candidate lists (same scheme and tie rule as before);
+//    warp 12: one elected thread issues both MMA streams.  All stages run concurrently on double-buffered TMEM
+//    operands / accumulators with mbarriers between them; one CTA per SM (16 users x all items).
+// ~125 instructions per pair instead of ~290.  Roundings (the oracle in tests/test_gpu_kernels.py mirrors them):
+// h1 = bf16(bf16(P) + bf16(Q)), W2 / b2 / w3 to bf16, h2 = bf16(relu(h1 W2 + b2)) - one more than v2, which kept h2,
+// b2 and w3 in fp32; accumulation fp32.
+constexpr int kW3Threads = 416;
+constexpr int kW3NB = 3;   // pipeline depth: buffers per TMEM operand / accumulator (a step passes 5 stages; with 2 the
+                           // loop was latency-bound at ~870 cycles per step, every role waiting half of the time)
+// TMEM columns: D1[NB] x 64, D2[NB] x 16, A1[NB] x 32, the shared constant-one K block (8), A2[NB] x 32 = 440 of 512
+constexpr uint32_t kW3ColD1 = 0, kW3ColD2 = 192, kW3ColA1 = 240, kW3ColOne = 336, kW3ColA2 = 344;
+
+struct ScoreTc3Params {
+    const float *P; int64_t ldp;
+    const uint4 *Qb;            // [n_items_pad][8] : 64 bf16 per item, zero padded
+    int64_t n_users; int32_t n_items;
+    int32_t c1, c2;
+    const uint8_t *w_image;     // [2][64][128 B]: bf16(W2^T) K-major SWIZZLE_128B, then the block whose k = 0 column is bf16(b2)
+    const uint8_t *w3_image;    // [16][128 B]: row 0 = bf16(w3), rows 1..15 zero
+    const float *b3;
+    int32_t k;
+    int32_t *ids_out; float *scores_out;
+};
+
+__global__ void score_tc3_prep_kernel(const float *__restrict__ w2, const float *__restrict__ b2, const float *__restrict__ w3,
+                                      int c1, int c2, uint8_t *__restrict__ img, uint8_t *__restrict__ img3) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 2 * 64 * 64 + 16 * 64; e += gridDim.x * blockDim.x) {
+        if (e < 2 * 64 * 64) {
+            const int kb = e >> 12, n = (e >> 6) & 63, kk = e & 63;
+            float v = 0.f;
+            if (kb == 0) v = (n < c2 && kk < c1) ? w2[(int64_t)kk * c2 + n] : 0.f;
+            else v = (kk == 0 && n < c2) ? b2[n] : 0.f;
+            *reinterpret_cast<__nv_bfloat16 *>(img + kb * 8192 + tc::sw128_offset(n, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(v);
+        } else {
+            const int f = e - 2 * 64 * 64, n = f >> 6, kk = f & 63;
+            const float v = (n == 0 && kk < c2) ? w3[kk] : 0.f;
+            *reinterpret_cast<__nv_bfloat16 *>(img3 + tc::sw128_offset(n, kk >> 3) + (kk & 7) * 2) = __float2bfloat16_rn(v);
+        }
+    }
+}
+
+__device__ __forceinline__ void w3_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void w3_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void w3_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+                 "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t w3_tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void w3_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void w3_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// relu(a * 1 + c) on two bf16 lanes: the exact sum rounded once, then max(., 0) - what add.rn.bf16x2 + max.bf16x2 give
+__device__ __forceinline__ uint32_t w3_add_relu(uint32_t a, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x3F803F80u), "r"(c));
+    return d;
+}
+// {lo, hi} -> bf16x2 with relu (round to nearest even)
+__device__ __forceinline__ uint32_t w3_pack_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+
+__global__ void __launch_bounds__(kW3Threads, 1) score_tc3_kernel(const __grid_constant__ ScoreTc3Params p) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int cap = 2 * p.k + kTcTI;
+    unsigned char *W1 = smem_raw;                                    // [2][64][128 B]
+    unsigned char *W3 = W1 + 2 * 8192;                               // [16][128 B]
+    uint4 *Pb = reinterpret_cast<uint4 *>(W3 + 2048);                // [TU][8] bf16 rows of P
+    unsigned long long *cand = reinterpret_cast<unsigned long long *>(Pb + kTcTU * 8);   // [TU][cap]
+    unsigned long long *thr = cand + kTcTU * cap;                    // [TU]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(thr + kTcTU);      // 8 barriers x NB buffers
+    uint64_t *a1_full = bars, *a1_empty = bars + kW3NB, *d1_full = bars + 2 * kW3NB, *d1_empty = bars + 3 * kW3NB;
+    uint64_t *a2_full = bars + 4 * kW3NB, *a2_empty = bars + 5 * kW3NB, *d2_full = bars + 6 * kW3NB, *d2_empty = bars + 7 * kW3NB;
+    int *cnt = reinterpret_cast<int *>(bars + 8 * kW3NB);            // [TU]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(cnt + kTcTU);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t u0 = (int64_t)blockIdx.x * kTcTU;
+
+    if (warp == 0) tc::tmem_alloc(tmem_slot, 512);
+    if (tid == 32) {
+        for (int b = 0; b < kW3NB; ++b) {
+            // "full" / "empty" from the CUDA-core side: ONE arrival per warp (lane 0, after __syncwarp) - 32 lanes arriving
+            // on the same shared-memory word are 32 serialised atomics per warp, barrier and step
+            tc::mbar_init(a1_full + b, 4);  tc::mbar_init(a1_empty + b, 1);
+            tc::mbar_init(d1_full + b, 1);  tc::mbar_init(d1_empty + b, 4);
+            tc::mbar_init(a2_full + b, 4);  tc::mbar_init(a2_empty + b, 1);
+            tc::mbar_init(d2_full + b, 1);  tc::mbar_init(d2_empty + b, 4);
+        }
+        tc::fence_mbar_init();
+    }
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(p.w_image);
+        int4 *dst = reinterpret_cast<int4 *>(W1);
+        for (int e = tid; e < 2 * 8192 / 16; e += kW3Threads) dst[e] = __ldg(src + e);
+        const int4 *src3 = reinterpret_cast<const int4 *>(p.w3_image);
+        int4 *dst3 = reinterpret_cast<int4 *>(W3);
+        for (int e = tid; e < 2048 / 16; e += kW3Threads) dst3[e] = __ldg(src3 + e);
+        for (int e = tid; e < kTcTU * 8; e += kW3Threads) {
+            const int ul = e >> 3, cg = e & 7;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int kk = cg * 8 + j;
+                v[j] = (kk < p.c1 && u0 + ul < p.n_users) ? __ldg(p.P + (u0 + ul) * p.ldp + kk) : 0.f;
+            }
+            Pb[e] = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                               tc::pack_bf16x2(v[6], v[7]));
+        }
+        if (tid < kTcTU) { cnt[tid] = 0; thr[tid] = 0ull; }
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    if ((tc::smem_u32(W1) & 1023u) != 0u) __trap();
+    constexpr int kPasses = kTcTU / 4;
+    const int n_tiles = (p.n_items + kTcTI - 1) / kTcTI;
+    const int n_steps = n_tiles * kPasses;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's TMEM lane quadrant
+
+    if (warp < 4) {
+        // ---------------- producers: thread = pair (user of quadrant `warp`, item `lane`) ----------------
+        {   // the constant-one K block every step's product ends with: element 64 = 1, 65..79 = 0 (x the image's bias row)
+            const uint32_t one[8] = {0x00003F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            w3_tmem_st8(lane_base + kW3ColOne, one);
+        }
+        uint4 qreg[8], qnext[8];   // this item's Q row, and the next item tile's (requested a whole tile ahead)
+        auto load_q = [&](int tile, uint4 (&q)[8]) {   // rows are padded to a multiple of 32 items; past the end: tile 0 again
+            const uint4 *qr = p.Qb + ((int64_t)(tile < n_tiles ? tile : 0) * kTcTI + lane) * 8;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = __ldg(qr + j);
+        };
+        load_q(0, qreg);
+        int step = 0;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            load_q(tile + 1, qnext);
+#pragma unroll 1
+            for (int pass = 0; pass < kPasses; ++pass, ++step) {
+                const int buf = step % kW3NB;
+                const uint4 *prow = Pb + (pass * 4 + warp) * 8;
+                uint32_t h[32];
+#pragma unroll
+                for (int cg = 0; cg < 8; ++cg) {
+                    const uint4 pv = prow[cg], qv = qreg[cg];
+                    h[4 * cg] = w3_add_relu(pv.x, qv.x); h[4 * cg + 1] = w3_add_relu(pv.y, qv.y);
+                    h[4 * cg + 2] = w3_add_relu(pv.z, qv.z); h[4 * cg + 3] = w3_add_relu(pv.w, qv.w);
+                }
+                if (step >= kW3NB) {   // the MMAs that read this operand buffer NB steps ago must have completed
+                    tc::mbar_wait(a1_empty + buf, (uint32_t)(step / kW3NB - 1) & 1u);
+                    tc::tc_fence_after_sync();
+                }
+                w3_tmem_st32(lane_base + kW3ColA1 + (uint32_t)buf * 32, h);
+                w3_st_wait();
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) w3_arrive(a1_full + buf);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) qreg[j] = qnext[j];
+        }
+    } else if (warp < 8) {
+        // ---------------- mid: accumulator 1 -> relu -> bf16 -> operand of the output product ----------------
+        for (int step = 0; step < n_steps; ++step) {
+            const int buf = step % kW3NB;
+            tc::mbar_wait(d1_full + buf, (uint32_t)(step / kW3NB) & 1u);
+            tc::tc_fence_after_sync();
+            uint32_t v[64];
+#pragma unroll
+            for (int cb = 0; cb < 64; cb += 16)
+                tc::tmem_ld16(lane_base + kW3ColD1 + (uint32_t)(buf * 64 + cb), *reinterpret_cast<uint32_t(*)[16]>(v + cb));
+            tc::tmem_ld_wait();
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) w3_arrive(d1_empty + buf);
+            uint32_t h[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) h[j] = w3_pack_relu(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            if (step >= kW3NB) {
+                tc::mbar_wait(a2_empty + buf, (uint32_t)(step / kW3NB - 1) & 1u);
+                tc::tc_fence_after_sync();
+            }
+            w3_tmem_st32(lane_base + kW3ColA2 + (uint32_t)buf * 32, h);
+            w3_st_wait();
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) w3_arrive(a2_full + buf);
+        }
+    } else if (warp < 12) {
+        // ---------------- final: logit column -> candidate list of the row's user ----------------
+        const int quad = warp & 3;
+        const float b3 = __ldg(p.b3);
+        int step = 0;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            for (int ul = quad; ul < kTcTU; ul += 4)   // user ul is only ever touched by the final warp of quadrant ul % 4
+                if (cnt[ul] > cap - kTcTI) tcs_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
+#pragma unroll 1
+            for (int pass = 0; pass < kPasses; ++pass, ++step) {
+                const int buf = step % kW3NB;
+                tc::mbar_wait(d2_full + buf, (uint32_t)(step / kW3NB) & 1u);
+                tc::tc_fence_after_sync();
+                const float logit = __uint_as_float(w3_tmem_ld1(lane_base + kW3ColD2 + (uint32_t)buf * 16));
+                tc::tmem_ld_wait();
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) w3_arrive(d2_empty + buf);
+                const int ul = pass * 4 + quad;
+                const int item = tile * kTcTI + lane;
+                const int64_t user = u0 + ul;
+                if (item < p.n_items && user < p.n_users) {
+                    const unsigned long long key =
+                        ((unsigned long long)tcs_orderable(logit + b3) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)item);
+                    if (key > thr[ul]) {
+                        const int pos = atomicAdd(cnt + ul, 1);
+                        cand[ul * cap + pos] = key;
+                    }
+                }
+            }
+        }
+    } else {
+        // ---------------- MMA issuer (warp 12): one elected thread, both product streams ----------------
+        if (tc::elect_one()) {
+            const uint32_t idesc1 = tc::idesc_bf16_f32(128, 64), idesc2 = tc::idesc_bf16_f32(128, 16);
+            const uint32_t w1_addr = tc::smem_u32(W1), w3_addr = tc::smem_u32(W3);
+            for (int step = 0; step <= n_steps; ++step) {
+                if (step < n_steps) {
+                    const int buf = step % kW3NB;
+                    tc::mbar_wait(a1_full + buf, (uint32_t)(step / kW3NB) & 1u);
+                    if (step >= kW3NB) tc::mbar_wait(d1_empty + buf, (uint32_t)(step / kW3NB - 1) & 1u);
+                    tc::tc_fence_after_sync();
+                    const uint32_t d = tmem_base + kW3ColD1 + (uint32_t)buf * 64, a = tmem_base + kW3ColA1 + (uint32_t)buf * 32;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)   // 4 x K=16 of h1 . W2
+                        w3_mma_ts(d, a + (uint32_t)ks * 8, tc::smem_desc_sw128(w1_addr + (uint32_t)ks * 32), idesc1, ks > 0 ? 1u : 0u);
+                    w3_mma_ts(d, tmem_base + kW3ColOne, tc::smem_desc_sw128(w1_addr + 8192u), idesc1, 1u);   // + 1 . bias row
+                    tc::mma_commit(a1_empty + buf);
+                    tc::mma_commit(d1_full + buf);
+                }
+                if (step >= 1) {
+                    const int t = step - 1, buf = t % kW3NB;
+                    tc::mbar_wait(a2_full + buf, (uint32_t)(t / kW3NB) & 1u);
+                    if (t >= kW3NB) tc::mbar_wait(d2_empty + buf, (uint32_t)(t / kW3NB - 1) & 1u);
+                    tc::tc_fence_after_sync();
+                    const uint32_t d = tmem_base + kW3ColD2 + (uint32_t)buf * 16, a = tmem_base + kW3ColA2 + (uint32_t)buf * 32;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        w3_mma_ts(d, a + (uint32_t)ks * 8, tc::smem_desc_sw128(w3_addr + (uint32_t)ks * 32), idesc2, ks > 0 ? 1u : 0u);
+                    tc::mma_commit(a2_empty + buf);
+                    tc::mma_commit(d2_full + buf);
+                }
+            }
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc::tc_fence_after_sync();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+    for (int ul = warp; ul < kTcTU; ul += kW3Threads / 32) {
+        tcs_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
+        const int64_t user = u0 + ul;
+        if (user >= p.n_users) continue;
+        const int n = cnt[ul];
+        for (int r = lane; r < p.k; r += 32) {
+            const int64_t o = user * p.k + r;
+            if (r < n) {
+                const unsigned long long key = cand[ul * cap + r];
+                p.ids_out[o] = (int32_t)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+                p.scores_out[o] = 1.f / (1.f + expf(-tcs_from_orderable((uint32_t)(key >> 32))));
+            } else {
+                p.ids_out[o] = -1;
+                p.scores_out[o] = -INFINITY;
+            }
+        }
+    }
+}
+
+static size_t score_tc3_smem(int k) {
+    const int cap = 2 * k + kTcTI;
+    return 2 * 8192 + 2048 + (size_t)kTcTU * 8 * 16 + (size_t)kTcTU * cap * 8 + kTcTU * 8 + 8 * kW3NB * 8 + kTcTU * 4 + 16;
+}
+
 static size_t score_tc2_smem(int c2, int k) {
     const int n_pad = (c2 + 15) / 16 * 16, cap = 2 * k + kTcTI;
     return 1024 + 2 * 16384 + (size_t)n_pad * 128 + (size_t)kTcTU * 8 * 16 + (size_t)(n_pad / 2) * 16 +
@@ -578,11 +898,17 @@ static size_t score_tc_smem(int c1, int c2, int k) {
 using namespace cbrs;
 
 static bool score_tc_use_v2(int c1, int c2) { return c1 <= 64 && c2 <= 128; }
+static bool score_tc_use_v3(int c1, int c2) {   // CBRS_SCORE_BF16_KERNEL=2 keeps v2 (measurements)
+    static const int forced = getenv("CBRS_SCORE_BF16_KERNEL") ? atoi(getenv("CBRS_SCORE_BF16_KERNEL")) : 0;
+    return forced != 2 && c1 <= 64 && c2 <= 64;
+}
+constexpr size_t kTc3ImageBytes = 2 * 8192 + 2048;
 
 extern "C" size_t cbrs_score_catalog_topk_bf16_workspace_bytes(int32_t n_items, int32_t c1, int32_t c2) {
     const int kb = (c1 + 63) / 64, n_pad = (c2 + 15) / 16 * 16;
     size_t bytes = align_up((size_t)kb * n_pad * 128);
     if (score_tc_use_v2(c1, c2)) bytes += align_up((size_t)((n_items + kTcTI - 1) / kTcTI) * kTcTI * 128);  // Q as bf16, 128 B per item
+    if (c1 <= 64 && c2 <= 64) bytes += align_up(kTc3ImageBytes);   // v3: image of W2 with the bias row, image of w3
     return bytes;
 }
 
@@ -610,6 +936,19 @@ extern "C" int cbrs_score_catalog_topk_bf16(const float *P, int64_t ldp, const f
         uint4 *Qb = reinterpret_cast<uint4 *>((uint8_t *)workspace + align_up((size_t)kb * n_pad * 128));
         score_tc_qprep_kernel<<<(unsigned)cdiv((int64_t)n_items_pad * 8, 256), 256, 0, s>>>(Q, ldq, n_items, n_items_pad, c1, Qb);
         CBRS_CHECK_LAUNCH("score_tc_qprep");
+        if (score_tc_use_v3(c1, c2)) {
+            uint8_t *img = (uint8_t *)workspace + align_up((size_t)kb * n_pad * 128) + align_up((size_t)n_items_pad * 128);
+            score_tc3_prep_kernel<<<8, 256, 0, s>>>(w2, b2, w3, c1, c2, img, img + 2 * 8192);
+            CBRS_CHECK_LAUNCH("score_tc3_prep");
+            const size_t smem3 = score_tc3_smem(k);
+            CBRS_REQUIRE(smem3 <= 200 * 1024, CBRS_E_UNSUPPORTED, "score_catalog_bf16: needs %zu bytes of shared memory", smem3);
+            cudaError_t e3 = cudaFuncSetAttribute(score_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            CBRS_REQUIRE(e3 == cudaSuccess, CBRS_E_CUDA, "score_catalog_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e3));
+            ScoreTc3Params p3{P, ldp, Qb, n_users, n_items, c1, c2, img, img + 2 * 8192, b3, k, ids_out, scores_out};
+            score_tc3_kernel<<<(unsigned)cdiv(n_users, kTcTU), kW3Threads, smem3, s>>>(p3);
+            CBRS_CHECK_LAUNCH("score_tc3");
+            return CBRS_OK;
+        }
         const size_t smem2 = score_tc2_smem(c2, k);
         CBRS_REQUIRE(smem2 <= 220 * 1024, CBRS_E_UNSUPPORTED, "score_catalog_bf16: needs %zu bytes of shared memory", smem2);
         static const int mode = getenv("CBRS_SCORE_EPILOGUE") ? atoi(getenv("CBRS_SCORE_EPILOGUE")) : 0;  // tuning knob

@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(kS3WsThreads, 1) score_tf32x3_ws_kernel(const 
     if (warp == 0) tc::tmem_alloc(tmem_slot, kCols);
     if (tid == 32) {
         for (int b = 0; b < 2; ++b) {
-            tc::mbar_init(a_full + b, 256);    // every producer thread, after its own tcgen05.wait::st
+            tc::mbar_init(a_full + b, 8);      // one arrival per producer warp (lane 0, after the warp's tcgen05.wait::st)
             tc::mbar_init(a_empty + b, 1);     // tcgen05.commit
             tc::mbar_init(d_full + b, 1);      // tcgen05.commit
-            tc::mbar_init(d_empty + b, 128);   // every epilogue thread, after its own tcgen05.wait::ld
+            tc::mbar_init(d_empty + b, 4);     // one arrival per epilogue warp (32 lanes on one word = 32 serialised atomics)
         }
         tc::fence_mbar_init();
     }
@@ -245,7 +245,8 @@ __global__ void __launch_bounds__(kS3WsThreads, 1) score_tf32x3_ws_kernel(const 
             }
             s3_tmem_st_wait();
             tc::tc_fence_before_sync();
-            s3_arrive(a_full + buf);
+            __syncwarp();
+            if (lane == 0) s3_arrive(a_full + buf);
             ++step;
         };
         load_q(0);
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(kS3WsThreads, 1) score_tf32x3_ws_kernel(const 
                 for (int cb = 0; cb < NP; cb += 16) tc::tmem_ld16(drow + (uint32_t)cb, *reinterpret_cast<uint32_t(*)[16]>(v + cb));
                 tc::tmem_ld_wait();
                 tc::tc_fence_before_sync();
-                s3_arrive(d_empty + buf);      // the accumulator may be overwritten: its values sit in registers
+                __syncwarp();
+                if (lane == 0) s3_arrive(d_empty + buf);      // the accumulator may be overwritten: its values sit in registers
                 float lacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // independent chains, fixed combination order
 #pragma unroll
                 for (int j = 0; j < NP; j += 2) {

@@ -597,7 +597,7 @@ def score_catalog_topk(P, Q, w2, b2, w3, b3, k, precision="fp32"):
                                                  _ptr(w3, torch.float32), _ptr(b3, torch.float32), k, _ptr(ids),
                                                  _ptr(vals), _ptr(ws), ws.numel(), _stream()),
                 "cbrs_score_catalog_topk_bf16")
-        _count(3 if c1 <= 64 and c2 <= 128 else 2)
+        _count(4 if (c1 <= 64 and c2 <= 64) else (3 if c1 <= 64 and c2 <= 128 else 2))
         return ids, vals
     P, ldp = _rowmajor(P)
     Q, ldq = _rowmajor(Q)

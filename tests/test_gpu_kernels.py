@@ -386,7 +386,8 @@ def _bf16_round(x):
                                                       (33, 500, 8, 16, 3), (20, 700, 72, 80, 10)])
 def test_tensor_core_catalog_scorer_matches_bf16_oracle(dev, n_users, n_items, c1, c2, k):
     """tcgen05 path: operands rounded to bf16, fp32 accumulate.  Oracle = the same rounding in numpy;
-    tolerance 2e-5 on scores (fp32 summation order inside the MMA is unspecified)."""
+    tolerance 2e-5 on scores (fp32 summation order inside the MMA is unspecified; 1e-4 for the v3 kernel, where an
+    activation within an fp32 ulp of a bf16 rounding boundary may round the other way before the output product)."""
     from deep_cbrs_amar_renaissance_b200 import ops
     from tests.helpers import assert_topk_equivalent
     rng = np.random.RandomState(n_items + c2)
@@ -400,12 +401,20 @@ def test_tensor_core_catalog_scorer_matches_bf16_oracle(dev, n_users, n_items, c
         h1 = np.maximum(_bf16_round(_bf16_round(P)[:, None, :] + _bf16_round(Q)[None, :, :]), 0).reshape(-1, c1)
     else:
         h1 = _bf16_round(np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1))
-    h2 = np.maximum(h1.astype(np.float64) @ _bf16_round(w2).astype(np.float64) + b2, 0).astype(np.float32)
-    scores = ol.sigmoid(h2 @ w3 + b3).reshape(n_users, n_items)
+    if c1 <= 64 and c2 <= 64:
+        # v3 kernel (every product on the tensor core): the bias is a row of the bf16 image of W2, relu(h1 W2 + b2) is
+        # rounded to bf16 and the output layer is a second product against bf16(w3)
+        acc = h1.astype(np.float64) @ _bf16_round(w2).astype(np.float64) + _bf16_round(b2).astype(np.float64)
+        h2 = _bf16_round(np.maximum(acc, 0).astype(np.float32))
+        scores = ol.sigmoid((h2.astype(np.float64) @ _bf16_round(w3).astype(np.float64)).astype(np.float32) + b3)
+        scores = scores.reshape(n_users, n_items)
+    else:
+        h2 = np.maximum(h1.astype(np.float64) @ _bf16_round(w2).astype(np.float64) + b2, 0).astype(np.float32)
+        scores = ol.sigmoid(h2 @ w3 + b3).reshape(n_users, n_items)
     kk = min(k, n_items)
     ids_np, vals_np = ids.cpu().numpy(), vals.cpu().numpy()
     assert (ids_np[:, kk:] == -1).all()
-    assert_topk_equivalent(ids_np[:, :kk], vals_np[:, :kk], scores, kk, tol=2e-5)
+    assert_topk_equivalent(ids_np[:, :kk], vals_np[:, :kk], scores, kk, tol=1e-4 if (c1 <= 64 and c2 <= 64) else 2e-5)
     # and it stays within bf16 distance of the exact fp32 scorer
     exact = ol.sigmoid(np.maximum(np.maximum(P[:, None, :] + Q[None, :, :], 0).reshape(-1, c1) @ w2 + b2, 0) @ w3 + b3)
     got_exact = np.take_along_axis(exact.reshape(n_users, n_items), ids_np[:, :kk].astype(np.int64), axis=1)
