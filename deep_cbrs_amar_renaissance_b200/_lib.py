@@ -66,6 +66,8 @@ _SIGS = {
     "cbrs_dense_tf32x3_image_bytes": (c_size_t, [c_int32, c_int32]),
     "cbrs_dense_tf32x3_prepare": (c_int, [P, c_int32, c_int32, P, P]),
     "cbrs_dense_tf32x3": (c_int, [P, c_int64, P, P, c_int64, c_int32, c_int32, c_int, P, c_int64, c_int, POINTER(c_void_p), c_int, P]),
+    "cbrs_dense_tf32x3_ex": (c_int, [P, c_int64, P, P, P, c_int64, c_int, c_int64, c_int32, c_int32, c_int, P, c_int64, c_int,
+                                     POINTER(c_void_p), c_int, P]),
     "cbrs_dense_tf32x3_attn": (c_int, [P, c_int64, P, c_int64, c_int32, c_int32, P, P, P, P, P, c_int64, POINTER(c_void_p),
                                        POINTER(c_void_p), c_int, P]),
     "cbrs_reduce_layers": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int32, POINTER(c_float), c_float,

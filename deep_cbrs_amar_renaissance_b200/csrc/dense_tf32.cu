@@ -58,6 +58,8 @@ struct T3Params {
     int32_t n_peer;
     int32_t out_bf16;   // out / out_peer hold bf16 (round to nearest even), ldo in elements
     int64_t n_tiles;
+    const float *addend; int64_t ld_add;   // optional [m, n] matrix added to the product before bias / row-op (cbrs_dense_tf32x3_ex)
+    int32_t l2norm;     // CBRS_ROWOP_L2NORM: v / sqrt(max(sum v^2, 1e-12)) before the activation (GraphSageConv)
     int32_t n_raw;      // landing slots (2 .. kT3MaxRaw)
     int32_t acc_bufs;   // accumulators in TMEM (2 when 2 n + 128 <= 512 columns, else 1)
     // GAT row-op (cbrs_dense_tf32x3_attn): p[m] = out[m,:] . a_self, q[m] = out[m,:] . a_neigh (GATConv's attention logits)
@@ -129,6 +131,14 @@ __device__ __forceinline__ void t3_tmem_st32(uint32_t taddr, const uint32_t (&v)
         "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
         "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
         "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void t3_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
         : "memory");
 }
 __device__ __forceinline__ void t3_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -321,6 +331,42 @@ __global__ void __launch_bounds__(kT3Threads, 1)
             const int64_t row = tile * kT3Rows + quad * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n);
             float ps = 0.f, qs = 0.f;
+            float scale = 1.f;
+            const float *arow = (!kPlain && p.addend && row < p.m) ? p.addend + row * p.ld_add : nullptr;
+            bool folded = false;   // the accumulator already holds product + addend + bias (first pass of the row-op)
+            if (!kPlain && (p.l2norm || p.addend)) {
+                // first pass over the accumulator: x = product + addend + bias, written back into the accumulator's own
+                // TMEM columns (the addend is read from HBM once: 64 contiguous bytes per lane and block, the next
+                // block's four 128-bit loads in flight while this one is processed), and the row's sum of squares
+                float ss = 0.f;
+                float4 a_cur[4], a_nxt[4];
+                auto load_add = [&](int cb, float4 (&a)[4]) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a[q] = arow ? ldg4(arow + cb + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                };
+                load_add(0, a_cur);
+                for (int cb = 0; cb < p.n; cb += 16) {
+                    if (cb + 16 < p.n) load_add(cb + 16, a_nxt);
+                    uint32_t v[16];
+                    tc::tmem_ld16(taddr + (uint32_t)cb, v);   // warp-collective
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 bb = *reinterpret_cast<const float4 *>(bias_s + cb + 4 * q);
+                        const float x0 = __uint_as_float(v[4 * q]) + a_cur[q].x + bb.x, x1 = __uint_as_float(v[4 * q + 1]) + a_cur[q].y + bb.y;
+                        const float x2 = __uint_as_float(v[4 * q + 2]) + a_cur[q].z + bb.z, x3 = __uint_as_float(v[4 * q + 3]) + a_cur[q].w + bb.w;
+                        ss = fmaf(x0, x0, ss); ss = fmaf(x1, x1, ss); ss = fmaf(x2, x2, ss); ss = fmaf(x3, x3, ss);
+                        v[4 * q] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
+                        v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+                    }
+                    t3_tmem_st16(taddr + (uint32_t)cb, v);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) a_cur[q] = a_nxt[q];
+                }
+                t3_tmem_st_wait();
+                if (p.l2norm) scale = 1.f / sqrtf(fmaxf(ss, 1e-12f));
+                folded = true;
+            }
             for (int cb = 0; cb < p.n; cb += 16) {
                 uint32_t v[16];
                 tc::tmem_ld16(taddr + (uint32_t)cb, v);   // warp-collective
@@ -328,8 +374,14 @@ __global__ void __launch_bounds__(kT3Threads, 1)
                 if (row < p.m) {
                     float o[2][8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        o[j >> 3][j & 7] = kPlain ? __uint_as_float(v[j]) : t3_act(__uint_as_float(v[j]) + bias_s[cb + j], p.act);
+                    for (int j = 0; j < 16; ++j) {
+                        if (kPlain) {
+                            o[j >> 3][j & 7] = __uint_as_float(v[j]);
+                        } else {
+                            const float x = folded ? __uint_as_float(v[j]) : __uint_as_float(v[j]) + bias_s[cb + j];
+                            o[j >> 3][j & 7] = t3_act(x * scale, p.act);
+                        }
+                    }
                     if (kAttn) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
@@ -428,7 +480,8 @@ extern "C" int cbrs_dense_tf32x3_prepare(const float *w, int32_t k, int32_t n, v
     return CBRS_OK;
 }
 
-static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k, int32_t n, int act,
+static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float *b, const float *addend, int64_t ld_add, int rowop,
+                   int64_t m, int32_t k, int32_t n, int act,
                    void *out_v, int64_t ldo, int out_dtype, void *const *out_peers_host, int n_peers, const float *a_self,
                    const float *a_neigh, float *p_out, float *q_out, void *const *q_peers_host, void *stream) {
     float *out = (float *)out_v;
@@ -440,6 +493,10 @@ static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float
     CBRS_REQUIRE(out_dtype == CBRS_DTYPE_F32 || (ldo % 16 == 0 && (reinterpret_cast<uintptr_t>(out_v) & 31u) == 0), CBRS_E_INVALID,
                  "cbrs_dense_tf32x3: a bf16 output needs 32-byte aligned rows (ldo %% 16 == 0)");
     CBRS_REQUIRE(x && w_image && out, CBRS_E_INVALID, "cbrs_dense_tf32x3: null pointer");
+    CBRS_REQUIRE(rowop == CBRS_ROWOP_NONE || rowop == CBRS_ROWOP_L2NORM, CBRS_E_INVALID, "cbrs_dense_tf32x3: rowop %d (none or l2norm)", rowop);
+    CBRS_REQUIRE(!attn || (!addend && rowop == CBRS_ROWOP_NONE), CBRS_E_INVALID, "cbrs_dense_tf32x3_attn takes no addend / row-op");
+    CBRS_REQUIRE(!addend || (ld_add >= n && ld_add % 4 == 0 && (reinterpret_cast<uintptr_t>(addend) & 15u) == 0), CBRS_E_INVALID,
+                 "cbrs_dense_tf32x3: addend rows must be 16-byte aligned (ld_add %% 4 == 0, ld_add >= n)");
     CBRS_REQUIRE(cbrs_dense_tf32x3_eligible(k, n), CBRS_E_INVALID, "cbrs_dense_tf32x3: k = %d, n = %d not supported (see "
                  "cbrs_dense_tf32x3_eligible); use cbrs_dense", k, n);
     CBRS_REQUIRE(m >= 0 && m < ((int64_t)1 << 31) && ldx >= k && ldo >= n, CBRS_E_INVALID, "cbrs_dense_tf32x3: bad shape");
@@ -476,6 +533,7 @@ static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float
         p.q_peer[q] = (attn && q < n_peers) ? (float *)q_peers_host[q] : nullptr;
         CBRS_REQUIRE(!attn || q >= n_peers || p.q_peer[q], CBRS_E_INVALID, "cbrs_dense_tf32x3_attn: q peer copy %d is null", q);
     }
+    p.addend = addend; p.ld_add = ld_add; p.l2norm = rowop == CBRS_ROWOP_L2NORM;
     p.n_tiles = cdiv(m, kT3Rows);
     p.n_raw = t3_raw_slots(k, n);
     p.acc_bufs = (2 * n + 128 <= 512) ? 2 : 1;
@@ -493,7 +551,7 @@ static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float
     const unsigned grid = (unsigned)(p.n_tiles < kSMs ? p.n_tiles : kSMs);
     if (attn)
         dense_tf32x3_kernel<true, true><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(map, p);
-    else if (!b && act == CBRS_ACT_NONE)
+    else if (!b && act == CBRS_ACT_NONE && !addend && rowop == CBRS_ROWOP_NONE)
         dense_tf32x3_kernel<true><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(map, p);
     else
         dense_tf32x3_kernel<false><<<grid, kT3Threads, smem, (cudaStream_t)stream>>>(map, p);
@@ -504,8 +562,15 @@ static int t3_impl(const float *x, int64_t ldx, const void *w_image, const float
 extern "C" int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const float *b, int64_t m, int32_t k,
                                  int32_t n, int act, void *out, int64_t ldo, int out_dtype, void *const *out_peers_host,
                                  int n_peers, void *stream) {
-    return t3_impl(x, ldx, w_image, b, m, k, n, act, out, ldo, out_dtype, out_peers_host, n_peers, nullptr, nullptr, nullptr,
-                   nullptr, nullptr, stream);
+    return t3_impl(x, ldx, w_image, b, nullptr, 0, CBRS_ROWOP_NONE, m, k, n, act, out, ldo, out_dtype, out_peers_host, n_peers, nullptr,
+                   nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int cbrs_dense_tf32x3_ex(const float *x, int64_t ldx, const void *w_image, const float *b, const float *addend,
+                                    int64_t ld_add, int rowop, int64_t m, int32_t k, int32_t n, int act, void *out, int64_t ldo,
+                                    int out_dtype, void *const *out_peers_host, int n_peers, void *stream) {
+    return t3_impl(x, ldx, w_image, b, addend, ld_add, rowop, m, k, n, act, out, ldo, out_dtype, out_peers_host, n_peers, nullptr,
+                   nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int cbrs_dense_tf32x3_attn(const float *x, int64_t ldx, const void *w_image, int64_t m, int32_t k, int32_t n,
@@ -513,6 +578,6 @@ extern "C" int cbrs_dense_tf32x3_attn(const float *x, int64_t ldx, const void *w
                                       int64_t ldo, void *const *out_peers_host, void *const *q_peers_host, int n_peers,
                                       void *stream) {
     CBRS_REQUIRE(a_self && a_neigh && p_out && q_out, CBRS_E_INVALID, "cbrs_dense_tf32x3_attn: null attention argument");
-    return t3_impl(x, ldx, w_image, nullptr, m, k, n, CBRS_ACT_NONE, out, ldo, CBRS_DTYPE_F32, out_peers_host, n_peers, a_self,
+    return t3_impl(x, ldx, w_image, nullptr, nullptr, 0, CBRS_ROWOP_NONE, m, k, n, CBRS_ACT_NONE, out, ldo, CBRS_DTYPE_F32, out_peers_host, n_peers, a_self,
                    a_neigh, p_out, q_out, q_peers_host, stream);
 }

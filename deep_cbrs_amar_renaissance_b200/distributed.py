@@ -619,8 +619,8 @@ class RowPartition:
                     agg = self._buf(("agg", l, a), sl.n_rows, widths[l], emb.device)
                     ops.spmm(sl, x_full, agg, agg=L.AGG_MEAN if layer.aggregate == "mean" else L.AGG_SUM)
                     ov = out[a:b]
-                    ops.dense(x_full[a:b], layer.kernel, layer.bias, layer.activation, x2=agg, rowop=L.ROWOP_L2NORM,
-                              out=ov, peers=out_peers(ov, a))
+                    ops.sage_dense(x_full[a:b], agg, layer.kernel, layer.bias, layer.activation, x_full.shape[0],
+                                   out=ov, peers=out_peers(ov, a))
             else:
                 raise NotImplementedError("no partitioned form for {}".format(type(layer).__name__))
             x_full = out

@@ -81,8 +81,8 @@ class GraphSageConv(_Conv):
         agg = torch.empty(csr.n_rows, x.shape[1], dtype=torch.float32, device=x.device)
         ops.spmm(csr, x, agg, agg=L.AGG_MEAN if self.aggregate == "mean" else L.AGG_SUM)
         x_self = x[csr.row_offset:csr.row_offset + csr.n_rows]
-        return ops.dense(x_self, self.kernel, self.bias, self.activation, x2=agg, rowop=L.ROWOP_L2NORM,
-                         out=self._out(out, csr.n_rows, x.device))
+        return ops.sage_dense(x_self, agg, self.kernel, self.bias, self.activation, x.shape[0],
+                              out=self._out(out, csr.n_rows, x.device))
 
 
 class GATConv(_Conv):

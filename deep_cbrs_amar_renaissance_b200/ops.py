@@ -326,6 +326,46 @@ def dense_tf32x3(x, w, b=None, act=None, out=None, peers=None, out_dtype=None):
     return out
 
 
+def sage_dense(x_self, agg, kernel, bias, act, rows_total, out=None, peers=None):
+    """GraphSageConv's dense part act(l2_normalize([x_self || agg] @ kernel + bias)) (spektral GraphSageConv.call).
+    From TF32X3_MIN_ROWS graph nodes up (the same GLOBAL rule as the GCN transform, so every rank of a row partition and
+    the single-GPU run take the same kernel) it runs on the tensor cores at fp32 accuracy as two products - the operand
+    images of a 2f-deep kernel do not fit shared memory at once: t = x_self @ kernel[:f], then
+    act(l2norm(agg @ kernel[f:] + t + bias)) with the normalisation in the second product's epilogue
+    (cbrs_dense_tf32x3_ex); below that, and for shapes the kernel does not take, the FFMA kernel (cbrs_dense)."""
+    f, n = x_self.shape[1], kernel.shape[1]
+    if not (agg.shape[1] == f and tf32x3_chosen(rows_total, f, n, x_self, out) and tf32x3_chosen(rows_total, f, n, agg)
+            and (out is None or out.dtype == torch.float32)):
+        return dense(x_self, kernel, bias, act, x2=agg, rowop=L.ROWOP_L2NORM, out=out, peers=peers)
+    lib = L.load()
+    x_self, ld1 = _rowmajor(x_self)
+    agg, ld2 = _rowmajor(agg)
+    m = x_self.shape[0]
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=x_self.device)
+    out, ldo = _rowmajor(out)
+    t = torch.empty(m, n, dtype=torch.float32, device=x_self.device)
+    nbytes = lib.cbrs_dense_tf32x3_image_bytes(f, n)
+    images = torch.empty(2 * nbytes, dtype=torch.uint8, device=x_self.device)
+    top, bot = images[:nbytes], images[nbytes:]
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.check(lib.cbrs_dense_tf32x3_prepare(_ptr(kernel[:f], torch.float32), f, n, _ptr(top), _stream()), "cbrs_dense_tf32x3_prepare")
+    L.check(lib.cbrs_dense_tf32x3_prepare(_ptr(kernel[f:], torch.float32), f, n, _ptr(bot), _stream()), "cbrs_dense_tf32x3_prepare")
+    L.check(lib.cbrs_dense_tf32x3(_ptr(x_self), ld1, _ptr(top), None, m, f, n, L.ACT_NONE, _ptr(t), n, L.DTYPE_F32, None, 0,
+                                  _stream()), "cbrs_dense_tf32x3")
+    code = act if isinstance(act, int) else L.ACTS[act]
+    L.check(lib.cbrs_dense_tf32x3_ex(_ptr(agg), ld2, _ptr(bot), _ptr(bias, torch.float32), _ptr(t), n, L.ROWOP_L2NORM, m, f, n,
+                                     code, _ptr(out), ldo, L.DTYPE_F32, _ptr_array(peers) if peers else None,
+                                     len(peers) if peers else 0, _stream()), "cbrs_dense_tf32x3_ex")
+    _count(4)
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("dense", e0, e1, m * n))
+    return out
+
+
 def gat_transform(x, w, a_self, a_neigh, rows_total, out=None, q_out=None, peers=None, q_peers=None):
     """(z, p, q) = (x @ w, z . a_self, z . a_neigh) for a GAT layer: the tensor-core kernel with the attention row-op from
     TF32X3_MIN_ROWS graph nodes up (cbrs_dense_tf32x3_attn), else cbrs_dense with CBRS_ROWOP_ATTN."""

@@ -247,6 +247,15 @@ int cbrs_dense_tf32x3(const float *x, int64_t ldx, const void *w_image, const fl
                       int32_t n, int act, void *out, int64_t ldo, int out_dtype, void *const *out_peers_host,
                       int n_peers, void *stream);
 
+/* General form: out = act( rowop( x @ W + addend + b ) ).  addend: optional [m, n] fp32 matrix (ld_add in elements) added
+ * to the product; rowop = CBRS_ROWOP_NONE or CBRS_ROWOP_L2NORM.  GraphSageConv's dense part
+ * relu(l2_normalize([x || agg] @ K + b)) (spektral GraphSageConv.call, built at src/models/gnn.py:354-361) runs as two such
+ * products, x @ K[:f] and then agg @ K[f:] + the first + b (the two operand images of a 2f-deep kernel do not fit shared
+ * memory at once).                                                                                                   */
+int cbrs_dense_tf32x3_ex(const float *x, int64_t ldx, const void *w_image, const float *b, const float *addend,
+                         int64_t ld_add, int rowop, int64_t m, int32_t k, int32_t n, int act, void *out, int64_t ldo,
+                         int out_dtype, void *const *out_peers_host, int n_peers, void *stream);
+
 /* The GAT transform on the same kernel (spektral GATConv built at src/models/gnn.py:321-328: z = x W, then the two
  * attention logits per node): out = X W (fp32) plus p[m] = out[m,:] . a_self and q[m] = out[m,:] . a_neigh, i.e.
  * cbrs_dense with CBRS_ROWOP_ATTN on the tensor cores.  q_peers_host as in cbrs_dense_bcast.                          */

@@ -148,3 +148,49 @@ def test_gat_transform_on_the_tensor_cores(dev, monkeypatch):
     ptr, idx, _ = og.reorder_raw(adj)
     want = ol.gat_conv(xx, ptr, idx, w, a_s, a_n, b, "relu")
     assert_close(out.cpu().numpy(), want, rtol=1e-5, what="GAT layer, tensor-core transform")
+
+
+def test_graphsage_dense_part_on_the_tensor_cores(dev, monkeypatch):
+    """act(l2_normalize([x || agg] @ K + b)) as two 3xTF32 products with the normalisation in the second one's epilogue
+    (cbrs_dense_tf32x3_ex) against float64, against the FFMA kernel, under row slices, and a whole GraphSage layer against
+    the oracle"""
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from deep_cbrs_amar_renaissance_b200.graph import DeviceGraph
+    from deep_cbrs_amar_renaissance_b200.layers import GraphSageConv
+    from oracle import layers as ol
+    rng = np.random.RandomState(5)
+    m, f, n = 3001, 64, 48
+    x = rng.standard_normal((m, f)).astype(np.float32)
+    agg = rng.standard_normal((m, f)).astype(np.float32)
+    agg[7] = 0.0
+    x[7] = 0.0                                        # an all-zero pre-activation row when the bias is zero
+    k = (rng.standard_normal((2 * f, n)) / 11).astype(np.float32)
+    b = (rng.standard_normal(n) * 0.1).astype(np.float32)
+    xd, ad, kd, bd = (torch.from_numpy(t).to(dev) for t in (x, agg, k, b))
+    assert torch.equal(ops.sage_dense(xd, ad, kd, bd, "relu", m), ops.dense(xd, kd, bd, "relu", x2=ad, rowop=1))   # auto: FFMA
+    monkeypatch.setattr(ops, "GCN_TRANSFORM", "tf32x3")
+    for bias_np, bias_d in ((b, bd), (np.zeros(n, np.float32), torch.zeros(n, device=dev))):
+        v = np.concatenate([x, agg], 1).astype(np.float64) @ k.astype(np.float64) + bias_np
+        want = np.maximum(v / np.sqrt(np.maximum((v * v).sum(1, keepdims=True), 1e-12)), 0).astype(np.float32)
+        launches = ops.LAUNCHES
+        got = ops.sage_dense(xd, ad, kd, bias_d, "relu", m)
+        assert ops.LAUNCHES - launches == 4               # two operand images, two tensor-core products
+        assert_close(got.cpu().numpy(), want, rtol=1e-5, what="GraphSage dense part (3xTF32)")
+        ffma = ops.dense(xd, kd, bias_d, "relu", x2=ad, rowop=1)
+        assert float((got - ffma).abs().max()) <= 3e-6
+    full = ops.sage_dense(xd, ad, kd, bd, "relu", m)
+    for a, e in ((0, m), (1, 2999), (129, 300)):
+        buf = torch.full((e - a, n + 16), -2.0, device=dev)
+        part = ops.sage_dense(xd[a:e], ad[a:e], kd, bd, "relu", m, out=buf[:, 8:8 + n])
+        assert torch.equal(part, full[a:e]) and (buf[:, :8] == -2).all() and (buf[:, 8 + n:] == -2).all()
+    # a whole layer
+    adj = random_bipartite(300, 80, 6000, seed=8)
+    nn = adj.shape[0]
+    xs = rng.standard_normal((nn, 64)).astype(np.float32)
+    g = DeviceGraph.from_scipy(adj, dev)
+    layer = GraphSageConv(32, activation="relu")
+    layer.build([(nn, 64)])
+    out = layer([torch.from_numpy(xs).to(dev), g]).cpu().numpy()
+    ptr, idx, _ = og.reorder_raw(adj)
+    want = ol.sage_conv(xs, ptr, idx, layer.kernel.cpu().numpy(), layer.bias.cpu().numpy(), "mean", "relu")
+    assert_close(out, want, rtol=1e-5, what="GraphSage layer, tensor-core dense part")

@@ -82,6 +82,9 @@ def main():
     ms = timeit(lambda: ops.dense(x, w2, bias, "relu", x2=agg, rowop=L.ROWOP_L2NORM, out=out2))
     report("GraphSage [x||agg]W + l2norm + relu (dense, fp32 FFMA)", ms, 0, n * 3 * d * s,
            {"tflops": 2 * n * 2 * d * d / (ms * 1e-3) / 1e12})
+    ms = timeit(lambda: ops.sage_dense(x, agg, w2, bias, "relu", n, out=out2))
+    report("GraphSage [x||agg]W + l2norm + relu (tcgen05, 3xTF32, two products: the path the layer takes at this scale)", ms, 0,
+           n * 3 * d * s, {"tflops_fp32_equivalent": 2 * n * 2 * d * d / (ms * 1e-3) / 1e12})
     # GCN transform
     ms = timeit(lambda: ops.dense(x, w, out=out2))
     report("GCN transform X W (dense, fp32 FFMA)", ms, 0, n * 2 * d * s, {"tflops": 2 * n * d * d / (ms * 1e-3) / 1e12})
