@@ -154,6 +154,20 @@ def partition_parity(group=None, log=None, families=("BasicGCN", "BasicGraphSage
                             check(torch.equal(got, full), "64-wide GAT tf32x3%s" % (" blocked" if blocking else ""))
                             part.close()
                             seq.partition = None
+                            # GraphSage with its dense part as two tensor-core products (ops.sage_dense), partitioned
+                            set_seed(17)
+                            model = basic.BasicGraphSage(adj, n_hiddens=[64, 64], embedding_dim=64, dense_units=[48, 48],
+                                                         clf_units=[64, 64])
+                            seq = model.gnn.gnn_layers
+                            model((u, i))
+                            full = model.gnn(None).clone()
+                            part = RowPartition([n_users, n_items, n_props], group=group, final_types=[0, 1, 2],
+                                                exchange="peer").attach(seq)
+                            got = model.gnn(None)
+                            torch.cuda.synchronize()
+                            check(torch.equal(got, full), "64-wide GraphSage tf32x3%s" % (" blocked" if blocking else ""))
+                            part.close()
+                            seq.partition = None
                 finally:
                     ops.GCN_TRANSFORM = saved
                 say("partition parity: 128-wide GCN (fused / replicated / tensor-core transform)%s done" % (" blocked" if blocking else ""))
