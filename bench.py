@@ -38,6 +38,9 @@ DENSE_UNITS, CLF_UNITS = [48, 48], [64, 64]  # econfigs/basic-gnn.yaml grid2 sco
 PAIR_BATCH = 65536
 
 
+BF16_SCORER_FLOPS = 2 * (64 + 16) * 64 + 2 * 64 * 16   # per pair, cbrs_score_catalog_topk_bf16 at the reference's 64 -> 64 -> 1 classifier
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -552,9 +555,10 @@ def run_b200(args):
                   "ms": cat_ms, "tensor_flops_per_pair": 3 * 2 * CLF_UNITS[0] * CLF_UNITS[1],
                   "fp32_ffma": {"value": pairs_ffma, "unit": "pairs/s", "users_per_rank": cu, "ms": ffma_ms,
                                 "what": "cbrs_score_catalog_topk (CUDA-core FFMA kernel, round 1's parity path)"},
+                  # v3 kernel: h1 . [W2; b2] (K = 64 + 16 for the bias row) and relu(.) . w3 (N = 16) both on the tensor core
                   "bf16_tcgen05": {"value": pairs_tc, "unit": "pairs/s", "users_per_rank": cu_tc, "ms": tc_ms,
-                                   "tensor_flops_per_pair": 2 * CLF_UNITS[0] * CLF_UNITS[1],
-                                   "frac_of_bf16_peak": pairs_tc / world * 2 * CLF_UNITS[0] * CLF_UNITS[1] / 1e12 / (peaks.get("bf16_tflops_sustained") or 1398.0)}},
+                                   "tensor_flops_per_pair": BF16_SCORER_FLOPS,
+                                   "frac_of_bf16_peak": pairs_tc / world * BF16_SCORER_FLOPS / 1e12 / (peaks.get("bf16_tflops_sustained") or 1398.0)}},
     }
     if world == 1:
         # hybrid scorer towers (BASELINE config 4: Dense 768 -> 256 -> 64 over BERT rows, bf16): cbrs_dense_tc (tcgen05)
