@@ -573,12 +573,12 @@ __global__ void __launch_bounds__(kTcThreads, 4) score_tc2_kernel(const __grid_c
 //    (one cvt.rn.relu.bf16x2.f32 per two elements) and store the row as the A operand of an M128 x N16 x K64 MMA
 //    against a 16-row image whose row 0 is bf16(w3): the logit arrives in one accumulator column;
 //  * final warps (8-11) read that column and feed the per-user candidate lists (same scheme and tie rule as before);
-//    warp 12: one elected thread issues both MMA streams.  All stages run concurrently on double-buffered TMEM
+//    warps 12 / 13: one elected thread each issues the MMAs of the first / the output product.  All stages run concurrently on double-buffered TMEM
 //    operands / accumulators with mbarriers between them; one CTA per SM (16 users x all items).
 // ~125 instructions per pair instead of ~290.  Roundings (the oracle in tests/test_gpu_kernels.py mirrors them):
 // h1 = bf16(bf16(P) + bf16(Q)), W2 / b2 / w3 to bf16, h2 = bf16(relu(h1 W2 + b2)) - one more than v2, which kept h2,
 // b2 and w3 in fp32; accumulation fp32.
-constexpr int kW3Threads = 416;
+constexpr int kW3Threads = 448;
 constexpr int kW3NB = 3;   // pipeline depth: buffers per TMEM operand / accumulator (a step passes 5 stages; with 2 the
                            // loop was latency-bound at ~870 cycles per step, every role waiting half of the time)
 // TMEM columns: D1[NB] x 64, D2[NB] x 16, A1[NB] x 32, the shared constant-one K block (8), A2[NB] x 32 = 440 of 512
@@ -760,7 +760,8 @@ __global__ void __launch_bounds__(kW3Threads, 1) score_tc3_kernel(const __grid_c
             for (int j = 0; j < 8; ++j) qreg[j] = qnext[j];
         }
     } else if (warp < 8) {
-        // ---------------- mid: accumulator 1 -> relu -> bf16 -> operand of the output product ----------------
+        // ---------------- mid: accumulator 1 -> relu -> bf16 -> operand of the output product (a second set of mid warps
+        // alternating steps measured slower: 53 vs 60 G pairs/s - registers per thread drop to 96) ----------------
         for (int step = 0; step < n_steps; ++step) {
             const int buf = step % kW3NB;
             tc::mbar_wait(d1_full + buf, (uint32_t)(step / kW3NB) & 1u);
@@ -818,12 +819,13 @@ __global__ void __launch_bounds__(kW3Threads, 1) score_tc3_kernel(const __grid_c
             }
         }
     } else {
-        // ---------------- MMA issuer (warp 12): one elected thread, both product streams ----------------
+        // ---------------- MMA issuers: warp 12 the first product, warp 13 the output product, one elected thread each
+        // (one thread for both streams blocks the next step's first product on the previous step's mid stage) ----------------
         if (tc::elect_one()) {
             const uint32_t idesc1 = tc::idesc_bf16_f32(128, 64), idesc2 = tc::idesc_bf16_f32(128, 16);
             const uint32_t w1_addr = tc::smem_u32(W1), w3_addr = tc::smem_u32(W3);
-            for (int step = 0; step <= n_steps; ++step) {
-                if (step < n_steps) {
+            if (warp == 12) {
+                for (int step = 0; step < n_steps; ++step) {
                     const int buf = step % kW3NB;
                     tc::mbar_wait(a1_full + buf, (uint32_t)(step / kW3NB) & 1u);
                     if (step >= kW3NB) tc::mbar_wait(d1_empty + buf, (uint32_t)(step / kW3NB - 1) & 1u);
@@ -836,8 +838,9 @@ __global__ void __launch_bounds__(kW3Threads, 1) score_tc3_kernel(const __grid_c
                     tc::mma_commit(a1_empty + buf);
                     tc::mma_commit(d1_full + buf);
                 }
-                if (step >= 1) {
-                    const int t = step - 1, buf = t % kW3NB;
+            } else {
+                for (int t = 0; t < n_steps; ++t) {
+                    const int buf = t % kW3NB;
                     tc::mbar_wait(a2_full + buf, (uint32_t)(t / kW3NB) & 1u);
                     if (t >= kW3NB) tc::mbar_wait(d2_empty + buf, (uint32_t)(t / kW3NB - 1) & 1u);
                     tc::tc_fence_after_sync();
