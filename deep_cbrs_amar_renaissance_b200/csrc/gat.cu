@@ -4,9 +4,10 @@
 // (attn_heads=1, add_self_loops=True, dropout 0): 4 gathers + unsorted_segment_max/sum/sum +
 // softmax, unfused, in the reference.  Restated semantics: SURVEY.md Appendix A.4.
 //
-// Per chunk of a row (G lanes): pass 1 gathers q[col] (4 B per edge, L2-resident) and
-// reduces the chunk max; pass 2 computes w = exp(e - max) one edge per lane, then streams
-// the H-wide z rows exactly like the SpMM kernel.  The edge set {A minus self loops} +
+// Per chunk of a row (G lanes): one pass - a batch of G edges gathers q[col] (4 B per edge,
+// L2-resident), the running max is raised (online softmax: accumulator and sums rescaled when
+// it moves), w = exp(e - max) one edge per lane, then the H-wide z rows stream exactly like in
+// the SpMM kernel.  The edge set {A minus self loops} +
 // {(i,i)} is formed on the fly: existing diagonal entries are masked and the first chunk
 // of each row adds the self edge.  Heavy rows park (max, sum, acc) per chunk and a merge
 // kernel rescales them in ascending chunk order (fixed tree => launch-shape independent).
@@ -79,19 +80,15 @@ __global__ void __launch_bounds__(kGatThreads, 4) gat_chunk_kernel(const GatPara
     const bool first = (b == row_b);  // the first chunk of a row carries the self edge
     const float pi = __ldg(p.p + grow);
 
-    // pass 1: chunk max of the edge scores
-    float m = -INFINITY;
+    // ONE pass over the chunk's edges (online softmax): the running maximum m is raised G edges at a time and the
+    // accumulator, the lanes' weight sums and the self edge's weight are rescaled by exp(m_old - m_new) when it moves - a
+    // group-uniform decision, 4 multiplies per lane and batch.  (Round 1 made a first pass over colidx and q[col] for
+    // the maximum: one more index stream, one more 4-byte gather per edge and a serialised round trip before the row
+    // gathers could start.)  The sequence of maxima depends on the chunk's edges only, so the result is the same under
+    // any launch shape or row partition.
     float e_self = 0.f;
-    if (first) {
-        e_self = leaky02(pi + __ldg(p.q + grow));
-        m = e_self;
-    }
-    for (int64_t idx = b + lg; idx < e; idx += G) {
-        const int c = ld_stream_i32(p.colidx + idx);
-        if (c != grow) m = fmaxf(m, leaky02(pi + __ldg(p.q + c)));
-    }
-    m = group_max<G>(m, gmask);
-    const float w_self = first ? expf(e_self - m) : 0.f;
+    if (first) e_self = leaky02(pi + __ldg(p.q + grow));
+    float m = -INFINITY;
 
     float s_total = 0.f;
     for (int c0 = 0; c0 < p.h; c0 += G * VEC) {
@@ -102,22 +99,34 @@ __global__ void __launch_bounds__(kGatThreads, 4) gat_chunk_kernel(const GatPara
 #pragma unroll
         for (int t = 0; t < VEC; ++t) acc[t] = 0.f;
         float s_lane = 0.f;
+        float w_self = first ? 1.f : 0.f;   // exp(e_self - m) with m = e_self
+        m = first ? e_self : -INFINITY;
         if (first && col_ok) {
             if (VEC == 4) {
                 const float4 zz = ldg4(zcol + grow * p.ldz);
-                acc[0] = w_self * zz.x; acc[1 % VEC] = w_self * zz.y; acc[2 % VEC] = w_self * zz.z; acc[3 % VEC] = w_self * zz.w;
+                acc[0] = zz.x; acc[1 % VEC] = zz.y; acc[2 % VEC] = zz.z; acc[3 % VEC] = zz.w;
             } else {
-                acc[0] = w_self * __ldg(zcol + grow * p.ldz);
+                acc[0] = __ldg(zcol + grow * p.ldz);
             }
         }
         for (int64_t base = b; base < e; base += G) {
             const int64_t idx = base + lg;
             int c = 0;
-            float w = 0.f;
+            float ev = -INFINITY;
             if (idx < e) {
                 c = ld_stream_i32(p.colidx + idx);
-                if (c != grow) w = expf(leaky02(pi + __ldg(p.q + c)) - m);
+                if (c != grow) ev = leaky02(pi + __ldg(p.q + c));
             }
+            const float bm = group_max<G>(ev, gmask);
+            if (bm > m) {   // uniform over the group
+                const float sc = (m == -INFINITY) ? 0.f : expf(m - bm);
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) acc[t] *= sc;
+                s_lane *= sc;
+                w_self *= sc;
+                m = bm;
+            }
+            const float w = (ev > -INFINITY) ? expf(ev - m) : 0.f;
             s_lane += w;
             const int cnt = (e - base < G) ? (int)(e - base) : G;
 #pragma unroll
