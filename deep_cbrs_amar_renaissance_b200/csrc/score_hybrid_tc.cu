@@ -26,7 +26,8 @@ namespace cbrs {
 
 constexpr int kHyC = 64;         // width of every hidden layer after the towers (all hybrid grids of the reference)
 constexpr int kHyThreads = 128;
-constexpr int kHyTU = 16;        // users per CTA (4 passes of 4 users per item tile)
+// users per CTA = template parameter TU (TU / 4 passes of 4 users per item tile): 16, or 24 / 32 when that brings the
+// grid down to one wave of 2 CTAs per SM (6,040 users: 378 CTAs on 296 slots with 16, 252 with 24)
 constexpr int kHyTI = 32;        // items per tile
 constexpr int kHyTile = 128 * 128;   // one 128-row x 64-bf16 operand tile
 constexpr int kHyW = kHyC * 128;     // one 64 x 64 bf16 weight image
@@ -111,6 +112,7 @@ __device__ __forceinline__ void hy_store_row(unsigned char *tile, int tid, bool 
 
 constexpr int kHyQLd = kHyC + 4;   // padded row of the staged Q tile: 8 consecutive lanes hit 8 distinct 16-byte bank groups
 
+template <int TU>
 __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const HybridTcParams p) {
     extern __shared__ __align__(1024) unsigned char hy_smem[];
     const int cap = 2 * p.k + kHyTI;
@@ -118,18 +120,18 @@ __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const Hy
     unsigned char *A2 = A1 + kHyTile;
     unsigned char *Ws = A2 + kHyTile;                          // 5 weight images
     float *P1s = reinterpret_cast<float *>(Ws + 5 * kHyW);     // [TU][64]
-    float *P2s = P1s + kHyTU * kHyC;
-    float *bias = P2s + kHyTU * kHyC;                          // b3a2 | b3b2 | bc1 | bc2 | wc3  (5 x 64)
+    float *P2s = P1s + TU * kHyC;
+    float *bias = P2s + TU * kHyC;                          // b3a2 | b3b2 | bc1 | bc2 | wc3  (5 x 64)
     float *Q1s = bias + 5 * kHyC;                              // [TI][kHyQLd]: the tile's item halves, shared by all 4 users
     float *Q2s = Q1s + kHyTI * kHyQLd;
     unsigned long long *cand = reinterpret_cast<unsigned long long *>(Q2s + kHyTI * kHyQLd);   // [TU][cap]
-    unsigned long long *thr = cand + kHyTU * cap;              // [TU]
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + kHyTU);
+    unsigned long long *thr = cand + TU * cap;              // [TU]
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + TU);
     int *cnt = reinterpret_cast<int *>(mbar + 1);              // [TU]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(cnt + kHyTU);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(cnt + TU);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t u0 = (int64_t)blockIdx.x * kHyTU;
+    const int64_t u0 = (int64_t)blockIdx.x * TU;
     const float bc3 = __ldg(p.bc3);
     constexpr uint32_t kCols = 256;   // D1 | D2 | D3 | D4, 64 fp32 columns each
 
@@ -144,13 +146,13 @@ __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const Hy
         for (int e = tid; e < 5 * kHyW / 16; e += kHyThreads) dst[e] = __ldg(src + e);
         const float *bsrc[5] = {p.b3a2, p.b3b2, p.bc1, p.bc2, p.wc3};
         for (int e = tid; e < 5 * kHyC; e += kHyThreads) bias[e] = __ldg(bsrc[e / kHyC] + e % kHyC);
-        for (int e = tid; e < kHyTU * kHyC; e += kHyThreads) {
+        for (int e = tid; e < TU * kHyC; e += kHyThreads) {
             const int ul = e / kHyC, kk = e % kHyC;
             const bool ok = u0 + ul < p.n_users;
             P1s[e] = ok ? __ldg(p.P1 + (u0 + ul) * kHyC + kk) : 0.f;
             P2s[e] = ok ? __ldg(p.P2 + (u0 + ul) * kHyC + kk) : 0.f;
         }
-        if (tid < kHyTU) { cnt[tid] = 0; thr[tid] = 0ull; }
+        if (tid < TU) { cnt[tid] = 0; thr[tid] = 0ull; }
     }
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const Hy
     fetch_q(0);
 
     for (int t0 = 0; t0 < p.n_items; t0 += kHyTI) {
-        for (int ul = warp; ul < kHyTU; ul += kHyThreads / 32)   // user ul is always handled by warp ul % 4
+        for (int ul = warp; ul < TU; ul += kHyThreads / 32)   // user ul is always handled by warp ul % 4
             if (cnt[ul] > cap - kHyTI) hy_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
         const int item = t0 + lane;
         const bool item_ok = item < p.n_items;
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const Hy
         __syncthreads();
         fetch_q(t0 + kHyTI);       // next tile's rows: in flight during this tile's 4 passes
         const float *q1 = Q1s + lane * kHyQLd, *q2 = Q2s + lane * kHyQLd;
-        for (int pass = 0; pass < kHyTU / 4; ++pass) {
+        for (int pass = 0; pass < TU / 4; ++pass) {
             const int ul = pass * 4 + warp;
             const float *p1 = P1s + ul * kHyC, *p2 = P2s + ul * kHyC;
             // ---- h1, h2: first layers of dense3a / dense3b (hoisted halves added here) ----
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const Hy
         tc::tc_fence_after_sync();
         tc::tmem_dealloc(tmem_base, kCols);
     }
-    for (int ul = warp; ul < kHyTU; ul += kHyThreads / 32) {
+    for (int ul = warp; ul < TU; ul += kHyThreads / 32) {
         hy_compact(cand + ul * cap, cnt + ul, thr + ul, p.k, lane);
         const int64_t user = u0 + ul;
         if (user >= p.n_users) continue;
@@ -329,10 +331,25 @@ __global__ void __launch_bounds__(kHyThreads, 2) score_hybrid_tc_kernel(const Hy
     }
 }
 
-static size_t hy_smem_bytes(int k) {
+static size_t hy_smem_bytes(int k, int tu) {
     const int cap = 2 * k + kHyTI;
-    return 2 * (size_t)kHyTile + 5 * (size_t)kHyW + 2 * kHyTU * kHyC * 4 + 5 * kHyC * 4 + 2 * (size_t)kHyTI * kHyQLd * 4 +
-           (size_t)kHyTU * cap * 8 + kHyTU * 8 + 8 + kHyTU * 4 + 16;
+    return 2 * (size_t)kHyTile + 5 * (size_t)kHyW + 2 * tu * kHyC * 4 + 5 * kHyC * 4 + 2 * (size_t)kHyTI * kHyQLd * 4 +
+           (size_t)tu * cap * 8 + tu * 8 + 8 + tu * 4 + 16;
+}
+
+template <int TU>
+static int hy_launch(const HybridTcParams &p, cudaStream_t s) {
+    const size_t smem = hy_smem_bytes(p.k, TU);
+    CBRS_REQUIRE(smem <= 227 * 1024, CBRS_E_UNSUPPORTED, "score_hybrid_topk_bf16: needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(score_hybrid_tc_kernel<TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "score_hybrid_topk_bf16: %s", cudaGetErrorString(e));
+        configured = smem;
+    }
+    score_hybrid_tc_kernel<TU><<<(unsigned)cdiv(p.n_users, TU), kHyThreads, smem, s>>>(p);
+    CBRS_CHECK_LAUNCH("score_hybrid_topk_bf16");
+    return CBRS_OK;
 }
 
 }  // namespace cbrs
@@ -364,14 +381,11 @@ extern "C" int cbrs_score_hybrid_topk_bf16(const float *P1, const float *Q1, con
     p.w_images = (const uint8_t *)workspace;
     p.b3a2 = b3a2; p.b3b2 = b3b2; p.bc1 = bc1; p.bc2 = bc2; p.wc3 = wc3; p.bc3 = bc3;
     p.k = k; p.ids_out = ids_out; p.scores_out = scores_out;
-    const size_t smem = hy_smem_bytes(k);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(score_hybrid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        CBRS_REQUIRE(e == cudaSuccess, CBRS_E_CUDA, "score_hybrid_topk_bf16: %s", cudaGetErrorString(e));
-        configured = smem;
-    }
-    score_hybrid_tc_kernel<<<(unsigned)cdiv(n_users, kHyTU), kHyThreads, smem, s>>>(p);
-    CBRS_CHECK_LAUNCH("score_hybrid_topk_bf16");
-    return CBRS_OK;
+    // users per CTA: 16, unless 24 or 32 bring the grid down to one wave (2 CTAs per SM) - a second, part-filled wave
+    // costs as much as a full one
+    const int64_t slots = 2 * kSMs;
+    const size_t two_per_sm = (228 * 1024 - 2 * 1024) / 2;   // two CTAs (+ 1 KB reserved each) in an SM's 228 KB
+    if (cdiv(n_users, 16) > slots && cdiv(n_users, 24) <= slots && hy_smem_bytes(k, 24) <= two_per_sm) return hy_launch<24>(p, s);
+    if (cdiv(n_users, 16) > slots && cdiv(n_users, 32) <= slots && hy_smem_bytes(k, 32) <= two_per_sm) return hy_launch<32>(p, s);
+    return hy_launch<16>(p, s);
 }

@@ -44,7 +44,8 @@ def _oracle(P1, Q1, P2, Q2, w, rounded=True):
     return ol.sigmoid((h @ w["wc3"] + w["bc3"]).astype(np.float32)).reshape(len(P1), len(Q1))
 
 
-@pytest.mark.parametrize("n_users,n_items,k", [(37, 1000, 10), (5, 7, 5), (130, 333, 20), (16, 32, 3), (1, 2049, 10)])
+@pytest.mark.parametrize("n_users,n_items,k", [(37, 1000, 10), (5, 7, 5), (130, 333, 20), (16, 32, 3), (1, 2049, 10),
+                                               (4800, 40, 5)])   # 4800 users: 24 users per CTA (one wave of 2 CTAs per SM)
 def test_chained_hybrid_scorer_matches_bf16_oracle(dev, n_users, n_items, k):
     from deep_cbrs_amar_renaissance_b200 import ops
     rng = np.random.RandomState(n_users + n_items)
