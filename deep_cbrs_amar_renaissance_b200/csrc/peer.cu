@@ -141,6 +141,37 @@ extern "C" int cbrs_peer_copy(void *dst, const void *src, size_t bytes, void *st
     return CBRS_OK;
 }
 
+// Row block -> a mapped address (a peer's copy of a symmetric buffer, or its NVSwitch multicast mapping), coalesced:
+// consecutive threads write consecutive 16-byte pieces of a row, so the fabric sees full 128-byte lines.
+__global__ void push_rows_kernel(const float *__restrict__ src, int64_t lds, float *__restrict__ dst, int64_t ldd, int64_t m, int w4) {
+    const int64_t total = m * w4;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / w4;
+        const int c = (int)(e % w4) * 4;
+        *reinterpret_cast<float4 *>(dst + r * ldd + c) = *reinterpret_cast<const float4 *>(src + r * lds + c);
+    }
+}
+__global__ void push_rows_scalar_kernel(const float *__restrict__ src, int64_t lds, float *__restrict__ dst, int64_t ldd, int64_t m, int w) {
+    const int64_t total = m * w;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        dst[(e / w) * ldd + e % w] = src[(e / w) * lds + e % w];
+}
+
+extern "C" int cbrs_push_rows(const float *src, int64_t lds, void *dst, int64_t ldd, int64_t m, int32_t w, void *stream) {
+    CBRS_REQUIRE(src && dst, CBRS_E_INVALID, "push_rows: null argument");
+    CBRS_REQUIRE(m >= 0 && w > 0 && lds >= w && ldd >= w, CBRS_E_INVALID, "push_rows: bad shape");
+    if (m == 0) return CBRS_OK;
+    const bool vec = w % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src & 15u) == 0 && ((uintptr_t)dst & 15u) == 0;
+    const int64_t total = vec ? m * (w / 4) : m * (int64_t)w;
+    const unsigned grid = (unsigned)(cdiv(total, 256) < 16 * kSMs ? cdiv(total, 256) : 16 * kSMs);
+    if (vec)
+        push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, (float *)dst, ldd, m, w / 4);
+    else
+        push_rows_scalar_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, lds, (float *)dst, ldd, m, w);
+    CBRS_CHECK_LAUNCH("push_rows");
+    return CBRS_OK;
+}
+
 extern "C" int cbrs_peer_barrier(void *const *flags_peers_host, int n_ranks, int my_rank, uint64_t epoch,
                                  int32_t *status, double timeout_s, void *stream) {
     CBRS_REQUIRE(flags_peers_host && status, CBRS_E_INVALID, "peer_barrier: null argument");

@@ -596,9 +596,15 @@ class RowPartition:
                 p = self._buf(("p", l), n, 1, emb.device)
                 for a, b in self.mine:
                     zv, qv = z[a:b], q[a:b, 0]
+                    # the transform stores its rows locally; the finished block is pushed to the other ranks in one
+                    # coalesced pass (multicast when the fabric has it).  The tensor-core kernel's epilogue writes one row
+                    # per thread - 32-byte pieces of 32 different rows per instruction, which the fabric carries badly:
+                    # with 7 peers GAT ran at 54.9 G edges/s on 8 GPUs that way (profiles/r02_scale_families_n8.jsonl)
                     _, pp, _ = ops.gat_transform(x_full[a:b], layer.kernel.reshape(widths[l], layer.channels),
                                                  layer.attn_kernel_self.reshape(-1), layer.attn_kernel_neighs.reshape(-1), n,
-                                                 out=zv, q_out=qv, peers=zsb.peer_addrs(zv), q_peers=qsb.peer_addrs(qv))
+                                                 out=zv, q_out=qv)
+                    ops.push_rows(zv, zsb)
+                    ops.push_rows(q[a:b], qsb)
                     p[a:b, 0].copy_(pp)
                 heap.barrier()
                 for sl in self.csr_slices("raw", graph):
@@ -619,8 +625,9 @@ class RowPartition:
                     agg = self._buf(("agg", l, a), sl.n_rows, widths[l], emb.device)
                     ops.spmm(sl, x_full, agg, agg=L.AGG_MEAN if layer.aggregate == "mean" else L.AGG_SUM)
                     ov = out[a:b]
-                    ops.sage_dense(x_full[a:b], agg, layer.kernel, layer.bias, layer.activation, x_full.shape[0],
-                                   out=ov, peers=out_peers(ov, a))
+                    ops.sage_dense(x_full[a:b], agg, layer.kernel, layer.bias, layer.activation, x_full.shape[0], out=ov)
+                    if out_peers(ov, a) is not None:   # finished block -> every rank's copy, one coalesced pass (see GAT)
+                        ops.push_rows(ov, osb)
             else:
                 raise NotImplementedError("no partitioned form for {}".format(type(layer).__name__))
             x_full = out

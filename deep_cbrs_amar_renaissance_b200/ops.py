@@ -561,6 +561,26 @@ def gather_rows(x, idx, out=None):
     return out
 
 
+def push_rows(view, buf):
+    """Store the finished row block `view` (a view into the local copy of the SymmetricBuffer `buf`) into every rank's copy:
+    one coalesced pass to the NVSwitch multicast mapping when the buffer has one, else one per peer (cbrs_push_rows)."""
+    lib = L.load()
+    v = view if view.dim() == 2 else view.reshape(-1, 1)
+    v, ld = _rowmajor(v)
+    m, w = v.shape
+    mc = buf.mc_addr(view)
+    targets = [mc] if mc else buf.peer_addrs(view)
+    if PROFILE_ON:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    for addr in targets:
+        L.check(lib.cbrs_push_rows(_ptr(v), ld, ctypes.c_void_p(addr), ld, m, w, _stream()), "cbrs_push_rows")
+    _count(len(targets))
+    if PROFILE_ON:
+        e1.record()
+        PROFILE.append(("push", e0, e1, m * w * 4))
+
+
 def peer_copy(dst_addr, src):
     """copy-engine transfer of a contiguous tensor into a peer-mapped address (cbrs_peer_copy)"""
     if not src.is_contiguous():

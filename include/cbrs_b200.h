@@ -375,6 +375,12 @@ int cbrs_peer_close(void *ptr);
 /* copy-engine transfer into a peer-mapped buffer (no SMs): the alternative to the fused stores when the
  * producer's rows should travel while ANOTHER kernel owns the SMs */
 int cbrs_peer_copy(void *dst, const void *src, size_t bytes, void *stream);
+
+/* Coalesced copy of a row block (m rows of w floats, leading dimensions in elements) into a MAPPED address: the same view
+ * in a peer's copy of a symmetric buffer, or in the buffer's NVSwitch multicast mapping (one store reaches every copy).
+ * Used where the producing kernel's own stores would reach the fabric as scattered 32-byte pieces (the epilogues of the
+ * tensor-core Dense kernels write one row per thread): the kernel stores locally, this pushes the finished block.     */
+int cbrs_push_rows(const float *src, int64_t lds, void *dst, int64_t ldd, int64_t m, int32_t w, void *stream);
 /* flags_peers_host[r] = rank r's flag array (uint64[CBRS_MAX_PEERS], peer-mapped; own for r == my_rank) */
 int cbrs_peer_barrier(void *const *flags_peers_host, int n_ranks, int my_rank, uint64_t epoch,
                       int32_t *status, double timeout_s, void *stream);
