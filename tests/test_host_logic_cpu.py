@@ -166,3 +166,32 @@ def test_typed_edges_from_the_loader_follow_the_entry_order_of_the_reference_gra
         loaders.load_user_item_graph(*files[:2], type_adjacency="unary", relations="node-range")
     with pytest.raises(ValueError):
         edge_relations(3, raw[:, 2], "by-colour", True)
+
+
+def test_bf16_stored_sources_need_the_bf16_scorer():
+    """a source kept as bf16 (set_content_table(dtype='bf16')) can only be read by the TMA-fed tensor-core kernel: the Dense
+    layer says so before any kernel is called - there is no silent conversion and no CPU path"""
+    import torch
+    from deep_cbrs_amar_renaissance_b200 import ops
+    from deep_cbrs_amar_renaissance_b200.layers.dense import Dense, set_scorer_precision
+    layer = Dense(16, "relu")
+    table = torch.zeros(8, 64, dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="set_scorer_precision"):      # fp32 precision
+        layer.call_sources([(table, None)])
+    set_scorer_precision(layer, "bf16")
+    odd = Dense(16, "relu")
+    set_scorer_precision(odd, "bf16")
+    with pytest.raises(ValueError, match="multiples of 64"):           # a width the kernel does not take
+        odd.call_sources([(torch.zeros(8, 96, dtype=torch.bfloat16), None)])
+    with pytest.raises(ValueError, match="set_scorer_precision"):      # mixed storage of the two sources
+        layer.call_sources([(table, None), (torch.zeros(8, 64), None)])
+    assert ops.dense_tc_bf16_eligible(768, 0, 256) and ops.dense_tc_bf16_eligible(64, 64, 64)
+    assert not ops.dense_tc_bf16_eligible(96, 0, 16) and not ops.dense_tc_bf16_eligible(64, 0, 257)
+    with pytest.raises(ValueError):
+        set_scorer_precision(layer, "fp16")
+
+
+def test_nvlink_counters_degrade_to_none_without_nvml():
+    """bench.py's NVLink byte counters: None (reported as unavailable) wherever NVML cannot serve them - never an exception"""
+    import bench
+    assert bench.nvlink_counters(0) is None or len(bench.nvlink_counters(0)) == 2
